@@ -1,0 +1,203 @@
+/*
+ * rxb.h — C ABI of librxb.so: the B200 (sm_100a) hot path of the RxRx1 cellular image classifier.
+ *
+ * The reference (antoinecollas/recursion-cellular-image-classification) is pure Python and has no
+ * FFI layer; its "plugin API" for this path is five Python callables.  The entry
+ * points below are what those callables bind to (via ctypes).  Each one cites the
+ * reference code it replaces.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes only.  No torch / C++ types cross the boundary.
+ *   - return 0 on success, a negative rxb_status on failure; rxb_last_error() gives the message
+ *     (thread-local).  Nothing throws across the boundary.
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name says host; the library
+ *     never frees or retains caller memory beyond the lifetime of a plan it was bound to.
+ *   - every call takes a cudaStream_t (as void*) and is asynchronous on it.
+ *   - no hidden device allocations: workspaces are sized by *_workspace_bytes() and caller-provided.
+ *   - there is no CPU fallback: on a machine without an sm_100 device the calls fail loudly.
+ */
+#ifndef RXB_H_
+#define RXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rxb_stream_t; /* cudaStream_t */
+
+enum rxb_status {
+  RXB_OK = 0,
+  RXB_ERR_INVALID = -1,   /* bad argument */
+  RXB_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  RXB_ERR_UNSUPPORTED = -3,
+  RXB_ERR_NO_DEVICE = -4, /* no sm_100 device: there is no fallback */
+  RXB_ERR_NCCL = -5
+};
+
+int rxb_version(void);
+const char* rxb_last_error(void);
+/* 0 if cuda:current is an sm_100 part, RXB_ERR_NO_DEVICE otherwise. */
+int rxb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Family 1a — per-experiment channel statistics.
+ * Replaces the hot loop of compute_mean_std(), compute_stats_experiments.py:13-20 (count / sum(x) /
+ * sum(x^2) per channel of x = u8/255), with exact integer accumulation.
+ *   imgs    u8, layout RXB_LAYOUT_NCHW: [n, C, H, W] planar   (what dataloader.py:141-146 decodes)
+ *               layout RXB_LAYOUT_NHWC: [n, H, W, C] interleaved (what dataloader.py:129 moves to)
+ *   exp_id  i32[n], experiment slot of every image, 0 <= exp_id < n_exp
+ *   sum, sumsq, count  u64[n_exp, C], ACCUMULATED into (caller zeroes them once); count is in pixels
+ *               (compute_stats_experiments.py:21 multiplies the image count by 512*512).
+ * H*W must be a multiple of 16.
+ */
+enum rxb_layout { RXB_LAYOUT_NCHW = 0, RXB_LAYOUT_NHWC = 1 };
+int rxb_stats_accumulate(const uint8_t* imgs, const int32_t* exp_id, int64_t n, int H, int W, int C,
+                         int layout, int n_exp, unsigned long long* sum, unsigned long long* sumsq,
+                         unsigned long long* count, rxb_stream_t stream);
+/* mean/std of x/255 in f64 (compute_stats_experiments.py:22-23).  If pre_mean/pre_std (f64[n_exp,C],
+ * device) are non-NULL the statistics are those of (x/255 - pre_mean)/pre_std, i.e. the reference's
+ * verification pass (compute_stats_experiments.py:16-17, 51-57), derived from the same sums. */
+int rxb_stats_finalize(const unsigned long long* sum, const unsigned long long* sumsq,
+                       const unsigned long long* count, int n_exp, int C, const double* pre_mean,
+                       const double* pre_std, double* mean, double* std, rxb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Family 1b — fused D4 augmentation + crop + per-experiment normalisation loader.
+ * Replaces ImagesDS._transform, dataloader.py:128-139 (albumentations VerticalFlip, HorizontalFlip,
+ * rotation restricted to multiples of 90 degrees, Random/CenterCrop, Normalize) on already-decoded
+ * u8 planes, and the fp32 H2D copy of train.py:44.
+ *   src       u8 [n_src, 6, H, W] planar
+ *   src_idx   i32[B]   which source image each output image is cut from
+ *   exp_id    i32[B]   row of norm_m / norm_d to use
+ *   aug_code  u8[B]    bit0 vflip, bit1 hflip, bits2-3 k (number of 90-degree CCW turns, applied
+ *                      after the flips like dataloader.py:42-46), bit4 = reference-compatible rotation
+ *                      (the cv2.warpAffine gather about (W/2,H/2) with BORDER_REFLECT_101)
+ *   crop_yx   i32[B,2] top-left of the (Ho,Wo) crop in the augmented image (RandomCrop/CenterCrop)
+ *   norm_m    f32[n_exp,6] = f32(mean)*255 ;  norm_d f32[n_exp,6] = 1/(f32(std)*255)   (A.1)
+ *   dst       format RXB_OUT_F32_NCHW  : f32  [B,6,Ho,Wo]   = (f32(x) - m) * d, bit-exact vs numpy
+ *             format RXB_OUT_BF16_NHWC8: bf16 [B,Ho,Wo,8]   channels 6,7 = 0
+ *             format RXB_OUT_BF16_S2D32: bf16 [B,Ho/2,Wo/2,32] 2x2 space-to-depth of NHWC8
+ *                                        (channel = (y&1)*16 + (x&1)*8 + c) — the stem conv's input
+ * H and W must be equal (square, D4) and multiples of 16; Ho, Wo even for S2D32.
+ */
+enum rxb_out_format { RXB_OUT_F32_NCHW = 0, RXB_OUT_BF16_NHWC8 = 1, RXB_OUT_BF16_S2D32 = 2 };
+int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W, const int32_t* src_idx,
+                      const int32_t* exp_id, const uint8_t* aug_code, const int32_t* crop_yx,
+                      const float* norm_m, const float* norm_d, int n_exp, void* dst, int B, int Ho,
+                      int Wo, int out_format, rxb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Family 4 — test-time averaging, plate-group masking, rescale and greedy assignment.
+ * Replaces test.py:27 (softmax), :42-46 (mask + rescale) and :48-56 (greedy loop).
+ */
+/* probs[n,c] = rescale(mask(mean_v softmax(logits[v,n,:]))).  logits f32 [V,N,C].  plate i32[N];
+ * group_col i32[C] = plate_groups[:, experiment_type] (main.py:157-166).  A class is kept for row n
+ * iff group_col[c] == plate[n] (test.py:42-45).  rescale: row /= row-sum, zero rows unchanged.
+ * plate == NULL skips the mask. */
+int rxb_tta_softmax_avg_mask(const float* logits, int V, int N, int C, const int32_t* plate,
+                             const int32_t* group_col, float* probs, rxb_stream_t stream);
+/* In place on f32 probabilities that were produced elsewhere: preds[mask]=0 ; preds=rescale(preds). */
+int rxb_mask_rescale(float* preds, int N, int C, const int32_t* plate, const int32_t* group_col,
+                     rxb_stream_t stream);
+size_t rxb_greedy_assign_workspace_bytes(int N, int C);
+/* The loop of test.py:48-56, bit-exact (numpy's float32 pairwise row sums are reproduced).
+ * preds f32[N,C] is read only; result i32[N].  workspace from rxb_greedy_assign_workspace_bytes,
+ * N <= 8*SM count. */
+int rxb_greedy_assign(const float* preds, int N, int C, int32_t* result, void* workspace,
+                      rxb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Family 3 — classifier head loss.  Replaces nn.CrossEntropyLoss (train.py:37) forward + backward.
+ * logits f32 [B,C] (row stride ld), target i64[B].  loss_rows f32[B] (per-sample NLL); dlogits f32
+ * [B,C] (row stride ld) = (softmax - onehot) * grad_scale (pass 1/global_batch for the mean loss);
+ * dlogits may be NULL (eval).
+ */
+int rxb_softmax_ce(const float* logits, int ld, const int64_t* target, int B, int C, float* loss_rows,
+                   float* dlogits, float grad_scale, rxb_stream_t stream);
+
+/* SGD with momentum / nesterov / weight decay, torch.optim.SGD semantics (main.py:89-93):
+ * g = grad*grad_scale + wd*p ; m = mu*m + g ; p -= lr * (nesterov ? g + mu*m : m).
+ * (momentum buffers start at 0, which equals torch's first-step "m = g".) */
+int rxb_sgd_step(float* p, const float* grad, float* mom, int64_t n, float lr, float mu, float wd,
+                 int nesterov, float grad_scale, rxb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Family 2 — convolutions as tcgen05 implicit GEMMs (TMA-fed, TMEM accumulators).
+ * Low-level entry (used by tests and by the executor below):
+ *   out[p, c_off + n] = sum_{tap,k} A(p shifted by tap)[k] * Wt[tap][n][k]        (bf16 in, fp32 accum)
+ * with an optional per-channel affine+ReLU applied to A on the way in (pre-activation BatchNorm,
+ * torchvision densenet _DenseLayer: norm -> relu -> conv), zero padding applied AFTER it.
+ */
+typedef struct rxb_conv_desc {
+  int B, H, W;        /* output (== input, stride 1) spatial size and batch */
+  int Cin;            /* channels read per tap (multiple of 8) */
+  int ldA;            /* channel stride of the input tensor  (>= Cin; concat buffers are wider) */
+  int Cout;           /* 16..256, multiple of 16 */
+  int ldC;            /* channel stride of the output tensor */
+  int c_off;          /* first output channel (concat-by-offset) */
+  int taps_y, taps_x; /* 1x1, 3x3, 4x4 (space-to-depth stem) */
+  int pad_y, pad_x;   /* input row = y + ty - pad_y */
+  int prologue;       /* 1: A := relu(A*scale[k] + shift[k]) */
+  int stats;          /* 1: accumulate per-out-channel sum and sum of squares (of the bf16-rounded out) */
+} rxb_conv_desc;
+int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16 /*[taps][Cout][Cin]*/,
+                 const float* scale, const float* shift, void* out_bf16, float* ch_sum, float* ch_sumsq,
+                 rxb_stream_t stream);
+/* dW[tap][n][k] += sum_p dOut[p, n] * A'(p shifted by tap)[k]  (fp32 atomics into dW). */
+int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,
+                   const void* dOut_bf16, int ldD, float* dW, rxb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseNet-121 executor (6-channel stem, growth 32, blocks 6/12/24/16, 1108 classes):
+ * forward, loss, backward and the SGD update of one data-parallel rank, enqueued natively.
+ * Replaces TwoSitesNN.forward (models.py:41-57) with the north star's DenseNet-121 trunk, the
+ * train step of train.py:44 and the optimizer of main.py:89-93.
+ */
+typedef struct rxb_dn121 rxb_dn121; /* opaque */
+typedef struct rxb_dn121_config {
+  int B;            /* images per rank */
+  int H, W;         /* input size (multiple of 32) */
+  int num_classes;  /* 1108 */
+  float bn_eps;     /* 1e-5 */
+  float bn_momentum;/* 0.1 */
+} rxb_dn121_config;
+/* number of fp32 parameters and of fp32 buffer elements (running mean/var), torchvision order */
+int64_t rxb_dn121_param_count(const rxb_dn121_config* cfg);
+int64_t rxb_dn121_buffer_count(const rxb_dn121_config* cfg);
+size_t rxb_dn121_workspace_bytes(const rxb_dn121_config* cfg, int training);
+/* params/grads/momentum: fp32[param_count] flat, torchvision parameter order (features.conv0.weight,
+ * features.norm0.weight, ...), conv weights in torch OIHW layout.  buffers: fp32[buffer_count]
+ * (running_mean, running_var per BN in module order).  All device pointers, bound for the plan's life. */
+int rxb_dn121_create(const rxb_dn121_config* cfg, float* params, float* grads, float* momentum,
+                     float* buffers, void* workspace, size_t workspace_bytes, int training,
+                     rxb_dn121** out);
+void rxb_dn121_destroy(rxb_dn121* net);
+/* Re-derive the bf16 GEMM operand copies from the fp32 master parameters (after an external update). */
+int rxb_dn121_sync_weights(rxb_dn121* net, rxb_stream_t stream);
+/* input: bf16 S2D32 [B,H/2,W/2,32] from rxb_load_norm_aug.  logits_out f32 [B,num_classes] (may be
+ * NULL).  training=1 uses batch statistics and updates running stats; 0 uses running stats. */
+int rxb_dn121_forward(rxb_dn121* net, const void* input_s2d, float* logits_out, int training,
+                      rxb_stream_t stream);
+/* forward (training) + mean CE loss over `global_batch` samples + backward into grads (overwritten).
+ * loss_out: f32[1] device, sum over this rank's samples of NLL / global_batch.
+ * phase: -1 = everything; otherwise 0..rxb_dn121_num_phases()-1 runs one slice so the caller can
+ * interleave collectives: phase 0 = forward+loss+head backward, later phases walk the dense blocks
+ * backwards; after phase p the gradient range rxb_dn121_phase_grad_range(p) is final. */
+int rxb_dn121_num_phases(void);
+int rxb_dn121_phase_grad_range(const rxb_dn121* net, int phase, int64_t* begin, int64_t* end);
+int rxb_dn121_train_step(rxb_dn121* net, const void* input_s2d, const int64_t* target,
+                         int global_batch, float* loss_out, int phase, rxb_stream_t stream);
+/* p -= lr * nesterov(grad*grad_scale + wd*p) on the flat buffers, then refresh the bf16 operands. */
+int rxb_dn121_sgd(rxb_dn121* net, float lr, float mu, float wd, int nesterov, float grad_scale,
+                  rxb_stream_t stream);
+/* number of kernels the last forward/train_step/sgd call enqueued (bench.py's gpu_launches). */
+int64_t rxb_launch_count(void);
+void rxb_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXB_H_ */

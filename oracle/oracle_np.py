@@ -1,0 +1,230 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+A numpy / OpenCV / torch-fp32 restatement of the reference algorithms on the hot path.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the
+product package never does (it fails loudly when librxb.so or the GPU is missing).
+
+Parity status
+  * compute_mean_std_arrays, mask_rescale, greedy_assign: PINNED — checked against outputs of the
+    reference's own functions (compute_stats_experiments.compute_mean_std, cell_classifier.test.test)
+    run in the build container; fixtures under tests/golden/ (tests/golden/make_golden.py).
+  * d4_augment / normalize: restate albumentations==0.3.0 (requirement.txt:1), which is NOT installed
+    and has no tests in the reference -> "parity unpinned" for that third-party boundary; the OpenCV
+    calls it makes (cv2.flip, cv2.warpAffine) are executed for real here.
+  * densenet121_6ch: torchvision's densenet121 with the reference's 6-channel stem recipe
+    (models.py:17-27); the north star's trunk, fp32 on CPU.
+"""
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# S1: compute_stats_experiments.py:8-24 on decoded planes instead of files.
+def compute_mean_std_arrays(planes, mean=None, std=None):
+    """planes: uint8 [n, C, H, W].  Returns (mean, std) float64 [C].
+    Follows compute_mean_std line by line: im = u8/255 (f64); optional pre-normalisation (:16-17);
+    count/sum/sum-of-squares per channel (:18-20); mean = sum/n, std = sqrt(sumsq/n - mean^2) (:21-23)."""
+    n, C, H, W = planes.shape
+    count = np.zeros(C)
+    sum_x = np.zeros(C)
+    sum_x2 = np.zeros(C)
+    for i in range(n):
+        for ch in range(C):
+            im = planes[i, ch] / 255
+            if (mean is not None) and (std is not None):
+                im = (im - mean[ch]) / std[ch]
+            count[ch] += 1
+            sum_x[ch] += np.sum(im)
+            sum_x2[ch] += np.sum(im ** 2)
+    count = count * H * W
+    m = sum_x / count
+    s = np.sqrt((sum_x2 / count) - m ** 2)
+    return m, s
+
+
+# ------------------------------------------------------------------------------------------------
+# L3-L5: dataloader.py:42-51, 128-139 through albumentations 0.3.0 (restated).
+def d4_augment(img_hwc, vflip=False, hflip=False, k=0, ref_compat=False):
+    """VerticalFlip -> HorizontalFlip -> rotation by k*90 degrees (counter-clockwise).
+    ref_compat=False: canonical D4 (np.rot90).  ref_compat=True: what ShiftScaleRotate does at that
+    angle: cv2.warpAffine about (w/2, h/2), INTER_LINEAR, BORDER_REFLECT_101."""
+    img = img_hwc
+    if vflip:
+        img = img[::-1]          # cv2.flip(img, 0)
+    if hflip:
+        img = img[:, ::-1]       # cv2.flip(img, 1)
+    img = np.ascontiguousarray(img)
+    if ref_compat:
+        import cv2
+        h, w = img.shape[:2]
+        M = cv2.getRotationMatrix2D((w / 2, h / 2), 90.0 * k, 1.0)
+        chans = [cv2.warpAffine(np.ascontiguousarray(img[:, :, c]), M, (w, h), flags=cv2.INTER_LINEAR,
+                                borderMode=cv2.BORDER_REFLECT_101) for c in range(img.shape[2])]
+        img = np.stack(chans, axis=2)
+    else:
+        img = np.rot90(img, k)
+    return np.ascontiguousarray(img)
+
+
+def crop(img_hwc, y0, x0, h, w):
+    return img_hwc[y0:y0 + h, x0:x0 + w]
+
+
+def normalize_constants(mean, std):
+    m = np.asarray(mean, dtype=np.float32) * np.float32(255.0)
+    s = np.asarray(std, dtype=np.float32) * np.float32(255.0)
+    return m, np.reciprocal(s, dtype=np.float32)
+
+
+def normalize(img_hwc_u8, mean, std):
+    """albumentations.Normalize(mean, std, max_pixel_value=255): float32 throughout."""
+    m, d = normalize_constants(mean, std)
+    img = img_hwc_u8.astype(np.float32)
+    img -= m
+    img *= d
+    return img
+
+
+def transform(img_chw_u8, mean, std, vflip=False, hflip=False, k=0, crop_yx=(0, 0), out_hw=None,
+              ref_compat=False):
+    """ImagesDS._transform (dataloader.py:128-139) with explicit augmentation parameters.
+    Returns float32 CHW."""
+    img = np.moveaxis(img_chw_u8, 0, 2)
+    img = d4_augment(img, vflip, hflip, k, ref_compat)
+    if out_hw is not None:
+        img = crop(img, crop_yx[0], crop_yx[1], out_hw[0], out_hw[1])
+    img = normalize(img, mean, std)
+    return np.ascontiguousarray(np.moveaxis(img, 2, 0))
+
+
+def to_nhwc8_bf16(x_chw_f32):
+    """float32 [6,H,W] -> the loader's bf16 NHWC8 as float32 values (channels 6,7 zero)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(np.moveaxis(x_chw_f32, 0, 2)))
+    t = torch.cat([t, torch.zeros(*t.shape[:2], 2)], dim=2)
+    return t.to(torch.bfloat16).float().numpy()
+
+
+def to_s2d32(x_hwc8):
+    """[H,W,8] -> [H/2,W/2,32] with channel = (y&1)*16 + (x&1)*8 + c."""
+    H, W, C = x_hwc8.shape
+    t = x_hwc8.reshape(H // 2, 2, W // 2, 2, C)
+    return np.ascontiguousarray(np.transpose(t, (0, 2, 1, 3, 4)).reshape(H // 2, W // 2, 4 * C))
+
+
+# ------------------------------------------------------------------------------------------------
+# T3: test.py:27, 34-56
+def softmax(x):
+    x = x - x.max(axis=1, keepdims=True)
+    e = np.exp(x)
+    return e / e.sum(axis=1, keepdims=True)
+
+
+def rescale(preds):
+    """test.py:34-39, verbatim semantics."""
+    temp = np.sum(preds, axis=1)
+    temp[temp == 0] = 1
+    temp = np.repeat(temp[:, np.newaxis], preds.shape[1], axis=1)
+    return preds / temp
+
+
+def mask_rescale(preds, plate_groups_col, plates):
+    """test.py:42-46: zero the classes whose plate group differs from the row's plate, then rescale."""
+    preds = preds.copy()
+    mask = np.repeat(plate_groups_col[np.newaxis, :], len(preds), axis=0) != \
+        np.repeat(np.asarray(plates)[:, np.newaxis], preds.shape[1], axis=1)
+    preds[mask] = 0
+    return rescale(preds)
+
+
+def greedy_assign(preds):
+    """test.py:48-56."""
+    preds = preds.copy()
+    results = np.zeros(preds.shape[0])
+    for _ in range(preds.shape[0]):
+        max_per_row_idx = np.argmax(preds, axis=1)
+        max_row_idx = np.argmax(preds[np.arange(len(preds)), max_per_row_idx])
+        max_column_idx = max_per_row_idx[max_row_idx]
+        results[max_row_idx] = max_column_idx
+        preds[:, max_column_idx] = 0
+        preds[max_row_idx, :] = 0
+        preds = rescale(preds)
+    return results
+
+
+def pairwise_sum_f32(a):
+    """numpy's float32 pairwise summation (loops_utils.h.src *_pairwise_sum), restated so the CUDA kernel's
+    association order can be checked against np.sum itself."""
+    a = np.asarray(a, dtype=np.float32)
+    n = a.shape[0]
+    f = np.float32
+    if n < 8:
+        res = f(-0.0)
+        for i in range(n):
+            res = f(res + a[i])
+        return res
+    if n <= 128:
+        r = [f(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = f(r[j] + a[i + j])
+            i += 8
+        res = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+        while i < n:
+            res = f(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return f(pairwise_sum_f32(a[:n2]) + pairwise_sum_f32(a[n2:]))
+
+
+# ------------------------------------------------------------------------------------------------
+# M1-M3: models.py
+def two_sites_features(features, bs):
+    """models.py:46-53 given trunk features [bs*G, F] (torch): reshape to [bs, G, F], split G into the
+    image / negative-control / positive-control thirds, mean over the sites of each third, concat."""
+    import torch
+    features = features.reshape([bs, -1, features.shape[1]])
+    shape = int(features.shape[1] / 3)
+    f_img = features[:, 0:shape, :].mean(1)
+    f_neg = features[:, shape:2 * shape, :].mean(1)
+    f_pos = features[:, 2 * shape:, :].mean(1)
+    return torch.cat([f_img, f_neg, f_pos], dim=1)
+
+
+def densenet121_6ch(num_classes=1108, seed=0):
+    """torchvision densenet121 with the reference's stem surgery (models.py:17-27): a 6-channel 7x7/2
+    conv whose filters are the channel-mean of the 3-channel stem, replicated 6 times."""
+    import torch
+    import torch.nn as nn
+    from torchvision import models
+    torch.manual_seed(seed)
+    net = models.densenet121(weights=None, num_classes=num_classes)
+    trained_kernel = net.features.conv0.weight
+    new_conv = nn.Conv2d(6, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    with torch.no_grad():
+        new_conv.weight[:, :] = torch.stack([torch.mean(trained_kernel, 1)] * 6, dim=1)
+    net.features.conv0 = new_conv
+    return net
+
+
+def resnet18_6ch(num_classes=1108, seed=0):
+    """BASELINE config 1: ResNet-18-style 6-channel network with the same stem recipe."""
+    import torch
+    import torch.nn as nn
+    from torchvision import models
+    torch.manual_seed(seed)
+    net = models.resnet18(weights=None, num_classes=num_classes)
+    trained_kernel = net.conv1.weight
+    new_conv = nn.Conv2d(6, 64, kernel_size=7, stride=2, padding=3, bias=False)
+    with torch.no_grad():
+        new_conv.weight[:, :] = torch.stack([torch.mean(trained_kernel, 1)] * 6, dim=1)
+    net.conv1 = new_conv
+    return net
+
+
+def sgd_reference(params, lr, momentum=0.9, nesterov=True, weight_decay=3e-5):
+    """main.py:89-93."""
+    import torch
+    return torch.optim.SGD(params, lr=lr, momentum=momentum, nesterov=nesterov, weight_decay=weight_decay)

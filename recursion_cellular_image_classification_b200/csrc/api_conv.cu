@@ -1,0 +1,82 @@
+// api_conv.cu — C-ABI wrappers of the implicit-GEMM convolution kernels (rxb_conv_fwd / rxb_conv_wgrad).
+#include "conv_gemm.cuh"
+
+namespace rxb {
+
+int pick_bn(int n) {
+  if (n <= 256) return n;
+  return (n % 256 == 0) ? 256 : 128;
+}
+
+}  // namespace rxb
+
+extern "C" {
+
+int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16, const float* scale,
+                 const float* shift, void* out_bf16, float* ch_sum, float* ch_sumsq, rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(d && A_bf16 && W_bf16 && out_bf16, "rxb_conv_fwd: null pointer");
+  RXB_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0, "rxb_conv_fwd: bad spatial size");
+  RXB_CHECK_ARG(d->Cin > 0 && d->Cin % 8 == 0 && d->ldA >= d->Cin && d->ldA % 8 == 0, "rxb_conv_fwd: bad Cin/ldA");
+  RXB_CHECK_ARG(d->Cout >= 32 && d->Cout % 32 == 0, "rxb_conv_fwd: Cout must be a multiple of 32");
+  RXB_CHECK_ARG(d->ldC >= d->c_off + d->Cout && d->ldC % 8 == 0 && d->c_off % 8 == 0, "rxb_conv_fwd: bad ldC/c_off");
+  RXB_CHECK_ARG(d->taps_x >= 1 && d->taps_y >= 1 && d->taps_x <= 8 && d->taps_y <= 8, "rxb_conv_fwd: bad taps");
+  RXB_CHECK_ARG(!d->prologue || (scale && shift), "rxb_conv_fwd: prologue needs scale/shift");
+  RXB_CHECK_ARG(!d->stats || (ch_sum && ch_sumsq), "rxb_conv_fwd: stats needs ch_sum/ch_sumsq");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+  const int bk = d->Cin <= 32 ? 32 : 64;
+  if (d->prologue && bk != 64) return set_error(RXB_ERR_UNSUPPORTED, "rxb_conv_fwd: prologue needs Cin > 32");
+  GemmParams p = {};
+  p.t = make_tiling(d->B, d->H, d->W);
+  p.bn = pick_bn(d->Cout);
+  p.n_tiles = ceil_div(d->Cout, p.bn);
+  p.n_total = d->Cout;
+  p.taps_x = d->taps_x; p.taps_y = d->taps_y; p.pad_x = d->pad_x; p.pad_y = d->pad_y;
+  p.kb_per_tap = ceil_div(d->Cin, bk);
+  p.cin = d->Cin;
+  p.epi_mode = EPI_STORE;
+  p.out_mode = OUT_DY;
+  p.do_stats = d->stats;
+  p.out = static_cast<__nv_bfloat16*>(out_bf16);
+  p.ldc = d->ldC;
+  p.c_off = d->c_off;
+  p.ch_sum = ch_sum;
+  p.ch_sumsq = ch_sumsq;
+  p.scale = scale;
+  p.shift = shift;
+  return launch_conv_gemm(p, A_bf16, d->ldA, W_bf16, bk, d->prologue != 0, as_stream(stream));
+}
+
+int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,
+                   const void* dOut_bf16, int ldD, float* dW, rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(d && A_bf16 && dOut_bf16 && dW, "rxb_conv_wgrad: null pointer");
+  RXB_CHECK_ARG(d->Cin > 0 && d->Cin % 8 == 0 && d->ldA >= d->Cin && d->ldA % 8 == 0, "rxb_conv_wgrad: bad Cin/ldA");
+  RXB_CHECK_ARG(d->Cout == 32 || d->Cout % 64 == 0, "rxb_conv_wgrad: Cout must be 32 or a multiple of 64");
+  RXB_CHECK_ARG(ldD >= d->Cout && ldD % 8 == 0, "rxb_conv_wgrad: bad ldD");
+  RXB_CHECK_ARG(!d->prologue || (scale && shift), "rxb_conv_wgrad: prologue needs scale/shift");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+  const int n_tile = d->Cout <= 256 ? d->Cout : (d->Cout % 256 == 0 ? 256 : (d->Cout % 128 == 0 ? 128 : 64));
+  for (int n_off = 0; n_off < d->Cout; n_off += n_tile) {
+    WgradParams p = {};
+    p.t = make_tiling(d->B, d->H, d->W);
+    p.taps_x = d->taps_x; p.taps_y = d->taps_y; p.pad_x = d->pad_x; p.pad_y = d->pad_y;
+    p.cin = d->Cin;
+    p.bkc = d->Cin <= 32 ? 32 : 64;
+    p.n = n_tile;
+    p.n_off = n_off;
+    p.prologue = d->prologue;
+    p.scale = scale;
+    p.shift = shift;
+    p.dW = dW;
+    p.cout_total = d->Cout;
+    p.w_mode = 0;
+    rc = launch_conv_wgrad(p, A_bf16, d->ldA, dOut_bf16, ldD, as_stream(stream));
+    if (rc) return rc;
+  }
+  return RXB_OK;
+}
+
+}  // extern "C"

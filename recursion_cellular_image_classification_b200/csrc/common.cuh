@@ -1,0 +1,86 @@
+// common.cuh — error plumbing and small device helpers shared by every translation unit of librxb.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/rxb.h"
+
+namespace rxb {
+
+// thread-local last error message (rxb_last_error)
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+extern long long g_launches;  // kernels enqueued since the last reset (gpu_launches in bench.py)
+
+#define RXB_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return rxb::set_error(RXB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define RXB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return rxb::set_error(RXB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,         \
+                            cudaGetErrorString(e__));                                          \
+  } while (0)
+
+// after a <<<>>> launch
+#define RXB_LAUNCH_OK()                                                                        \
+  do {                                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                      \
+    if (e__ != cudaSuccess)                                                                    \
+      return rxb::set_error(RXB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,     \
+                            cudaGetErrorString(e__));                                          \
+    ++rxb::g_launches;                                                                         \
+  } while (0)
+
+inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+int num_sms();
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 16-byte load that does not pollute L1 (read-once data)
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float bf16_round(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+}  // namespace rxb

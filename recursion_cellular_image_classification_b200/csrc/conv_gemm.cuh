@@ -1,0 +1,81 @@
+// conv_gemm.cuh — parameter blocks and host launchers of the tcgen05 implicit-GEMM convolution kernels.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace rxb {
+
+// Pixel-space tiling: a GEMM M-tile is 128 pixels = tb images x th rows x tw columns (powers of two),
+// fetched by ONE 4-D TMA box (channels, x, y, image); shifting the box by a filter tap is the implicit
+// im2col, and TMA's out-of-bounds zero fill is the convolution's zero padding.
+struct PixelTiling {
+  int W, H, B;
+  int tw_log2, th_log2, tb_log2;
+  int tiles_x, tiles_y, tiles_b;
+};
+PixelTiling make_tiling(int B, int H, int W);
+
+enum EpiMode {
+  EPI_STORE = 0,     // out[p, c_off+n] = bf16(acc) ; optional per-channel sum / sum-of-squares
+  EPI_DGRAD_BN = 1,  // dy = acc * [x*es+et > 0] ; stats sum(dy), sum(dy*xhat) ; out per out_mode
+};
+enum OutMode { OUT_DY = 0, OUT_G_WRITE = 1, OUT_G_ACCUM = 2 };
+
+struct GemmParams {
+  PixelTiling t;
+  int n_tiles;      // tiles along N
+  int bn;           // N per tile (multiple of 32, <= 256)
+  int n_total;      // valid N (multiple of 32)
+  int taps_x, taps_y, pad_x, pad_y;
+  int kb_per_tap;   // k-blocks (of BK channels) per tap
+  int cin;          // valid A channels per tap
+  int epi_mode;
+  int out_mode;
+  int do_stats;
+  // EPI_STORE
+  __nv_bfloat16* out;
+  long long ldc;
+  int c_off;
+  float* ch_sum;    // [>= c_off + n_total] (EPI_STORE) or [n_total] (EPI_DGRAD_BN)
+  float* ch_sumsq;
+  // prologue (A := relu(A*scale + shift)), indexed by A channel
+  const float* scale;
+  const float* shift;
+  // EPI_DGRAD_BN: activation the BN saw, and that BN's folded parameters per N channel
+  const __nv_bfloat16* X;
+  long long ldx;
+  const float* e_scale;
+  const float* e_shift;
+  const float* e_mean;
+  const float* e_rstd;
+};
+
+// A: bf16 activation [B,H,W,ldA] (first `cin` channels used per tap); Wt: bf16 [taps][n_total][cin].
+// bk = 64 (128B swizzle) or 32 (64B swizzle).
+int launch_conv_gemm(const GemmParams& p, const void* A, long long ldA, const void* Wt, int bk, bool prologue,
+                     cudaStream_t stream);
+
+struct WgradParams {
+  PixelTiling t;
+  int taps_x, taps_y, pad_x, pad_y;
+  int cin;              // A channels per tap
+  int bkc;              // channels per A box: 64 or 32
+  int boxes_per_tap;    // ceil(cin / bkc)
+  int boxes_per_chunk;  // 128 / bkc
+  int n_chunks;         // accumulator groups (128 A-rows each) in total
+  int chunks_per_cta;   // <= 512 / n
+  int n;                // Cout (32, or a multiple of 64 up to 256)
+  int n_off;            // first dOut channel of this launch (N tiling for Cout > 256)
+  int pix_tiles_per_cta;
+  int prologue;
+  const float* scale;
+  const float* shift;
+  float* dW;            // fp32, torch OIHW [Cout_total][cin_w][taps_y_w][taps_x_w], atomically accumulated
+  int cout_total;
+  int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch)
+};
+// A: bf16 [B,H,W,ldA]; dOut: bf16 [B,H,W,ldD].
+int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* dOut, long long ldD,
+                      cudaStream_t stream);
+
+}  // namespace rxb

@@ -1,0 +1,193 @@
+"""Tensor-level wrappers over the C ABI (include/rxb.h).  Every function runs on the current CUDA
+stream of the tensors' device and raises RxbError on failure; none has a CPU path."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, load, ptr, require_gpu, stream_ptr
+
+OUT_F32_NCHW, OUT_BF16_NHWC8, OUT_BF16_S2D32 = 0, 1, 2
+AUG_VFLIP, AUG_HFLIP, AUG_REF_COMPAT = 1, 2, 16
+
+
+def aug_code(vflip=False, hflip=False, k=0, ref_compat=False):
+    """bit0 vflip, bit1 hflip, bits2-3 k quarter turns CCW, bit4 reference-compatible rotation."""
+    return (1 if vflip else 0) | (2 if hflip else 0) | ((int(k) & 3) << 2) | (16 if ref_compat else 0)
+
+
+def _cuda(t, dtype=None):
+    if not t.is_cuda:
+        raise _lib.RxbError("expected a CUDA tensor (librxb has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.RxbError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------ family 1a: statistics
+def stats_accumulate(imgs, exp_id, n_exp, acc=None):
+    """imgs u8 [n,C,H,W] planar; exp_id int32 [n].  Returns (sum, sumsq, count) int64 [n_exp, C]
+    (exact integer accumulators; pass `acc` to keep accumulating over chunks)."""
+    require_gpu()
+    imgs = _cuda(imgs, torch.uint8)
+    exp_id = _cuda(exp_id, torch.int32)
+    n, C, H, W = imgs.shape
+    if acc is None:
+        acc = tuple(torch.zeros(n_exp, C, dtype=torch.int64, device=imgs.device) for _ in range(3))
+    s, q, cnt = acc
+    check(load().rxb_stats_accumulate(ptr(imgs), ptr(exp_id), n, H, W, C, 0, n_exp, ptr(s), ptr(q), ptr(cnt),
+                                      stream_ptr()))
+    return acc
+
+
+def stats_finalize(acc, pre_mean=None, pre_std=None):
+    """(mean, std) float64 [n_exp, C] of x/255 — or of (x/255-pre_mean)/pre_std (verification mode)."""
+    require_gpu()
+    s, q, cnt = acc
+    n_exp, C = s.shape
+    mean = torch.empty(n_exp, C, dtype=torch.float64, device=s.device)
+    std = torch.empty_like(mean)
+    pm = _cuda(pre_mean, torch.float64) if pre_mean is not None else None
+    ps = _cuda(pre_std, torch.float64) if pre_std is not None else None
+    check(load().rxb_stats_finalize(ptr(s), ptr(q), ptr(cnt), n_exp, C, ptr(pm), ptr(ps), ptr(mean), ptr(std),
+                                    stream_ptr()))
+    return mean, std
+
+
+# ------------------------------------------------------------------ family 1b: loader
+def normalize_constants(mean, std):
+    """albumentations-0.3.0 Normalize constants: m = f32(mean)*255, d = 1/(f32(std)*255),
+    all float32.  mean/std: float64 [..., 6] as stored in the stats pickle."""
+    m = np.asarray(mean, dtype=np.float32) * np.float32(255.0)
+    s = np.asarray(std, dtype=np.float32) * np.float32(255.0)
+    d = np.reciprocal(s, dtype=np.float32)
+    return m.astype(np.float32), d.astype(np.float32)
+
+
+def load_norm_aug(src, src_idx, exp_id, aug, crop_yx, norm_m, norm_d, out_hw, out_format, out=None):
+    """src u8 [n,6,H,W]; src_idx/exp_id int32 [B]; aug u8 [B]; crop_yx int32 [B,2];
+    norm_m/norm_d float32 [n_exp,6].  Returns the normalised, augmented batch in `out_format`."""
+    require_gpu()
+    src = _cuda(src, torch.uint8)
+    n, C, H, W = src.shape
+    if C != 6:
+        raise _lib.RxbError("loader expects 6 channels")
+    src_idx = _cuda(src_idx, torch.int32)
+    exp_id = _cuda(exp_id, torch.int32)
+    aug = _cuda(aug, torch.uint8)
+    crop_yx = _cuda(crop_yx, torch.int32)
+    norm_m = _cuda(norm_m, torch.float32)
+    norm_d = _cuda(norm_d, torch.float32)
+    B = src_idx.numel()
+    Ho, Wo = out_hw
+    if out is None:
+        if out_format == OUT_F32_NCHW:
+            out = torch.empty(B, 6, Ho, Wo, dtype=torch.float32, device=src.device)
+        elif out_format == OUT_BF16_NHWC8:
+            out = torch.empty(B, Ho, Wo, 8, dtype=torch.bfloat16, device=src.device)
+        else:
+            out = torch.empty(B, Ho // 2, Wo // 2, 32, dtype=torch.bfloat16, device=src.device)
+    check(load().rxb_load_norm_aug(ptr(src), n, H, W, ptr(src_idx), ptr(exp_id), ptr(aug), ptr(crop_yx),
+                                   ptr(norm_m), ptr(norm_d), norm_m.shape[0], ptr(out), B, Ho, Wo, out_format,
+                                   stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------ family 4: TTA / assignment
+def tta_softmax_avg_mask(logits, plate=None, group_col=None):
+    """logits f32 [V,N,C] -> rescale(mask(mean_v softmax)) f32 [N,C]."""
+    require_gpu()
+    logits = _cuda(logits, torch.float32)
+    V, N, C = logits.shape
+    probs = torch.empty(N, C, dtype=torch.float32, device=logits.device)
+    pl = _cuda(plate, torch.int32) if plate is not None else None
+    gc = _cuda(group_col, torch.int32) if group_col is not None else None
+    check(load().rxb_tta_softmax_avg_mask(ptr(logits), V, N, C, ptr(pl), ptr(gc), ptr(probs), stream_ptr()))
+    return probs
+
+
+def mask_rescale_(preds, plate=None, group_col=None):
+    require_gpu()
+    preds = _cuda(preds, torch.float32)
+    N, C = preds.shape
+    pl = _cuda(plate, torch.int32) if plate is not None else None
+    gc = _cuda(group_col, torch.int32) if group_col is not None else None
+    check(load().rxb_mask_rescale(ptr(preds), N, C, ptr(pl), ptr(gc), stream_ptr()))
+    return preds
+
+
+def greedy_assign(preds):
+    """preds f32 [N,C] (masked + rescaled) -> int32 [N] class per row, the loop of test.py:48-56."""
+    require_gpu()
+    preds = _cuda(preds, torch.float32)
+    N, C = preds.shape
+    result = torch.zeros(N, dtype=torch.int32, device=preds.device)
+    ws = torch.empty(load().rxb_greedy_assign_workspace_bytes(N, C), dtype=torch.uint8, device=preds.device)
+    check(load().rxb_greedy_assign(ptr(preds), N, C, ptr(result), ptr(ws), stream_ptr()))
+    return result
+
+
+# ------------------------------------------------------------------ family 3: loss, optimizer
+def softmax_ce(logits, target, grad_scale=None):
+    """Returns (loss_rows f32 [B], dlogits f32 [B,C] or None)."""
+    require_gpu()
+    logits = _cuda(logits, torch.float32)
+    target = _cuda(target, torch.int64)
+    B, C = logits.shape
+    loss = torch.empty(B, dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits) if grad_scale is not None else None
+    check(load().rxb_softmax_ce(ptr(logits), C, ptr(target), B, C, ptr(loss), ptr(d),
+                                float(grad_scale if grad_scale is not None else 0.0), stream_ptr()))
+    return loss, d
+
+
+def sgd_step_(p, grad, mom, lr, momentum=0.9, weight_decay=0.0, nesterov=True, grad_scale=1.0):
+    require_gpu()
+    for t in (p, grad, mom):
+        _cuda(t, torch.float32)
+    check(load().rxb_sgd_step(ptr(p), ptr(grad), ptr(mom), p.numel(), lr, momentum, weight_decay,
+                              1 if nesterov else 0, grad_scale, stream_ptr()))
+    return p
+
+
+# ------------------------------------------------------------------ family 2: convolutions
+def _desc(B, H, W, Cin, ldA, Cout, ldC, c_off, taps, pad, prologue, stats):
+    return ConvDesc(B, H, W, Cin, ldA, Cout, ldC, c_off, taps[0], taps[1], pad[0], pad[1],
+                    1 if prologue else 0, 1 if stats else 0)
+
+
+def conv_fwd(A, Wt, Cin=None, scale=None, shift=None, out=None, c_off=0, pad=(0, 0), stats=False):
+    """A bf16 [B,H,W,ldA]; Wt bf16 [ty,tx,Cout,Cin] (tap-major).  out bf16 [B,H,W,ldC] written at
+    channels c_off..c_off+Cout.  Returns (out, ch_sum, ch_sumsq)."""
+    require_gpu()
+    A = _cuda(A, torch.bfloat16)
+    Wt = _cuda(Wt, torch.bfloat16)
+    B, H, W, ldA = A.shape
+    ty, tx, Cout, Cin_w = Wt.shape
+    Cin = Cin_w if Cin is None else Cin
+    if out is None:
+        out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=A.device)
+    ldC = out.shape[-1]
+    cs = cq = None
+    if stats:
+        cs = torch.zeros(ldC, dtype=torch.float32, device=A.device)
+        cq = torch.zeros(ldC, dtype=torch.float32, device=A.device)
+    d = _desc(B, H, W, Cin, ldA, Cout, ldC, c_off, (ty, tx), pad, scale is not None, stats)
+    check(load().rxb_conv_fwd(ctypes.byref(d), ptr(A), ptr(Wt), ptr(scale), ptr(shift), ptr(out), ptr(cs),
+                              ptr(cq), stream_ptr()))
+    return out, cs, cq
+
+
+def conv_wgrad(A, dOut, Cin, Cout, taps=(1, 1), pad=(0, 0), scale=None, shift=None):
+    """dW f32 [Cout,Cin,ty,tx] (torch OIHW) = sum_p dOut[p,n] * A'(p+tap)[k]."""
+    require_gpu()
+    A = _cuda(A, torch.bfloat16)
+    dOut = _cuda(dOut, torch.bfloat16)
+    B, H, W, ldA = A.shape
+    ldD = dOut.shape[-1]
+    dW = torch.zeros(Cout, Cin, taps[0], taps[1], dtype=torch.float32, device=A.device)
+    d = _desc(B, H, W, Cin, ldA, Cout, ldD, 0, taps, pad, scale is not None, False)
+    check(load().rxb_conv_wgrad(ctypes.byref(d), ptr(A), ptr(scale), ptr(shift), ptr(dOut), ldD, ptr(dW),
+                                stream_ptr()))
+    return dW
