@@ -121,14 +121,15 @@ extern "C" {
 int rxb_stats_accumulate(const uint8_t* imgs, const int32_t* exp_id, int64_t n, int H, int W, int C,
                          int layout, int n_exp, unsigned long long* sum, unsigned long long* sumsq,
                          unsigned long long* count, rxb_stream_t stream) {
-  RXB_CHECK_ARG(imgs && exp_id && sum && sumsq && count, "rxb_stats_accumulate: null pointer");
   RXB_CHECK_ARG(n >= 0 && H > 0 && W > 0 && C > 0 && n_exp > 0, "rxb_stats_accumulate: bad sizes");
+  RXB_CHECK_ARG(sum && sumsq && count, "rxb_stats_accumulate: null pointer");
+  if (n == 0) return RXB_OK;  // an empty chunk is a no-op (its data pointer may be null)
+  RXB_CHECK_ARG(imgs && exp_id, "rxb_stats_accumulate: null pointer");
   RXB_CHECK_ARG(((long long)H * W) % 16 == 0, "rxb_stats_accumulate: H*W must be a multiple of 16");
   RXB_CHECK_ARG((reinterpret_cast<uintptr_t>(imgs) & 15) == 0, "rxb_stats_accumulate: imgs not 16B aligned");
   if (layout != RXB_LAYOUT_NCHW)
     return rxb::set_error(RXB_ERR_UNSUPPORTED, "rxb_stats_accumulate: only planar NCHW u8 is supported");
   RXB_CHECK_ARG(n * C < (1ll << 31), "rxb_stats_accumulate: too many planes for one call");
-  if (n == 0) return RXB_OK;
   int rc = rxb_check_device();
   if (rc) return rc;
   int plane_vecs = (int)(((long long)H * W) / 16);

@@ -1,0 +1,112 @@
+"""GPU parity tests for the tcgen05 implicit-GEMM convolution kernels against torch fp32 on the same
+bf16-rounded operands (tolerance: bf16 output rounding, 2e-2 relative per the north star)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from recursion_cellular_image_classification_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_bf16(shape, gen, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).to(torch.bfloat16)
+
+
+def _ref_conv(A_nhwc, W_oihw, pad, scale=None, shift=None):
+    x = A_nhwc.float().permute(0, 3, 1, 2)
+    if scale is not None:
+        x = torch.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+        x = x.to(torch.bfloat16).float()     # the kernel feeds the MMA bf16
+    return F.conv2d(x, W_oihw.float(), padding=pad).permute(0, 2, 3, 1)
+
+
+def _tap_major(W_oihw):
+    return W_oihw.permute(2, 3, 0, 1).contiguous()   # [ty,tx,Cout,Cin]
+
+
+CASES = [
+    # B, H, W, Cin, ldA, Cout, k, prologue
+    (2, 16, 16, 64, 64, 128, 1, False),
+    (2, 16, 16, 64, 64, 128, 1, True),
+    (3, 8, 8, 96, 256, 128, 1, True),       # Cin not a multiple of 64, A is a slice of a wider concat buffer
+    (2, 16, 16, 128, 128, 32, 3, True),      # dense-layer 3x3
+    (1, 32, 32, 128, 128, 32, 3, False),
+    (5, 4, 4, 256, 256, 128, 1, True),       # several images per 128-pixel tile
+    (2, 12, 20, 160, 192, 128, 1, True),     # non power-of-two spatial size
+    (2, 12, 20, 128, 128, 32, 3, True),
+    (1, 16, 16, 512, 512, 256, 1, False),    # transition-like, N = 256
+    (1, 16, 16, 32, 32, 64, 4, False),       # space-to-depth stem: 4x4 taps, 32 channels per tap
+    (2, 128, 128, 128, 128, 32, 3, True),    # block-1 geometry (tile = one 128-pixel row)
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,ldA,Cout,k,prologue", CASES)
+def test_conv_fwd_matches_torch(cuda, B, H, W, Cin, ldA, Cout, k, prologue):
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin + k)
+    A = _rand_bf16((B, H, W, ldA), gen)
+    Wt = _rand_bf16((Cout, Cin, k, k), gen, scale=(Cin * k * k) ** -0.5)
+    scale = shift = None
+    if prologue:
+        scale = torch.rand(Cin, generator=gen) + 0.5
+        shift = torch.randn(Cin, generator=gen) * 0.3
+    pad = {1: 0, 3: 1, 4: 2}[k]
+    # the 4x4 stem reads rows y+ty-2: torch's symmetric padding 2 gives one extra row/col at the end
+    ref = _ref_conv(A[..., :Cin], Wt, pad, scale, shift)[:, :H, :W]
+    ldC, c_off = Cout + 64, 32
+    out = torch.full((B, H, W, ldC), 7.0, dtype=torch.bfloat16, device=cuda)
+    out, cs, cq = ops.conv_fwd(A.to(cuda), _tap_major(Wt).to(cuda), Cin=Cin,
+                               scale=None if scale is None else scale.to(cuda),
+                               shift=None if shift is None else shift.to(cuda), out=out, c_off=c_off, pad=(pad, pad),
+                               stats=True)
+    torch.cuda.synchronize()
+    got = out[..., c_off:c_off + Cout].float().cpu()
+    err = (got - ref).abs().max().item()
+    ref_mag = ref.abs().max().item()
+    assert err <= 2e-2 * ref_mag, "max err %g vs magnitude %g" % (err, ref_mag)
+    # channels outside [c_off, c_off+Cout) untouched (concat-by-offset)
+    assert torch.all(out[..., :c_off].float() == 7.0) and torch.all(out[..., c_off + Cout:].float() == 7.0)
+    # BatchNorm statistics of the bf16-rounded output
+    g64 = got.double().reshape(-1, Cout)
+    np.testing.assert_allclose(cs[c_off:c_off + Cout].cpu().numpy(), g64.sum(0).numpy(), rtol=2e-3,
+                               atol=2e-3 * g64.abs().sum(0).max().item())
+    np.testing.assert_allclose(cq[c_off:c_off + Cout].cpu().numpy(), (g64 ** 2).sum(0).numpy(), rtol=2e-3)
+
+
+WG_CASES = [
+    # B, H, W, Cin, ldA, Cout, k, prologue
+    (2, 16, 16, 64, 64, 128, 1, False),
+    (2, 16, 16, 96, 256, 128, 1, True),
+    (2, 16, 16, 128, 128, 32, 3, True),
+    (4, 8, 8, 640, 1024, 128, 1, True),      # 5 accumulator groups -> two chunk groups
+    (2, 12, 20, 128, 128, 32, 3, False),
+    (1, 16, 16, 256, 256, 256, 1, False),    # transition-like
+    (1, 16, 16, 32, 32, 64, 4, False),       # stem-like: 32-channel boxes, 4 taps per accumulator group
+    (2, 64, 64, 128, 128, 32, 3, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,ldA,Cout,k,prologue", WG_CASES)
+def test_conv_wgrad_matches_torch(cuda, B, H, W, Cin, ldA, Cout, k, prologue):
+    gen = torch.Generator().manual_seed(B * 77 + H + Cin + k)
+    A = _rand_bf16((B, H, W, ldA), gen)
+    dOut = _rand_bf16((B, H, W, Cout), gen)
+    scale = shift = None
+    if prologue:
+        scale = torch.rand(Cin, generator=gen) + 0.5
+        shift = torch.randn(Cin, generator=gen) * 0.3
+    pad = {1: 0, 3: 1, 4: 2}[k]
+    x = A[..., :Cin].float().permute(0, 3, 1, 2)
+    if prologue:
+        x = torch.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    x = x.double().requires_grad_(False)
+    w = torch.zeros(Cout, Cin, k, k, dtype=torch.double, requires_grad=True)
+    y = F.conv2d(x, w, padding=pad)[:, :, :H, :W]
+    y.backward(dOut.double().permute(0, 3, 1, 2))
+    ref = w.grad.float()
+    got = ops.conv_wgrad(A.to(cuda), dOut.to(cuda), Cin, Cout, taps=(k, k), pad=(pad, pad),
+                         scale=None if scale is None else scale.to(cuda),
+                         shift=None if shift is None else shift.to(cuda)).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, "max err %g vs %g" % (err, ref.abs().max().item())
