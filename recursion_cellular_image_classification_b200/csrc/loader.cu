@@ -8,9 +8,10 @@
 //
 // HBM-bound: 6 B read + 12 B (16 B with the two pad channels) written per pixel.
 // One CTA produces a 64x64 output tile.  The D4 image of that tile is a 64x64 source square, fetched
-// for all 6 planes by ONE TMA box load (u8, 64B-swizzled so the transposing maps read shared memory
-// with at most 4-way bank conflicts); threads then gather bytes through the affine index map and emit
-// one coalesced 16-byte store per pixel.  Reference-compatible rotations (the cv2.warpAffine gather
+// for all 6 planes by ONE TMA box load (u8; the box is 80 bytes wide because TMA needs the box start
+// 16-byte aligned in the innermost dimension while crops start at any x; the 80-byte pitch also keeps
+// the transposing maps at 4-way shared-memory bank conflicts); threads then gather bytes through the
+// affine index map and emit one coalesced 16-byte store per pixel.  Reference-compatible rotations (the cv2.warpAffine gather
 // with BORDER_REFLECT_101, not affine at the border) take a plain global-gather path.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -20,6 +21,7 @@ namespace rxb {
 constexpr int kLdTile = 64;
 constexpr int kLdThreads = 256;
 constexpr int kLdPlanes = 6;
+constexpr int kLdPitch = kLdTile + 16;  // box width: 64 + slack for 16-byte alignment of the box start
 
 // (cy,cx): coordinates in the augmented SxS image -> (sy,sx) in the source image.
 __device__ __forceinline__ void d4_source_coord(int code, int S, int cy, int cx, int& sy, int& sx) {
@@ -81,7 +83,7 @@ __device__ __forceinline__ void emit_pixel(const LoaderArgs& a, int b, int oy, i
 
 __global__ void __launch_bounds__(kLdThreads)
 loader_kernel(const __grid_constant__ CUtensorMap tmap_src, const LoaderArgs a) {
-  __shared__ __align__(1024) uint8_t tile[kLdPlanes * kLdTile * kLdTile];  // 24 KB, 64B-swizzled rows
+  __shared__ __align__(128) uint8_t tile[kLdPlanes * kLdTile * kLdPitch];  // 30 KB: [plane][row][80]
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_m[kLdPlanes], s_d[kLdPlanes];
 
@@ -110,13 +112,14 @@ loader_kernel(const __grid_constant__ CUtensorMap tmap_src, const LoaderArgs a) 
   const int dyx = sy01 - sy00, dxx = sx01 - sx00;  // d(source)/d(dx)
   const int sy_min = sy00 + min(0, (kLdTile - 1) * dyy) + min(0, (kLdTile - 1) * dyx);
   const int sx_min = sx00 + min(0, (kLdTile - 1) * dxy) + min(0, (kLdTile - 1) * dxx);
+  const int sx_al = (sx_min >> 4) << 4;  // floor to a multiple of 16 (arithmetic shift: works for negatives)
 
   if (!compat) {
     if (threadIdx.x == 0) {
       ptx::mbar_init(&bar, 1);
       ptx::fence_barrier_init();
-      ptx::mbar_arrive_expect_tx(&bar, kLdPlanes * kLdTile * kLdTile);
-      ptx::tma_load_3d(tile, &tmap_src, &bar, sx_min, sy_min, img * kLdPlanes);
+      ptx::mbar_arrive_expect_tx(&bar, kLdPlanes * kLdTile * kLdPitch);
+      ptx::tma_load_3d(tile, &tmap_src, &bar, sx_al, sy_min, img * kLdPlanes);
     }
   }
   __syncthreads();
@@ -138,12 +141,11 @@ loader_kernel(const __grid_constant__ CUtensorMap tmap_src, const LoaderArgs a) 
     float v[kLdPlanes];
     if (!compat) {
       const int ly = sy00 + dy * dyy + dx * dyx - sy_min;
-      const int lx = sx00 + dy * dxy + dx * dxx - sx_min;
-      // 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3
-      const int phys = ly * kLdTile + ((((lx >> 4) ^ (ly >> 1)) & 3) << 4) + (lx & 15);
+      const int lx = sx00 + dy * dxy + dx * dxx - sx_al;
+      const int phys = ly * kLdPitch + lx;
 #pragma unroll
       for (int c = 0; c < kLdPlanes; ++c) {
-        float x = (float)tile[c * kLdTile * kLdTile + phys];
+        float x = (float)tile[c * kLdTile * kLdPitch + phys];
         v[c] = __fmul_rn(__fsub_rn(x, m[c]), d[c]);
       }
     } else {
@@ -186,9 +188,9 @@ extern "C" int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W
   CUtensorMap tm;
   uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)n_src * 6};
   uint64_t strides[2] = {(uint64_t)W, (uint64_t)W * H};
-  uint32_t box[3] = {kLdTile, kLdTile, kLdPlanes};
+  uint32_t box[3] = {kLdPitch, kLdTile, kLdPlanes};
   rc = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(src), dims, strides, box,
-                 CU_TENSOR_MAP_SWIZZLE_64B);
+                 CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
 
   LoaderArgs a;

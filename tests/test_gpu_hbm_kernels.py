@@ -144,8 +144,9 @@ def test_assign_matches_reference_golden_1108(cuda, golden_dir):
                            torch.from_numpy(pg[:, int(g["et1108"])].astype(np.int32)).to(cuda))
     res = ops.greedy_assign(pr).cpu().numpy()
     np.testing.assert_array_equal(res, g["res1108"].astype(np.int32))
-    # one class per well and one well per class inside each plate group (size-independent property)
-    assert len(set(res.tolist())) == N
+    # size-independent property: a class is never handed to two wells (class 0 is also the "no pick" value)
+    picked = res[res != 0]
+    assert len(set(picked.tolist())) == len(picked)
 
 
 @pytest.mark.parametrize("N,C", [(1, 8), (5, 7), (37, 300), (200, 1108)])
