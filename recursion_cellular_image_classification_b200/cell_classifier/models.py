@@ -1,0 +1,265 @@
+"""Model surface of the hot path (mirrors reference cell_classifier/models.py).
+
+`DenseNet121` is the north star's trunk: torchvision's densenet121 with the reference's 6-channel stem
+(models.py:17-27), executed by the native librxb executor (csrc/densenet.cu) — tcgen05 implicit-GEMM
+convolutions, fused BatchNorm/ReLU/concat, native backward and SGD.  Parameters live in ONE flat fp32
+tensor in torchvision's named_parameters() order; `state_dict()` / `load_state_dict()` speak torchvision's
+names so checkpoints interchange with `torchvision.models.densenet121`.
+
+`TwoSitesNN` keeps the reference's constructor and call signature (models.py:8-12, 41):
+x[B, G, 6, H, W] -> [B, nb_classes]; the G images of a sample are averaged in feature space (models.py:46-50),
+which for DenseNet's linear classifier equals averaging the logits.  `DummyClassifier` is the reference's
+fake backend (models.py:60-68).
+"""
+import ctypes
+import math
+from collections import OrderedDict
+
+import torch
+
+from .. import _lib, ops
+from .._lib import Dn121Config, check, load, ptr, stream_ptr
+
+_BLOCKS = (6, 12, 24, 16)
+
+
+def densenet121_param_specs(nb_classes=1108):
+    """[(torchvision name, shape)] in named_parameters() order, and the BN buffer list in module order."""
+    specs, bufs = [], []
+
+    def bn(prefix, c):
+        specs.append((prefix + ".weight", (c,)))
+        specs.append((prefix + ".bias", (c,)))
+        bufs.append((prefix + ".running_mean", (c,)))
+        bufs.append((prefix + ".running_var", (c,)))
+
+    specs.append(("features.conv0.weight", (64, 6, 7, 7)))
+    bn("features.norm0", 64)
+    c = 64
+    for b, n_layers in enumerate(_BLOCKS, 1):
+        for i in range(1, n_layers + 1):
+            p = "features.denseblock%d.denselayer%d" % (b, i)
+            bn(p + ".norm1", c)
+            specs.append((p + ".conv1.weight", (128, c, 1, 1)))
+            bn(p + ".norm2", 128)
+            specs.append((p + ".conv2.weight", (32, 128, 3, 3)))
+            c += 32
+        if b < 4:
+            p = "features.transition%d" % b
+            bn(p + ".norm", c)
+            specs.append((p + ".conv.weight", (c // 2, c, 1, 1)))
+            c //= 2
+    bn("features.norm5", c)
+    specs.append(("classifier.weight", (nb_classes, c)))
+    specs.append(("classifier.bias", (nb_classes,)))
+    return specs, bufs
+
+
+def to_s2d32(x_nchw):
+    """f32/bf16 [B,6,H,W] (already normalised) -> bf16 [B,H/2,W/2,32], the stem conv's input layout
+    (channel = (y&1)*16 + (x&1)*8 + c).  Compatibility path only: the fused loader writes this directly."""
+    B, C, H, W = x_nchw.shape
+    x = torch.zeros(B, H, W, 8, dtype=torch.bfloat16, device=x_nchw.device)
+    x[..., :C] = x_nchw.permute(0, 2, 3, 1)
+    x = x.view(B, H // 2, 2, W // 2, 2, 8).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 32)
+    return x.contiguous()
+
+
+class DenseNet121(torch.nn.Module):
+    def __init__(self, nb_classes=1108, device="cuda", bn_eps=1e-5, bn_momentum=0.1, seed=None):
+        super().__init__()
+        self.nb_classes = nb_classes
+        self.bn_eps, self.bn_momentum = bn_eps, bn_momentum
+        self.specs, self.buf_specs = densenet121_param_specs(nb_classes)
+        n = sum(math.prod(s) for _, s in self.specs)
+        nb = sum(math.prod(s) for _, s in self.buf_specs)
+        dev = torch.device(device)
+        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32, device=dev))
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.register_buffer("momentum_buf", torch.zeros(n, dtype=torch.float32, device=dev))
+        self.register_buffer("bn_buffers", torch.zeros(nb, dtype=torch.float32, device=dev))
+        self._plans = {}
+        self._views = OrderedDict()
+        off = 0
+        for name, shape in self.specs:
+            k = math.prod(shape)
+            self._views[name] = (off, k, shape)
+            off += k
+        self._bviews = OrderedDict()
+        off = 0
+        for name, shape in self.buf_specs:
+            k = math.prod(shape)
+            self._bviews[name] = (off, k, shape)
+            off += k
+        self.reset_parameters(seed)
+
+    # ---------------------------------------------------------------- parameters
+    def view(self, name):
+        off, k, shape = self._views[name]
+        return self.flat.data[off:off + k].view(shape)
+
+    def grad_view(self, name):
+        off, k, shape = self._views[name]
+        return self.flat.grad[off:off + k].view(shape)
+
+    def buffer_view(self, name):
+        off, k, shape = self._bviews[name]
+        return self.bn_buffers[off:off + k].view(shape)
+
+    def reset_parameters(self, seed=None):
+        """torchvision densenet init: kaiming_normal conv, BN weight 1 / bias 0, classifier bias 0; the stem is
+        the channel-mean of a 3-channel kaiming stem replicated 6x (reference models.py:24-26)."""
+        g = torch.Generator().manual_seed(0 if seed is None else seed)
+        with torch.no_grad():
+            for name, shape in self.specs:
+                v = self.view(name)
+                if name == "features.conv0.weight":
+                    w3 = torch.empty(64, 3, 7, 7)
+                    torch.nn.init.kaiming_normal_(w3, generator=g)
+                    v.copy_(w3.mean(1, keepdim=True).expand(64, 6, 7, 7))
+                elif name.endswith("conv.weight") or "conv1.weight" in name or "conv2.weight" in name:
+                    w = torch.empty(shape)
+                    torch.nn.init.kaiming_normal_(w, generator=g)
+                    v.copy_(w)
+                elif name == "classifier.weight":
+                    w = torch.empty(shape)
+                    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5), generator=g)
+                    v.copy_(w)
+                elif name.endswith(".weight"):
+                    v.fill_(1.0)
+                else:
+                    v.zero_()
+            for name, _ in self.buf_specs:
+                self.buffer_view(name).fill_(1.0 if name.endswith("running_var") else 0.0)
+        self._weights_dirty = True
+
+    def state_dict(self, *args, **kwargs):
+        sd = OrderedDict()
+        for name in self._views:
+            sd[name] = self.view(name).clone()
+        for name in self._bviews:
+            sd[name] = self.buffer_view(name).clone()
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        with torch.no_grad():
+            for name in self._views:
+                key = name if name in sd else "module." + name   # DataParallel-prefixed checkpoints (train.py:96)
+                if key in sd:
+                    self.view(name).copy_(sd[key])
+                elif strict:
+                    raise KeyError(name)
+            for name in self._bviews:
+                key = name if name in sd else "module." + name
+                if key in sd:
+                    self.buffer_view(name).copy_(sd[key])
+                elif strict:
+                    raise KeyError(name)
+        self._weights_dirty = True
+
+    # ---------------------------------------------------------------- plans
+    def _plan(self, B, H, W, training):
+        key = (B, H, W, bool(training))
+        if key in self._plans:
+            return self._plans[key]
+        _lib.require_gpu()
+        lib = load()
+        cfg = Dn121Config(B, H, W, self.nb_classes, self.bn_eps, self.bn_momentum)
+        assert lib.rxb_dn121_param_count(ctypes.byref(cfg)) == self.flat.numel()
+        assert lib.rxb_dn121_buffer_count(ctypes.byref(cfg)) == self.bn_buffers.numel()
+        nbytes = lib.rxb_dn121_workspace_bytes(ctypes.byref(cfg), 1 if training else 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+        handle = ctypes.c_void_p()
+        check(lib.rxb_dn121_create(ctypes.byref(cfg), ptr(self.flat.data), ptr(self.flat.grad), ptr(self.momentum_buf),
+                                   ptr(self.bn_buffers), ptr(ws), nbytes, 1 if training else 0, ctypes.byref(handle)))
+        plan = {"handle": handle, "ws": ws, "cfg": cfg, "synced": False}
+        self._plans[key] = plan
+        return plan
+
+    def _sync(self, plan):
+        if self._weights_dirty:
+            for p in self._plans.values():
+                p["synced"] = False
+            self._weights_dirty = False
+        if not plan["synced"]:
+            check(load().rxb_dn121_sync_weights(plan["handle"], stream_ptr()))
+            plan["synced"] = True
+
+    def __del__(self):
+        try:
+            lib = load()
+            for p in self._plans.values():
+                lib.rxb_dn121_destroy(p["handle"])
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- compute
+    def _as_s2d(self, x):
+        if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == 32:
+            return x.contiguous()
+        return to_s2d32(x.to(self.flat.device))
+
+    def forward(self, x):
+        """x: bf16 S2D32 [B,H/2,W/2,32] (fused-loader output) or float [B,6,H,W] / [B,G,6,H,W]."""
+        groups = None
+        if x.dim() == 5:
+            groups = x.shape[1]
+            x = x.reshape(-1, *x.shape[2:])
+        xs = self._as_s2d(x)
+        B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
+        plan = self._plan(B, H, W, False)
+        self._sync(plan)
+        logits = torch.empty(B, self.nb_classes, dtype=torch.float32, device=xs.device)
+        check(load().rxb_dn121_forward(plan["handle"], ptr(xs), ptr(logits), 1 if self.training else 0, stream_ptr()))
+        if groups is not None:
+            logits = logits.view(-1, groups, self.nb_classes).mean(1)
+        return logits
+
+    def train_step(self, xs, target, global_batch=None, phase=-1, loss_out=None):
+        """forward + CrossEntropy(mean over global_batch) + backward into self.flat.grad.  Returns the
+        device scalar holding this rank's share of the loss."""
+        xs = self._as_s2d(xs)
+        B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
+        plan = self._plan(B, H, W, True)
+        self._sync(plan)
+        if loss_out is None:
+            loss_out = torch.empty(1, dtype=torch.float32, device=xs.device)
+        check(load().rxb_dn121_train_step(plan["handle"], ptr(xs), ptr(target.contiguous()), global_batch or B,
+                                          ptr(loss_out), phase, stream_ptr()))
+        return loss_out
+
+    def phase_grad_range(self, B, H, W, phase):
+        plan = self._plan(B, H, W, True)
+        b, e = ctypes.c_int64(), ctypes.c_int64()
+        check(load().rxb_dn121_phase_grad_range(plan["handle"], phase, ctypes.byref(b), ctypes.byref(e)))
+        return b.value, e.value
+
+    def sgd_step(self, B, H, W, lr, momentum=0.9, weight_decay=3e-5, nesterov=True, grad_scale=1.0):
+        """torch.optim.SGD semantics (main.py:89-93) on the flat buffers, then refresh the bf16 operands."""
+        plan = self._plan(B, H, W, True)
+        check(load().rxb_dn121_sgd(plan["handle"], lr, momentum, weight_decay, 1 if nesterov else 0, grad_scale,
+                                   stream_ptr()))
+        for p in self._plans.values():
+            p["synced"] = p is plan
+
+
+class TwoSitesNN(DenseNet121):
+    """Reference constructor signature (models.py:8-12); DenseNet-121 trunk per the north star."""
+
+    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device="cuda"):
+        if pretrained:
+            raise _lib.RxbError("pretrained ImageNet weights need network access; load a state_dict instead")
+        super().__init__(nb_classes=nb_classes, device=device)
+
+
+class DummyClassifier():
+    """models.py:60-68: uniform random 'logits' in [-1, 1)."""
+
+    def __init__(self, nb_classes):
+        self.nb_classes = nb_classes
+
+    def __call__(self, x):
+        bs = x.shape[0]
+        output = torch.zeros((bs, self.nb_classes))
+        output = output.random_(-10000, 10000) / 10000
+        return output
