@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json).
+
+Metric: 6x512x512 DenseNet-121 bf16 TRAIN images/s on N B200s (config[1]/[2]); one "step" = one pass of the
+hot path over one batch per GPU: fused D4-augment + per-experiment normalise loader (u8 -> bf16 S2D) ->
+DenseNet-121 forward -> CrossEntropy -> backward -> (NCCL gradient all-reduce over NVLink for N>1) -> nesterov SGD.
+
+  python bench.py --gpus N --steps K --warmup W          our arm (launched under torchrun for N>1)
+  python bench.py --impl reference ...                   the reference path on the host CPUs (oracle port)
+
+One JSON line on stdout from rank 0 (see the contract in the task description): value (inputs resident in HBM),
+e2e (host u8 batch in pinned memory -> H2D -> step -> D2H of the loss), roofline (conv implicit-GEMM family),
+hbm_kernels (stats / loader GB/s against the measured HBM peak), cpu_baseline, clocks, gpu_launches.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "densenet121_6x512x512_bf16_train_images_per_sec"
+UNIT = "images/s"
+IMG = 512
+NUM_CLASSES = 1108
+FLOP_FWD_BWD_PER_IMG = 90.05e9     # SURVEY §A.3 (torchvision op order), 2*MAC
+STATS_BYTES_PER_IMG = 6 * IMG * IMG            # 1,572,864
+LOADER_BYTES_PER_IMG = 3 * 6 * IMG * IMG       # 1 B read + 2 B bf16 written per element = 4,718,592
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.samples.append([f.strip() for f in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax = max(smax, float(s[1]))
+                for i, nme in enumerate(names):
+                    if s[3 + i].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference path on the host CPUs: oracle normalise+augment (numpy/OpenCV restatement of
+    dataloader.py:128-139) + torchvision DenseNet-121 (6-ch stem) fp32 forward/backward + SGD (main.py:89-93),
+    all host threads, on a bounded sample of the same workload (batch `--ref-batch` of 6x512x512)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_np as O
+    from recursion_cellular_image_classification_b200.synth import synth_planes
+    torch.manual_seed(0)
+    cores = torch.get_num_threads()
+    B = args.ref_batch
+    net = O.densenet121_6ch(NUM_CLASSES, seed=0)
+    net.train()
+    opt = O.sgd_reference(net.parameters(), lr=0.0005 * B)
+    lossf = torch.nn.CrossEntropyLoss()
+    planes = synth_planes(3, n=B)
+    mean = np.full(6, 0.1)
+    std = np.full(6, 0.08)
+    rng = np.random.default_rng(0)
+    y = torch.from_numpy(rng.integers(0, NUM_CLASSES, size=B))
+
+    def step():
+        xs = [O.transform(planes[i], mean, std, vflip=bool(rng.integers(2)), hflip=bool(rng.integers(2)),
+                          k=int(rng.integers(4)), crop_yx=(0, 0), out_hw=(IMG, IMG)) for i in range(B)]
+        x = torch.from_numpy(np.stack(xs))
+        opt.zero_grad()
+        loss = lossf(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    steps, warmup = min(args.steps, args.ref_max_steps), min(args.warmup, 1)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * steps / dt
+    sample = "batch %d x 6x512x512, %d timed steps after %d warm-up, torch fp32 CPU + numpy loader" % (B, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DenseNet-121 6x512x512 train step incl. normalise+D4 loader, CPU oracle port",
+                       "batch": B},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def cpu_baseline(seconds_budget=25.0):
+    """Oracle port of the same train step on the host cores: bounded sample (batch 2, as many steps as fit)."""
+    from oracle import oracle_np as O
+    torch.manual_seed(0)
+    B = 2
+    net = O.densenet121_6ch(NUM_CLASSES, seed=0)
+    net.train()
+    opt = O.sgd_reference(net.parameters(), lr=0.001)
+    lossf = torch.nn.CrossEntropyLoss()
+    x = torch.randn(B, 6, IMG, IMG)
+    y = torch.randint(0, NUM_CLASSES, (B,))
+
+    def step():
+        opt.zero_grad()
+        lossf(net(x), y).backward()
+        opt.step()
+
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 1 or (time.perf_counter() - t0 < seconds_budget and n < 8):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "torchvision densenet121 (6-ch stem) fp32 fwd+bwd+SGD, batch %d x 6x512x512, %d steps after 1 "
+                      "warm-up (model only, no loader)" % (B, n)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from recursion_cellular_image_classification_b200 import _lib, ops
+    from recursion_cellular_image_classification_b200.cell_classifier.models import DenseNet121
+    from recursion_cellular_image_classification_b200.synth import synth_planes_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_gpu()
+    lib = _lib.load()
+    peaks = measured_peaks()
+
+    B = args.batch
+    gB = B * world
+    lr = 0.0005 * gB                                   # main.py:71
+    n_exp = 4
+    torch.manual_seed(1234 + rank)
+    src = synth_planes_torch(rank, B, dev)             # u8 [B,6,512,512] resident in HBM
+    host_src = torch.empty(src.shape, dtype=torch.uint8, pin_memory=True)
+    host_src.copy_(src)
+    src_idx = torch.arange(B, dtype=torch.int32, device=dev)
+    exp_id = (torch.arange(B, device=dev) % n_exp).to(torch.int32)
+    crop = torch.zeros(B, 2, dtype=torch.int32, device=dev)
+    labels = torch.randint(0, NUM_CLASSES, (B,), device=dev)
+    # per-experiment statistics through our own stats kernel (family 1a)
+    acc = ops.stats_accumulate(src, exp_id, n_exp)
+    mean, std = ops.stats_finalize(acc)
+    m, d = ops.normalize_constants(mean.cpu().numpy(), std.cpu().numpy())
+    norm_m, norm_d = torch.from_numpy(m).to(dev), torch.from_numpy(d).to(dev)
+
+    net = DenseNet121(nb_classes=NUM_CLASSES, device=dev, seed=0)
+    net.train()
+    xs = torch.empty(B, IMG // 2, IMG // 2, 32, dtype=torch.bfloat16, device=dev)
+    loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+    host_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank)
+    n_phases = lib.rxb_dn121_num_phases()
+    ranges = [net.phase_grad_range(B, IMG, IMG, ph) for ph in range(n_phases)]
+
+    def step(from_host):
+        if from_host:
+            src.copy_(host_src, non_blocking=True)                       # H2D of this step's u8 batch
+        aug = torch.randint(0, 16, (B,), device=dev, generator=gen, dtype=torch.uint8)   # D4 code per image
+        ops.load_norm_aug(src, src_idx, exp_id, aug, crop, norm_m, norm_d, (IMG, IMG), ops.OUT_BF16_S2D32, out=xs)
+        works = []
+        for ph in range(n_phases):
+            net.train_step(xs, labels, global_batch=gB, phase=ph, loss_out=loss_dev)
+            if world > 1:
+                b, e = ranges[ph]
+                works.append(dist.all_reduce(net.flat.grad[b:e], async_op=True))   # overlaps the next phase
+        for w in works:
+            w.wait()
+        net.sgd_step(B, IMG, IMG, lr=lr, momentum=0.9, weight_decay=3e-5, nesterov=True)
+        if from_host:
+            host_loss.copy_(loss_dev, non_blocking=True)                 # D2H of the step's result
+
+    def timed(from_host, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    loss_first = loss_dev.item()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.rxb_launch_count_reset()
+    ms = timed(False, args.steps)
+    launches = lib.rxb_launch_count()
+    clocks = sampler.finish() if rank == 0 else None
+    value = gB * args.steps / (ms * 1e-3)
+
+    for _ in range(2):
+        step(True)
+    ms_e2e = timed(True, args.steps)
+    e2e_value = gB * args.steps / (ms_e2e * 1e-3)
+    loss_last = host_loss.item()
+
+    # ---- kernel-family breakdown (event-bracketed launches, separate untimed pass) and HBM kernels
+    breakdown, roofline, hbm_kernels = None, None, None
+    if rank == 0:
+        ncat = 9
+        msb = (ctypes.c_float * ncat)()
+        cnt = (ctypes.c_int64 * ncat)()
+        prof_steps = 2
+        torch.cuda.synchronize()
+        lib.rxb_profile_enable(1)
+        for _ in range(prof_steps):
+            step(False)
+        _lib.check(lib.rxb_profile_collect(msb, cnt, ncat))
+        lib.rxb_profile_enable(0)
+        names = ["stats", "loader", "conv_fwd", "conv_dgrad", "conv_wgrad", "elementwise", "head", "optimizer", "tta"]
+        breakdown = {nme: {"ms_per_step": msb[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps}
+                     for i, nme in enumerate(names)}
+        conv_ms = sum(breakdown[k]["ms_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
+        conv_launches = sum(breakdown[k]["launches_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
+        achieved_tf = FLOP_FWD_BWD_PER_IMG * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roofline = {"kernel": "conv_gemm_kernel + conv_wgrad_kernel (tcgen05 implicit GEMM family)",
+                    "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                    "peak_source": peaks["source"] + " sustained cuBLAS bf16",
+                    "algorithmic_flops_per_step": FLOP_FWD_BWD_PER_IMG * B, "launches_per_step": conv_launches,
+                    "avg_launch_ms": conv_ms / max(conv_launches, 1), "traffic": None,
+                    "note": "the stride-1 DenseNet convs at bf16 have 64-230 FLOP/B arithmetic intensity, below the "
+                            "B200 ridge (~217 FLOP/B): they are HBM-bound; see DESIGN.md"}
+        # HBM-bound families, timed alone on >L2 inputs
+        def time_kernel(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / reps
+        nbig = max(B, 128)
+        big = synth_planes_torch(7, nbig, dev) if nbig != B else src
+        big_exp = (torch.arange(nbig, device=dev) % n_exp).to(torch.int32)
+        acc2 = tuple(torch.zeros(n_exp, 6, dtype=torch.int64, device=dev) for _ in range(3))
+        t_stats = time_kernel(lambda: ops.stats_accumulate(big, big_exp, n_exp, acc2))
+        big_idx = torch.arange(nbig, dtype=torch.int32, device=dev)
+        big_crop = torch.zeros(nbig, 2, dtype=torch.int32, device=dev)
+        big_aug = torch.randint(0, 16, (nbig,), device=dev, dtype=torch.uint8)
+        big_out = torch.empty(nbig, IMG // 2, IMG // 2, 32, dtype=torch.bfloat16, device=dev)
+        t_load = time_kernel(lambda: ops.load_norm_aug(big, big_idx, big_exp, big_aug, big_crop, norm_m, norm_d,
+                                                       (IMG, IMG), ops.OUT_BF16_S2D32, out=big_out))
+        def hb(bytes_per_img, t_ms):
+            ach = bytes_per_img * nbig / (t_ms * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "images": nbig, "ms": t_ms, "peak_source": peaks["source"] + " copy"}
+        hbm_kernels = {"stats_planar_kernel": hb(STATS_BYTES_PER_IMG, t_stats),
+                       "loader_kernel": hb(LOADER_BYTES_PER_IMG, t_load)}
+        del big_out
+
+    if rank == 0:
+        cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "DenseNet-121 6-channel 512x512 bf16 training step: fused normalise+D4 loader, "
+                                       "fwd, CE, bwd, %snesterov SGD" % ("NCCL grad all-reduce, " if world > 1 else ""),
+                           "batch_per_gpu": B, "global_batch": gB, "num_classes": NUM_CLASSES,
+                           "parallelism": "dp%d" % world, "l2": "inputs and activations exceed the 126 MB L2",
+                           "lr": lr},
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(host_src.numel()) * world, "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": roofline, "hbm_kernels": hbm_kernels, "kernel_breakdown": breakdown,
+                "cpu_baseline": cpu,
+                "loss": {"after_warmup": loss_first, "last": loss_last}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=4)
+    ap.add_argument("--ref-max-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

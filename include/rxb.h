@@ -196,6 +196,12 @@ int rxb_dn121_sgd(rxb_dn121* net, float lr, float mu, float wd, int nesterov, fl
 /* number of kernels the last forward/train_step/sgd call enqueued (bench.py's gpu_launches). */
 int64_t rxb_launch_count(void);
 void rxb_launch_count_reset(void);
+/* Per-kernel-family timing for bench.py: while enabled every launch is bracketed by CUDA events on its
+ * stream.  rxb_profile_collect synchronises, writes milliseconds and launch counts per category
+ * (0 stats, 1 loader, 2 conv fwd, 3 conv dgrad, 4 conv wgrad, 5 elementwise, 6 head, 7 optimizer+repack,
+ * 8 TTA/assignment; ncat >= 9) and clears the record. */
+void rxb_profile_enable(int on);
+int rxb_profile_collect(float* ms, long long* launches, int ncat);
 
 #ifdef __cplusplus
 }

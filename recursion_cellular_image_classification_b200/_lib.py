@@ -71,6 +71,8 @@ SIGNATURES = {
     "rxb_dn121_sgd": (c_int, [c_void_p, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     "rxb_launch_count": (c_int64, []),
     "rxb_launch_count_reset": (None, []),
+    "rxb_profile_enable": (None, [c_int]),
+    "rxb_profile_collect": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int64), c_int]),
 }
 
 _lib = None

@@ -1,4 +1,5 @@
 // common.cu — error state, device check, launch counter.
+#include <vector>
 #include "common.cuh"
 
 namespace rxb {
@@ -14,6 +15,25 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(t_err, sizeof(t_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool g_prof_on = false;
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; };
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(cudaStream_t s, int cat) : st(s), slot(-1) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.cat = cat;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
 }
 
 int num_sms() {
@@ -46,6 +66,24 @@ int rxb_check_device(void) {
     return rxb::set_error(RXB_ERR_NO_DEVICE,
                           "device %d is sm_%d%d; librxb is built for sm_100a only (no fallback)", dev,
                           major, minor);
+  return RXB_OK;
+}
+
+void rxb_profile_enable(int on) { rxb::g_prof_on = on != 0; }
+
+// Sums the recorded launches per category (ms and count), then clears the record.  Synchronises the device.
+int rxb_profile_collect(float* ms, long long* launches, int ncat) {
+  if (!ms || !launches || ncat < rxb::PROF_NCAT) return rxb::set_error(RXB_ERR_INVALID, "rxb_profile_collect: need %d slots", (int)rxb::PROF_NCAT);
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return rxb::set_error(RXB_ERR_CUDA, "rxb_profile_collect: %s", cudaGetErrorString(e));
+  for (auto& r : rxb::g_prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cat] += t; launches[r.cat] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  rxb::g_prof.clear();
   return RXB_OK;
 }
 

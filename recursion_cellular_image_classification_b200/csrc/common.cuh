@@ -37,6 +37,19 @@ extern long long g_launches;  // kernels enqueued since the last reset (gpu_laun
     ++rxb::g_launches;                                                                         \
   } while (0)
 
+// Optional per-launch timing (bench.py's kernel-family breakdown): when enabled, every launcher brackets its
+// kernel with CUDA events on the launching stream; rxb_profile_collect sums them per category.
+enum ProfCat { PROF_STATS = 0, PROF_LOADER, PROF_CONV_FWD, PROF_CONV_DGRAD, PROF_CONV_WGRAD, PROF_ELEMENTWISE,
+               PROF_HEAD, PROF_OPTIM, PROF_TTA, PROF_NCAT };
+extern bool g_prof_on;
+struct ProfScope {
+  cudaStream_t st;
+  int slot;
+  ProfScope(cudaStream_t s, int cat);
+  ~ProfScope();
+};
+#define RXB_PROF(stream, cat) rxb::ProfScope prof_scope__((stream), (cat))
+
 inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int num_sms();
 

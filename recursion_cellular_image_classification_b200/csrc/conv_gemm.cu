@@ -625,6 +625,7 @@ int launch_conv_gemm(const GemmParams& p, const void* A, long long ldA, const vo
   if (grid > total_tiles) grid = total_tiles;
   if (grid <= 0) return RXB_OK;
 
+  RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
 #define RXB_LAUNCH_GEMM(BK_, PRO_)                                                                             \
   do {                                                                                                         \
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
@@ -674,6 +675,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_wgrad: tile too large for shared memory");
   const size_t smem = (size_t)stages * (kWgA_BYTES + b_bytes) + sizeof(WgradAux) + 1024;
   RXB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RXB_PROF(stream, PROF_CONV_WGRAD);
   conv_wgrad_kernel<<<dim3(pix_ctas, chunk_groups), kGemmThreads, smem, stream>>>(tmA, tmD, p, stages);
   RXB_LAUNCH_OK();
   return RXB_OK;

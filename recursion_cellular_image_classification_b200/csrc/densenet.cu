@@ -358,10 +358,9 @@ static int forward(rxb_dn121& n, const void* input, int training, cudaStream_t s
                      n.S0, 64, 0, stats ? n.s0sum : nullptr, stats ? n.s0sq : nullptr, st));
   RXB_TRY(prep(n, n.bn0, n.s0sum, n.s0sq, (float)((long long)c.B * n.Hs * n.Ws), training, st));
   Block& b0 = n.blocks[0];
-  if (n.pool_idx == nullptr && training) return set_error(RXB_ERR_INVALID, "dn121: plan was created for inference");
   {
-    // inference plans have no index buffer: reuse the (unused) dlogits-sized scratch is not possible, so the
-    // kernel always writes indices; an inference plan points them at the head of block 1's Y scratch.
+    // plans created for inference have no index buffer (no backward): park the indices in block 1's
+    // bottleneck scratch, which is not live until the first dense layer runs.
     uint8_t* idx = n.pool_idx ? n.pool_idx : reinterpret_cast<uint8_t*>(b0.layers[0].Y);
     RXB_TRY(stem_bn_relu_maxpool(n.S0, c.B, n.Hs, n.Ws, n.bn0.fold.scale, n.bn0.fold.shift, b0.X, b0.Ctot, idx,
                                  b0.xsum, b0.xsq, st));

@@ -81,6 +81,7 @@ __global__ void bn_prep_kernel(const float* __restrict__ sum, const float* __res
 int bn_prep(const float* sum, const float* sumsq, float count, const float* gamma, const float* beta,
             float* running_mean, float* running_var, float eps, float momentum, int training, int C, BnFold f,
             cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   bn_prep_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sum, sumsq, count, gamma, beta, running_mean, running_var, eps,
                                                   momentum, training, C, f);
   RXB_LAUNCH_OK();
@@ -145,6 +146,7 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
 
 int stem_bn_relu_maxpool(const __nv_bfloat16* S0, int B, int Hs, int Ws, const float* scale, const float* shift,
                          __nv_bfloat16* out, int ld_out, uint8_t* idx, float* sum, float* sumsq, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   const long long total = (long long)B * (Hs / 2) * (Ws / 2);
   stem_bn_relu_maxpool_kernel<<<ew_grid(total, 32), kEwThreads, 0, st>>>(S0, B, Hs, Ws, scale, shift, out, ld_out,
                                                                         idx, sum, sumsq);
@@ -191,6 +193,7 @@ transition_pool_fwd_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int B, 
 
 int transition_pool_fwd(const __nv_bfloat16* X, int ldx, int B, int H, int W, int C, const float* scale,
                         const float* shift, __nv_bfloat16* P, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
   transition_pool_fwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, st>>>(X, ldx, B, H, W, C, scale, shift, P);
   RXB_LAUNCH_OK();
@@ -223,6 +226,7 @@ final_bn_relu_gap_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int B, in
 
 int final_bn_relu_gap(const __nv_bfloat16* X, int ldx, int B, int HW, int C, const float* scale,
                       const float* shift, float* feat, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   const int total = B * (C / 8);
   final_bn_relu_gap_kernel<<<ceil_div(total, 128), 128, 0, st>>>(X, ldx, B, HW, C, scale, shift, feat);
   RXB_LAUNCH_OK();
@@ -282,6 +286,7 @@ bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* 
 
 int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int ldx, int B, int H, int W, int C,
                      BnFold f, __nv_bfloat16* G, float* dsum, float* dsq, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   const int groups = C / 8;
   if (groups > kEwThreads || kEwThreads % groups) return set_error(RXB_ERR_INVALID, "bn_relu_bwd_to_G: C=%d", C);
   const int ppi = kEwThreads / groups;
@@ -317,6 +322,7 @@ __global__ void bn_bwd_finalize_kernel(int mode, float* __restrict__ dsum, float
 
 int bn_bwd_finalize(int mode, float* dsum, float* dsq, const float* scale, float count, int C, float* dgamma,
                     float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mode, dsum, dsq, scale, count, C, dgamma, dbeta, corrA,
                                                           corrB);
   RXB_LAUNCH_OK();
@@ -349,6 +355,7 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
                  const float* m2, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), kEwThreads * 2), kEwThreads, 0, st>>>(dy, X, M, C, f, m1, m2);
   RXB_LAUNCH_OK();
   return RXB_OK;
@@ -382,6 +389,7 @@ grad_fixup_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __re
 int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long M, int c0, int nch,
                const float* mean, const float* rstd, const float* corrA, const float* corrB, __nv_bfloat16* dst,
                cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   grad_fixup_kernel<<<ew_grid(M * (nch / 8), kEwThreads * 2), kEwThreads, 0, st>>>(G, X, ld, M, c0, nch, mean, rstd,
                                                                                  corrA, corrB, dst);
   RXB_LAUNCH_OK();
@@ -449,6 +457,7 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
 
 int stem_pool_bwd(const __nv_bfloat16* dPool, const uint8_t* idx, const __nv_bfloat16* S0, int B, int Hs, int Ws,
                   BnFold f, __nv_bfloat16* dy0, float* dsum, float* dsq, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   stem_pool_bwd_kernel<<<ew_grid((long long)B * Hs * Ws, 32 * 4), kEwThreads, 0, st>>>(dPool, idx, S0, B, Hs, Ws, f,
                                                                                       dy0, dsum, dsq);
   RXB_LAUNCH_OK();
@@ -495,6 +504,7 @@ sgemm_strided_kernel(int M, int N, int K, const float* __restrict__ A, long long
 
 int sgemm_strided(int M, int N, int K, const float* A, long long a_i, long long a_l, const float* Bm, long long b_l,
                   long long b_j, const float* bias, float* C, long long c_i, long long c_j, cudaStream_t st) {
+  RXB_PROF(st, PROF_HEAD);
   dim3 grid(ceil_div(N, 32), ceil_div(M, 32));
   sgemm_strided_kernel<<<grid, 256, 0, st>>>(M, N, K, A, a_i, a_l, Bm, b_l, b_j, bias, C, c_i, c_j);
   RXB_LAUNCH_OK();
@@ -510,6 +520,7 @@ __global__ void column_sum_kernel(const float* __restrict__ A, int rows, int col
   out[j] = s;
 }
 int column_sum(const float* A, int rows, int cols, long long ld, float* out, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   column_sum_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(A, rows, cols, ld, out);
   RXB_LAUNCH_OK();
   return RXB_OK;
@@ -529,6 +540,7 @@ __global__ void sum_scale_kernel(const float* __restrict__ v, int n, float scale
   }
 }
 int sum_scale(const float* v, int n, float scale, float* out, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
   sum_scale_kernel<<<1, 256, 0, st>>>(v, n, scale, out);
   RXB_LAUNCH_OK();
   return RXB_OK;
@@ -585,6 +597,7 @@ repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ aren
 
 int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* jobs_dev, int n_jobs,
                    long long max_elems, cudaStream_t st) {
+  RXB_PROF(st, PROF_OPTIM);
   int gx = (int)ceil_div<long long>(max_elems, 256 * 8);
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;

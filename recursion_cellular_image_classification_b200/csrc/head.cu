@@ -83,6 +83,7 @@ int rxb_softmax_ce(const float* logits, int ld, const int64_t* target, int B, in
   if (B == 0) return RXB_OK;
   int rc = rxb_check_device();
   if (rc) return rc;
+  RXB_PROF(as_stream(stream), PROF_HEAD);
   softmax_ce_kernel<<<B, kCeThreads, 0, as_stream(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target),
                                                              C, loss_rows, dlogits, grad_scale);
   RXB_LAUNCH_OK();
@@ -100,6 +101,7 @@ int rxb_sgd_step(float* p, const float* grad, float* mom, int64_t n, float lr, f
   long long blocks = ceil_div<long long>(n, 256);
   long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
+  RXB_PROF(as_stream(stream), PROF_OPTIM);
   sgd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, grad, mom, n, lr, mu, wd, nesterov, grad_scale);
   RXB_LAUNCH_OK();
   return RXB_OK;

@@ -200,6 +200,7 @@ extern "C" int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W
   a.tiles_x = ceil_div(Wo, kLdTile);
   a.tiles_y = ceil_div(Ho, kLdTile);
   dim3 grid(a.tiles_x * a.tiles_y, B);
+  RXB_PROF(as_stream(stream), PROF_LOADER);
   loader_kernel<<<grid, kLdThreads, 0, as_stream(stream)>>>(tm, a);
   RXB_LAUNCH_OK();
   return RXB_OK;

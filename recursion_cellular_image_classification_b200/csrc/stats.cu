@@ -133,6 +133,7 @@ int rxb_stats_accumulate(const uint8_t* imgs, const int32_t* exp_id, int64_t n, 
   int rc = rxb_check_device();
   if (rc) return rc;
   int plane_vecs = (int)(((long long)H * W) / 16);
+  RXB_PROF(rxb::as_stream(stream), rxb::PROF_STATS);
   rxb::stats_planar_kernel<<<(unsigned)(n * C), rxb::kStatsThreads, 0, rxb::as_stream(stream)>>>(
       reinterpret_cast<const uint4*>(imgs), exp_id, C, plane_vecs, n_exp, sum, sumsq, count);
   RXB_LAUNCH_OK();
@@ -147,6 +148,7 @@ int rxb_stats_finalize(const unsigned long long* sum, const unsigned long long* 
   int rc = rxb_check_device();
   if (rc) return rc;
   int total = n_exp * C;
+  RXB_PROF(rxb::as_stream(stream), rxb::PROF_STATS);
   rxb::stats_finalize_kernel<<<rxb::ceil_div(total, 128), 128, 0, rxb::as_stream(stream)>>>(
       sum, sumsq, count, total, pre_mean, pre_std, mean, std);
   RXB_LAUNCH_OK();

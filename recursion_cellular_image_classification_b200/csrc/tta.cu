@@ -352,6 +352,7 @@ int rxb_tta_softmax_avg_mask(const float* logits, int V, int N, int C, const int
   PairwisePlan plan;
   if (make_plan(plan, C)) return set_error(RXB_ERR_INVALID, "row length %d unsupported", C);
   size_t smem = (size_t)(C + kMaxLeaves) * sizeof(float);
+  RXB_PROF(as_stream(stream), PROF_TTA);
   tta_softmax_avg_mask_kernel<<<N, kTtaThreads, smem, as_stream(stream)>>>(logits, V, N, plate, group_col,
                                                                              probs, plan, 1);
   RXB_LAUNCH_OK();
@@ -370,6 +371,7 @@ int rxb_mask_rescale(float* preds, int N, int C, const int32_t* plate, const int
   PairwisePlan plan;
   if (make_plan(plan, C)) return set_error(RXB_ERR_INVALID, "row length %d unsupported", C);
   size_t smem = (size_t)(C + kMaxLeaves) * sizeof(float);
+  RXB_PROF(as_stream(stream), PROF_TTA);
   tta_softmax_avg_mask_kernel<<<N, kTtaThreads, smem, as_stream(stream)>>>(nullptr, 1, N, plate, group_col,
                                                                              preds, plan, 0);
   RXB_LAUNCH_OK();
@@ -404,6 +406,7 @@ int rxb_greedy_assign(const float* preds, int N, int C, int32_t* result, void* w
   RXB_CUDA(cudaFuncSetAttribute(greedy_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   Cand* cand = reinterpret_cast<Cand*>(workspace);
   void* args[] = {(void*)&preds, (void*)&N, (void*)&rows_per_cta, (void*)&result, (void*)&cand, (void*)&plan};
+  RXB_PROF(as_stream(stream), PROF_TTA);
   RXB_CUDA(cudaLaunchCooperativeKernel((void*)greedy_assign_kernel, dim3(grid), dim3(kGreedyThreads), args, smem,
                                        as_stream(stream)));
   ++g_launches;
