@@ -250,7 +250,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm):
         step(False)
     torch.cuda.synchronize()
     loss_first = loss_dev.item()
@@ -264,6 +265,14 @@ def run_ours(args):
     launches = lib.rxb_launch_count()
     clocks = sampler.finish() if rank == 0 else None
     value = gB * args.steps / (ms * 1e-3)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": n_warm, "ms_per_step": ms / args.steps, "quick": True,
+                              "gpu_launches": int(launches)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     for _ in range(2):
         step(True)
@@ -332,7 +341,7 @@ def run_ours(args):
     if rank == 0:
         cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "DenseNet-121 6-channel 512x512 bf16 training step: fused normalise+D4 loader, "
                                        "fwd, CE, bwd, %snesterov SGD" % ("NCCL grad all-reduce, " if world > 1 else ""),
@@ -361,6 +370,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid (ncu): exactly --warmup + --steps steps, no e2e / breakdown / cpu baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
