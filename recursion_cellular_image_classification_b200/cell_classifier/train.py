@@ -1,0 +1,113 @@
+"""Training loop of the hot path — mirrors reference cell_classifier/train.py:18-141 without ignite.
+
+`train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_workers, device, debug)` keeps the
+reference signature and side effects: per batch zero_grad/forward/CrossEntropy/backward/step (train.py:37,44),
+an evaluation before the first epoch and after every epoch with Loss and Accuracy (:39-42,82-102), the best
+validation accuracy's state_dict saved to models/best_model_<id>.pth with DataParallel's `module.` key prefix
+(:88-96, main.py:147), cosine annealing per epoch with eta_min = lr/100 (:104-112) and optional early stopping
+(:74-80).  TensorBoard/progress-bar handlers (:114-139) are out of scope.
+
+The step itself runs natively: workers decode JPEGs, the u8 batch goes to the GPU, the fused loader normalises
+and augments it into the stem conv's layout, the DenseNet-121 executor does forward / loss / backward, gradients
+are all-reduced over NCCL in phases when several ranks train, and the fused nesterov-SGD kernel updates the flat
+parameter buffer.  `optimizer` is read for its hyper-parameters (lr, momentum, nesterov, weight_decay).
+"""
+import math
+import os
+
+import torch
+
+from .. import ops, parallel
+from .dataloader import RawView, collate_raw
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def cosine_lr(lr0, epoch, nb_epochs):
+    """torch CosineAnnealingLR(T_max=nb_epochs, eta_min=lr0/100) evaluated after `epoch` scheduler steps."""
+    eta_min = lr0 / 100
+    return eta_min + (lr0 - eta_min) * (1 + math.cos(math.pi * epoch / nb_epochs)) / 2
+
+
+def evaluate(model, ds, bs, num_workers, device):
+    """Loss and Accuracy over a dataset (train.py:39-42) in eval mode; returns (accuracy, mean loss)."""
+    net = _unwrap(model)
+    was_training = net.training
+    net.eval()
+    loader = torch.utils.data.DataLoader(RawView(ds), batch_size=bs, shuffle=False, num_workers=num_workers,
+                                         collate_fn=collate_raw)
+    correct, total, loss_sum = 0, 0, 0.0
+    dev = torch.device(device)
+    for batch in loader:
+        xs = ds.device_batch(batch, dev, first_only=True)
+        y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
+        logits = net(xs)
+        loss_rows, _ = ops.softmax_ce(logits, y)
+        loss_sum += loss_rows.sum().item()
+        correct += (logits.argmax(1) == y).sum().item()
+        total += y.numel()
+    net.train(was_training)
+    return (correct / max(total, 1)), (loss_sum / max(total, 1))
+
+
+def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_workers, device, debug=False):
+    net = _unwrap(model)
+    dev = torch.device(device)
+    rank, _, world = parallel.init_from_env()
+    bs = hyperparams['bs'] // world if world > 1 else hyperparams['bs']      # hyperparams['bs'] is the global batch
+    group = optimizer.param_groups[0]
+    lr0 = hyperparams.get('lr', group['lr'])
+    momentum, nesterov, wd = group.get('momentum', 0.0), group.get('nesterov', False), group.get('weight_decay', 0.0)
+    nb_epochs = hyperparams['nb_epochs']
+    crop = hyperparams.get('crop', 512)
+    ds_train.crop = ds_val.crop = crop
+
+    sampler = None
+    if world > 1:
+        sampler = torch.utils.data.distributed.DistributedSampler(ds_train, num_replicas=world, rank=rank, shuffle=True)
+    loader = torch.utils.data.DataLoader(RawView(ds_train), batch_size=bs, shuffle=sampler is None, sampler=sampler,
+                                         num_workers=num_workers, collate_fn=collate_raw, drop_last=world > 1)
+    net.train()
+    best_acc, best_epoch, history = -1.0, 0, []
+    loss_dev = torch.zeros(1, device=dev)
+    n_phases = None
+
+    def validate(epoch):
+        nonlocal best_acc, best_epoch
+        acc, loss = evaluate(model, ds_val, bs, num_workers, device)
+        history.append({"epoch": epoch, "val_acc": acc, "val_loss": loss})
+        if rank == 0:
+            print("Validation Results - Epoch: {}  Average accuracy: {:.4f} Average loss: {:.4f}".format(epoch, acc, loss))
+        if acc > best_acc:                                                    # train.py:88-96
+            best_acc, best_epoch = acc, epoch
+            if rank == 0:
+                os.makedirs('models', exist_ok=True)
+                sd = {"module." + k: v.cpu() for k, v in net.state_dict().items()}
+                torch.save(sd, 'models/best_model_' + experiment_id + '.pth')
+        return acc
+
+    validate(0)                                                               # Events.STARTED evaluation (train.py:82)
+    for epoch in range(1, nb_epochs + 1):
+        lr = cosine_lr(lr0, epoch - 1, nb_epochs) if hyperparams.get('scheduler', True) else lr0
+        if sampler is not None:
+            sampler.set_epoch(epoch)
+        for batch in loader:
+            xs = ds_train.device_batch(batch, dev, first_only=True)
+            y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
+            B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
+            if n_phases is None:
+                from .._lib import load
+                n_phases = load().rxb_dn121_num_phases()
+            ranges = [net.phase_grad_range(B, H, W, p) for p in range(n_phases)]
+            ar = parallel.PhasedGradAllReduce(net.flat.grad, ranges)
+            for p in range(n_phases):
+                net.train_step(xs, y, global_batch=B * world, phase=p, loss_out=loss_dev)
+                ar.after_phase(p)
+            ar.wait()
+            net.sgd_step(B, H, W, lr=lr, momentum=momentum, weight_decay=wd, nesterov=nesterov)
+        validate(epoch)
+        if hyperparams.get('early_stopping', False) and epoch - best_epoch >= hyperparams.get('patience', 10):
+            break
+    return history

@@ -1,0 +1,95 @@
+"""CPU tests of the multi-rank host logic over the gloo backend (world_size 2): sharding, the exact-integer
+statistics all-reduce, the phased gradient all-reduce and the test-time row gather."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from recursion_cellular_image_classification_b200 import parallel
+from recursion_cellular_image_classification_b200.cell_classifier.train import cosine_lr
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    r, _, w = parallel.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    # 1. statistics: each rank reduces its shard of "images"; the int64 accumulators are summed exactly
+    rng = np.random.default_rng(0)
+    planes = rng.integers(0, 256, size=(10, 6, 8, 8)).astype(np.int64)
+    b, e = parallel.shard_range(10, rank, world)
+    acc = (torch.from_numpy(planes[b:e].sum(axis=(0, 2, 3))[None]), torch.from_numpy((planes[b:e] ** 2).sum(axis=(0, 2, 3))[None]),
+           torch.full((1, 6), (e - b) * 64, dtype=torch.int64))
+    acc = parallel.allreduce_stats(acc)
+    ok_stats = bool((acc[0][0].numpy() == planes.sum(axis=(0, 2, 3))).all() and
+                    (acc[1][0].numpy() == (planes ** 2).sum(axis=(0, 2, 3))).all() and int(acc[2][0, 0]) == 640)
+    # 2. phased gradient all-reduce: the flat buffer ends up as the sum over ranks, slice by slice
+    g = torch.arange(100, dtype=torch.float32) * (rank + 1)
+    ranges = [(80, 100), (50, 80), (20, 50), (0, 20), (0, 0)]
+    ar = parallel.PhasedGradAllReduce(g, ranges)
+    for p in range(len(ranges)):
+        ar.after_phase(p)
+    ar.wait()
+    ok_grad = bool(torch.equal(g, torch.arange(100, dtype=torch.float32) * sum(range(1, world + 1))))
+    # 3. test-time gather of per-rank probability rows (ragged shards)
+    counts = [parallel.shard_range(7, r_, world)[1] - parallel.shard_range(7, r_, world)[0] for r_ in range(world)]
+    b, e = parallel.shard_range(7, rank, world)
+    rows = torch.arange(7 * 3, dtype=torch.float32).view(7, 3)
+    got = parallel.allgather_rows(rows[b:e].clone(), counts)
+    ok_gather = bool(torch.equal(got, rows))
+    q.put((rank, ok_stats, ok_grad, ok_gather))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_host_logic():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, a, b, c in res:
+        assert a and b and c, (rank, a, b, c)
+
+
+def test_shard_range_covers_everything_without_overlap():
+    for n in (0, 1, 7, 51, 1108):
+        for world in (1, 2, 4, 8):
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b >= a
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_batch_and_lr_scaling_follow_main_py():
+    assert parallel.scaled_hyperparams(16, 8) == (128, 0.0005 * 128)      # main.py:67,71
+    assert parallel.scaled_hyperparams(16, 1, lr=0.1) == (16, 0.1)
+
+
+def test_cosine_schedule_matches_torch():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=0.008)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=20, eta_min=0.008 / 100)   # train.py:105-109
+    for epoch in range(20):
+        assert abs(opt.param_groups[0]["lr"] - cosine_lr(0.008, epoch, 20)) < 1e-12
+        opt.step()
+        sched.step()
