@@ -146,6 +146,16 @@ typedef struct rxb_conv_desc {
 int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16 /*[taps][Cout][Cin]*/,
                  const float* scale, const float* shift, void* out_bf16, float* ch_sum, float* ch_sumsq,
                  rxb_stream_t stream);
+/* Data gradient fused with the ReLU / BatchNorm backward of the layer that produced the conv's input
+ * (torch autograd runs conv dgrad, threshold_backward and batch_norm_backward as separate kernels):
+ *   acc[p, k] = sum_{tap,n} dOut(p shifted)[n] * Wt[tap][k][n]      (Wt: the dgrad operand layout, [taps][k][n])
+ *   dy        = acc * [X[p,k]*bn_scale[k] + bn_shift[k] > 0]
+ *   sum_dy[k] += sum_p dy ;  sum_dyx[k] += sum_p dy * X[p,k]
+ *   out_mode 0: out = dy ; 1: out = bn_scale*dy ; 2: out += bn_scale*dy      (bf16 [B,H,W,ldC], channels 0..Cout)
+ * In the descriptor Cin is the contraction size (channels of dOut per tap), Cout the width of the result. */
+int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
+                      int ldX, const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16,
+                      float* sum_dy, float* sum_dyx, rxb_stream_t stream);
 /* dW[tap][n][k] += sum_p dOut[p, n] * A'(p shifted by tap)[k]  (fp32 atomics into dW). */
 int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,
                    const void* dOut_bf16, int ldD, float* dW, rxb_stream_t stream);

@@ -3,10 +3,7 @@
 
 namespace rxb {
 
-int pick_bn(int n) {
-  if (n <= 256) return n;
-  return (n % 256 == 0) ? 256 : 128;
-}
+int pick_bn(int n) { return n < 128 ? n : 128; }
 
 }  // namespace rxb
 
@@ -28,24 +25,46 @@ int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16,
   const int bk = d->Cin <= 32 ? 32 : 64;
   if (d->prologue && bk != 64) return set_error(RXB_ERR_UNSUPPORTED, "rxb_conv_fwd: prologue needs Cin > 32");
   GemmParams p = {};
-  p.t = make_tiling(d->B, d->H, d->W);
-  p.bn = pick_bn(d->Cout);
-  p.n_tiles = ceil_div(d->Cout, p.bn);
+  p.B = d->B; p.H = d->H; p.W = d->W;
   p.n_total = d->Cout;
   p.taps_x = d->taps_x; p.taps_y = d->taps_y; p.pad_x = d->pad_x; p.pad_y = d->pad_y;
-  p.kb_per_tap = ceil_div(d->Cin, bk);
   p.cin = d->Cin;
   p.epi_mode = EPI_STORE;
   p.out_mode = OUT_DY;
   p.do_stats = d->stats;
-  p.out = static_cast<__nv_bfloat16*>(out_bf16);
-  p.ldc = d->ldC;
-  p.c_off = d->c_off;
-  p.ch_sum = ch_sum;
-  p.ch_sumsq = ch_sumsq;
+  p.ch_sum = ch_sum ? ch_sum + d->c_off : nullptr;
+  p.ch_sumsq = ch_sumsq ? ch_sumsq + d->c_off : nullptr;
   p.scale = scale;
   p.shift = shift;
-  return launch_conv_gemm(p, A_bf16, d->ldA, W_bf16, bk, d->prologue != 0, as_stream(stream));
+  return launch_conv_gemm(p, A_bf16, d->ldA, W_bf16, out_bf16, d->ldC, d->c_off, nullptr, 0, bk, d->prologue != 0,
+                          as_stream(stream));
+}
+
+int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16, int ldX,
+                      const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16, float* sum_dy,
+                      float* sum_dyx, rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(d && dOut_bf16 && Wt_bf16 && X_bf16 && bn_scale && bn_shift && out_bf16 && sum_dy && sum_dyx,
+                "rxb_conv_dgrad_bn: null pointer");
+  RXB_CHECK_ARG(d->Cin > 0 && d->Cin % 8 == 0 && d->ldA >= d->Cin && d->ldA % 8 == 0, "rxb_conv_dgrad_bn: bad Cin/ldA");
+  RXB_CHECK_ARG(d->Cout >= 32 && d->Cout % 32 == 0 && d->ldC >= d->Cout && ldX >= d->Cout, "rxb_conv_dgrad_bn: bad Cout");
+  RXB_CHECK_ARG(out_mode >= OUT_DY && out_mode <= OUT_G_ACCUM, "rxb_conv_dgrad_bn: bad out_mode");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+  GemmParams p = {};
+  p.B = d->B; p.H = d->H; p.W = d->W;
+  p.n_total = d->Cout;
+  p.taps_x = d->taps_x; p.taps_y = d->taps_y; p.pad_x = d->pad_x; p.pad_y = d->pad_y;
+  p.cin = d->Cin;
+  p.epi_mode = EPI_DGRAD_BN;
+  p.out_mode = out_mode;
+  p.do_stats = 1;
+  p.ch_sum = sum_dy;
+  p.ch_sumsq = sum_dyx;
+  p.e_scale = bn_scale;
+  p.e_shift = bn_shift;
+  return launch_conv_gemm(p, dOut_bf16, d->ldA, Wt_bf16, out_bf16, d->ldC, 0, X_bf16, ldX, d->Cin <= 32 ? 32 : 64, false,
+                          as_stream(stream));
 }
 
 int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,

@@ -2,21 +2,26 @@
 //
 // Forward / data-gradient kernel (conv_gemm_kernel):
 //     D[p, n] = sum_{tap, k} A'(p shifted by tap)[k] * Wt[tap][n][k]          bf16 x bf16 -> fp32 (TMEM)
-//   * a persistent, warp-specialised CTA per SM: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer and
-//     TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> global), warps 6-9 = A-operand transform.
+//   * persistent, warp-specialised CTA (one per SM): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer and
+//     TMEM owner, warps 2-5 = epilogue, warps 6-13 = A-operand transform.
 //   * the M tile is 128 pixels fetched by one 4-D TMA box; taps are box shifts, padding is TMA zero fill.
+//     For multi-row filters the box carries th+taps_y-1 image rows ("row halo") and the taps_y row taps are
+//     shared-memory descriptor offsets into the SAME stage, so an activation row is fetched from L2 (and
+//     transformed) taps_x times instead of taps_x*taps_y times.
 //   * DenseNet's pre-activation BatchNorm+ReLU (torchvision _DenseLayer: norm -> relu -> conv) is applied
 //     to the A tile IN SHARED MEMORY between the TMA and the MMA (zero padding stays zero), so the
 //     normalised activation never exists in HBM.
 //   * two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
-//   * epilogues: bf16 store at a channel offset of a wider tensor (DenseNet concat-by-offset) with
-//     per-channel sum / sum-of-squares for the NEXT BatchNorm, or the fused ReLU/BatchNorm backward
-//     (mask, per-channel reductions, accumulate into the concat gradient).
+//   * epilogues run through a swizzled shared-memory staging tile: results leave with ONE TMA store per
+//     64-channel box (coalesced, clipped at tensor edges, written at a channel offset of a wider tensor =
+//     DenseNet concat-by-offset); the fused ReLU/BatchNorm-backward epilogue gets the activation tile and
+//     the running concat-gradient tile by TMA loads issued by the producer warp.
 //
 // Weight-gradient kernel (conv_wgrad_kernel):
 //     dW[tap][n][k] += sum_p A'(p shifted by tap)[k] * dOut[p][n]
 //   both operands are MN-major (the contraction runs over pixels), 128 A-channels per accumulator group,
 //   up to 512 TMEM columns of groups per CTA, pixel range split over CTAs, fp32 atomics into torch OIHW.
+//   For 3x3 filters the A' tile is loaded and transformed once per pixel tile and dOut is shifted instead.
 //
 // Reference: torchvision densenet121 as swapped in for TwoSitesNN's trunk (reference
 // cell_classifier/models.py:16-29, 45); the convs there are cuDNN calls.
@@ -24,30 +29,53 @@
 
 namespace rxb {
 
-constexpr int kGemmThreads = 320;
+constexpr int kXformThreads = 256;                     // 8 A-operand transform warps
+constexpr int kGemmThreads = 192 + kXformThreads;      // + TMA, MMA, 4 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;   // TMEM columns per accumulator stage
 constexpr int kMaxPrologueC = 1024;
-constexpr int kMaxStatN = 1024;
+constexpr int kMaxBN = 128;
 
 struct __align__(16) GemmAux {
   float s_scale[kMaxPrologueC + 64];
   float s_shift[kMaxPrologueC + 64];
-  float s_stat[2][kMaxStatN];
+  float e_scale[kMaxBN];
+  float e_shift[kMaxBN];
+  float s_stat[2][kMaxBN];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t epi_in_full;
+  uint64_t epi_in_empty;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+static int log2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
 PixelTiling make_tiling(int B, int H, int W) {
   PixelTiling t;
   t.W = W; t.H = H; t.B = B;
-  auto log2_ceil = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
   int twl = log2_ceil(W); if (twl > 7) twl = 7;
+  int thl = log2_ceil(H); if (thl > 7 - twl) thl = 7 - twl;
+  int tbl = 7 - twl - thl;
+  t.tw_log2 = twl; t.th_log2 = thl; t.tb_log2 = tbl;
+  t.tiles_x = ceil_div(W, 1 << twl);
+  t.tiles_y = ceil_div(H, 1 << thl);
+  t.tiles_b = ceil_div(B, 1 << tbl);
+  return t;
+}
+
+PixelTiling make_tiling_tall(int B, int H, int W) {
+  PixelTiling t;
+  t.W = W; t.H = H; t.B = B;
+  int twl = log2_ceil(W); if (twl > 3) twl = 3;
   int thl = log2_ceil(H); if (thl > 7 - twl) thl = 7 - twl;
   int tbl = 7 - twl - thl;
   t.tw_log2 = twl; t.th_log2 = thl; t.tb_log2 = tbl;
@@ -66,18 +94,26 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
   y0 = ty << t.th_log2;
   b0 = tb << t.tb_log2;
 }
-__device__ __forceinline__ void row_coord(const PixelTiling& t, int row, int& xi, int& yi, int& bi) {
-  xi = row & ((1 << t.tw_log2) - 1);
-  yi = (row >> t.tw_log2) & ((1 << t.th_log2) - 1);
-  bi = row >> (t.tw_log2 + t.th_log2);
+
+// ---- A-operand transform: in-place relu(x*scale+shift) on [rows][64 ch] bf16 rows stored with the 128-byte
+// swizzle.  kXformThreads threads: thread t owns 16-byte chunk j = t&7 (channels 8j..8j+7) of rows (t>>3) + 32 i.
+// (bx, by, bb) is the image coordinate of box row 0; box rows run x fastest, then y (box_h rows), then image.
+// Rows whose pixel lies outside the image keep the zeros TMA wrote (conv zero padding); boxes entirely
+// inside the image take the path without per-row coordinate arithmetic.
+__device__ __forceinline__ void transform_chunk(uint4* p, const float (&s)[8], const float (&h)[8]) {
+  uint4 v = *p;
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float lo = fmaxf(fmaf(bf16_lo(w[e]), s[2 * e], h[2 * e]), 0.f);
+    float hi = fmaxf(fmaf(bf16_hi(w[e]), s[2 * e + 1], h[2 * e + 1]), 0.f);
+    w[e] = pack_bf16x2(lo, hi);
+  }
+  *p = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// In-place relu(x*scale+shift) on one [128 rows][64 ch] bf16 tile stored with the 128-byte swizzle.
-// 128 threads: thread t owns 16-byte chunk j = t&7 (channels 8j..8j+7) of rows (t>>3) + 16 i.
-// Rows whose (shifted) pixel lies outside the image keep the zeros TMA wrote (conv zero padding).
-__device__ __forceinline__ void transform_tile_sw128(uint8_t* tile, const float* sc, const float* sh, int t,
-                                                     const PixelTiling& til, int x0, int y0, int b0, int dx,
-                                                     int dy) {
+__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
+                                                    const PixelTiling& til, int box_h, int bx, int by, int bb) {
   const int j = t & 7;
   float s[8], h[8];
 #pragma unroll
@@ -85,23 +121,21 @@ __device__ __forceinline__ void transform_tile_sw128(uint8_t* tile, const float*
     s[e] = sc[j * 8 + e];
     h[e] = sh[j * 8 + e];
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = (t >> 3) + 16 * i;
-    int xi, yi, bi;
-    row_coord(til, row, xi, yi, bi);
-    const int x = x0 + xi + dx, y = y0 + yi + dy, b = b0 + bi;
-    if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
-    uint4* p = reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4));
-    uint4 v = *p;
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float lo = fmaxf(fmaf(bf16_lo(w[e]), s[2 * e], h[2 * e]), 0.f);
-      float hi = fmaxf(fmaf(bf16_hi(w[e]), s[2 * e + 1], h[2 * e + 1]), 0.f);
-      w[e] = pack_bf16x2(lo, hi);
+  const int tw = 1 << til.tw_log2, tb = 1 << til.tb_log2;
+  const bool interior = bx >= 0 && bx + tw <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
+  constexpr int kRowsPerIter = kXformThreads / 8;
+  if (interior) {
+    for (int row = t >> 3; row < rows; row += kRowsPerIter)
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
+  } else {
+    for (int row = t >> 3; row < rows; row += kRowsPerIter) {
+      const int xi = row & (tw - 1);
+      const int r2 = row >> til.tw_log2;
+      const int yi = r2 % box_h, bi = r2 / box_h;
+      const int x = bx + xi, y = by + yi, b = bb + bi;
+      if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
     }
-    *p = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -120,42 +154,70 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
+// Address of the 16-byte chunk holding channels [col, col+8) of pixel row `row` in a staging tile made of
+// boxes [128 rows][cw channels] (cw = 64: 128-byte rows, 128B swizzle; cw = 32: 64-byte rows, 64B swizzle).
+__device__ __forceinline__ uint4* staging_chunk(uint8_t* base, int cw, int row, int col) {
+  if (cw == 64) {
+    const int box = col >> 6, j = (col & 63) >> 3;
+    return reinterpret_cast<uint4*>(base + box * (128 * 128) + row * 128 + ((j ^ (row & 7)) << 4));
+  }
+  const int j = (col & 31) >> 3;
+  return reinterpret_cast<uint4*>(base + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
+}
+
 template <int BK, bool PROLOGUE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p, const int stages) {
   static_assert(BK == 64 || BK == 32, "BK");
   static_assert(!PROLOGUE || BK == 64, "the in-smem BatchNorm+ReLU transform is written for 128B rows");
-  constexpr int A_BYTES = 128 * BK * 2;
+  constexpr int ROW_BYTES = BK * 2;
   constexpr uint32_t kSwz = BK == 64 ? ptx::kSwizzle128B : ptx::kSwizzle64B;
-  constexpr uint32_t kSBO = 8 * BK * 2;  // 8 rows of BK bf16
+  constexpr uint32_t kSBO = 8 * ROW_BYTES;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = p.bn * BK * 2;
+  const int tps = p.halo ? p.taps_y : 1;                       // row taps served by one stage
+  const int a_tx = p.rows_a * ROW_BYTES;                       // bytes TMA delivers per A stage
+  const int a_stage = (a_tx + 1023) & ~1023;
+  const int b_tap = p.bn * ROW_BYTES;                          // one tap's weight tile
+  const int b_stage = tps * b_tap;
+  const int cw = p.bn >= 64 ? 64 : 32;                         // channels per staging / store box
+  const int n_boxes = (p.bn + cw - 1) / cw;
+  const int stage_tile = 128 * n_boxes * cw * 2;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + (size_t)stages * A_BYTES;
-  GemmAux* aux = reinterpret_cast<GemmAux*>(smB + (size_t)stages * b_bytes);
+  uint8_t* smB = smA + (size_t)stages * a_stage;
+  uint8_t* st_out = smB + (size_t)stages * b_stage;
+  uint8_t* st_x = st_out + stage_tile;
+  GemmAux* aux = reinterpret_cast<GemmAux*>(st_x + (p.epi_mode == EPI_DGRAD_BN ? stage_tile : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
-  const int total_tiles = m_tiles * p.n_tiles;
-  const int taps = p.taps_x * p.taps_y;
-  const int kb_total = taps * p.kb_per_tap;
+  const int n0 = blockIdx.y * p.bn;
+  const int groups = p.halo ? p.taps_x : p.taps_x * p.taps_y;
+  const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
+  const int box_h = p.halo ? th + p.taps_y - 1 : th;
+  const bool dgrad = p.epi_mode == EPI_DGRAD_BN;
+  const bool accum = dgrad && p.out_mode == OUT_G_ACCUM;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmOut);
+    if (dgrad) ptx::prefetch_tmap(&tmX);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&aux->full[s], 1);
-      ptx::mbar_init(&aux->xform[s], 128);
+      ptx::mbar_init(&aux->xform[s], kXformThreads);
       ptx::mbar_init(&aux->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
       ptx::mbar_init(&aux->tmem_empty[a], 128);
     }
+    ptx::mbar_init(&aux->epi_in_full, 1);
+    ptx::mbar_init(&aux->epi_in_empty, 1);
     ptx::fence_barrier_init();
   }
   if (PROLOGUE) {
@@ -165,8 +227,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
     }
   }
-  if (p.do_stats)
-    for (int c = threadIdx.x; c < 2 * kMaxStatN; c += kGemmThreads) (&aux->s_stat[0][0])[c] = 0.f;
+  for (int c = threadIdx.x; c < kMaxBN; c += kGemmThreads) {
+    aux->s_stat[0][c] = 0.f;
+    aux->s_stat[1][c] = 0.f;
+    const bool in = dgrad && n0 + c < p.n_total;
+    aux->e_scale[c] = in ? p.e_scale[n0 + c] : 0.f;
+    aux->e_shift[c] = in ? p.e_shift[n0 + c] : 0.f;
+  }
   if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -177,22 +244,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== TMA producer
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      uint32_t phase = 0, ephase = 0;
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
-        const int n0 = n_tile * p.bn;
-        for (int tp = 0; tp < taps; ++tp) {
-          const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
+        for (int g = 0; g < groups; ++g) {
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 1);
-            ptx::mbar_arrive_expect_tx(&aux->full[stage], A_BYTES + b_bytes);
-            ptx::tma_load_4d(smA + (size_t)stage * A_BYTES, &tmA, &aux->full[stage], kb * BK, x0 + tx - p.pad_x,
-                             y0 + ty - p.pad_y, b0);
-            ptx::tma_load_3d(smB + (size_t)stage * b_bytes, &tmB, &aux->full[stage], kb * BK, n0, tp);
+            ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + b_stage);
+            ptx::tma_load_4d(smA + (size_t)stage * a_stage, &tmA, &aux->full[stage], kb * BK, x0 + gx - p.pad_x,
+                             y0 + gy - p.pad_y, b0);
+            for (int ty = 0; ty < tps; ++ty) {
+              const int tap = p.halo ? ty * p.taps_x + gx : g;
+              ptx::tma_load_3d(smB + (size_t)stage * b_stage + ty * b_tap, &tmB, &aux->full[stage], kb * BK, n0, tap);
+            }
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
+        }
+        if (dgrad) {
+          // inputs of this tile's epilogue: the activation tile, and the running gradient tile to accumulate into
+          ptx::mbar_wait(&aux->epi_in_empty, ephase ^ 1, 6);
+          ptx::mbar_arrive_expect_tx(&aux->epi_in_full, accum ? 2 * stage_tile : stage_tile);
+          for (int bx = 0; bx < n_boxes; ++bx) {
+            ptx::tma_load_4d(st_x + bx * (128 * cw * 2), &tmX, &aux->epi_in_full, n0 + bx * cw, x0, y0, b0);
+            if (accum)
+              ptx::tma_load_4d(st_out + bx * (128 * cw * 2), &tmOut, &aux->epi_in_full, n0 + bx * cw, x0, y0, b0);
+          }
+          ephase ^= 1;
         }
       }
     }
@@ -200,27 +279,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.bn, 0, 0);
+      const uint32_t row_tap = (uint32_t)tw * ROW_BYTES;  // one image row of the box
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
         ptx::mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1, 2);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          ptx::mbar_wait(PROLOGUE ? &aux->xform[stage] : &aux->full[stage], phase, 3);
-          ptx::tcgen05_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smA + (size_t)stage * A_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smB + (size_t)stage * b_bytes);
+        uint32_t first = 1;
+        for (int g = 0; g < groups; ++g) {
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            ptx::mbar_wait(PROLOGUE ? &aux->xform[stage] : &aux->full[stage], phase, 3);
+            ptx::tcgen05_fence_after();
+            const uint32_t a_addr = ptx::smem_u32(smA + (size_t)stage * a_stage);
+            const uint32_t b_addr = ptx::smem_u32(smB + (size_t)stage * b_stage);
+            for (int ty = 0; ty < tps; ++ty) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, 16, kSBO, kSwz);
-            const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, 16, kSBO, kSwz);
-            ptx::umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = ptx::make_smem_desc(a_addr + ty * row_tap + k * 32, 16, kSBO, kSwz);
+                const uint64_t db = ptx::make_smem_desc(b_addr + ty * b_tap + k * 32, 16, kSBO, kSwz);
+                ptx::umma_bf16_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+            ptx::umma_commit(&aux->empty[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-          ptx::umma_commit(&aux->empty[stage]);
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&aux->tmem_full[acc]);
         acc ^= 1;
@@ -231,18 +317,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== epilogue: TMEM lanes (warp & 3) * 32 ..
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127
     int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      int x0, y0, b0, xi, yi, bi;
+    uint32_t acc_phase = 0, ephase = 0;
+    for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
+      int x0, y0, b0;
       tile_origin(p.t, m_tile, x0, y0, b0);
-      row_coord(p.t, row, xi, yi, bi);
-      const int x = x0 + xi, y = y0 + yi, b = b0 + bi;
-      const bool valid = x < p.t.W && y < p.t.H && b < p.t.B;
-      const long long pix = ((long long)b * p.t.H + y) * p.t.W + x;
-      const int n0 = n_tile * p.bn;
-
+      if (dgrad) {
+        ptx::mbar_wait(&aux->epi_in_full, ephase, 7);
+        ephase ^= 1;
+      }
+      // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
+      // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
+      const int r2 = row >> p.t.tw_log2;
+      const bool row_valid = x0 + (row & (tw - 1)) < p.t.W && y0 + (r2 & (th - 1)) < p.t.H &&
+                             b0 + (r2 >> p.t.th_log2) < p.t.B;
       ptx::mbar_wait(&aux->tmem_full[acc], acc_phase, 4);
       ptx::tcgen05_fence_after();
       for (int c = 0; c < p.bn; c += 32) {
@@ -251,87 +340,70 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c, r);
         ptx::tmem_ld_wait();
         float v[32];
-        if (p.epi_mode == EPI_STORE) {
-          uint32_t packed[16];
+        uint32_t packed[16];
+        if (!dgrad) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             packed[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            v[2 * i] = valid ? bf16_lo(packed[i]) : 0.f;
-            v[2 * i + 1] = valid ? bf16_hi(packed[i]) : 0.f;
+            v[2 * i] = row_valid ? bf16_lo(packed[i]) : 0.f;
+            v[2 * i + 1] = row_valid ? bf16_hi(packed[i]) : 0.f;
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.ldc + p.c_off + n0 + c);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          }
+          for (int i = 0; i < 4; ++i)
+            *staging_chunk(st_out, cw, row, c + 8 * i) =
+                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           if (p.do_stats) {
             float sq[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
             const float cs = warp_column_sums(v, lane);
             const float cq = warp_column_sums(sq, lane);
-            atomicAdd(&aux->s_stat[0][n0 + c + lane], cs);
-            atomicAdd(&aux->s_stat[1][n0 + c + lane], cq);
+            atomicAdd(&aux->s_stat[0][c + lane], cs);
+            atomicAdd(&aux->s_stat[1][c + lane], cq);
           }
-        } else {  // EPI_DGRAD_BN
-          float xh[32];
-          uint32_t xin[16];
-          if (valid) {
-            const uint4* xs = reinterpret_cast<const uint4*>(p.X + pix * p.ldx + n0 + c);
+        } else {
+          // fused ReLU / BatchNorm backward: dy = acc * [x*es+et > 0]
+          uint32_t xin[16], gin[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 t4 = *staging_chunk(st_x, cw, row, c + 8 * i);
+            xin[4 * i] = t4.x; xin[4 * i + 1] = t4.y; xin[4 * i + 2] = t4.z; xin[4 * i + 3] = t4.w;
+          }
+          if (accum) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint4 t4 = __ldg(xs + i);
-              xin[4 * i] = t4.x; xin[4 * i + 1] = t4.y; xin[4 * i + 2] = t4.z; xin[4 * i + 3] = t4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xin[i] = 0u;
-          }
-          uint32_t gin[16];
-          __nv_bfloat16* gp = p.out + pix * p.ldc + p.c_off + n0 + c;
-          if (p.out_mode == OUT_G_ACCUM && valid) {
-            const uint4* gs = reinterpret_cast<const uint4*>(gp);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 t4 = gs[i];
+              const uint4 t4 = *staging_chunk(st_out, cw, row, c + 8 * i);
               gin[4 * i] = t4.x; gin[4 * i + 1] = t4.y; gin[4 * i + 2] = t4.z; gin[4 * i + 3] = t4.w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) gin[i] = 0u;
           }
-          uint32_t packed[16];
+          float dyx[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int ch = n0 + c + i;
             const float xv = (i & 1) ? bf16_hi(xin[i >> 1]) : bf16_lo(xin[i >> 1]);
-            const float es = __ldg(p.e_scale + ch), et = __ldg(p.e_shift + ch);
-            const float pre = fmaf(xv, es, et);
-            float dy = (valid && pre > 0.f) ? __uint_as_float(r[i]) : 0.f;
+            const float es = aux->e_scale[c + i], eh = aux->e_shift[c + i];
+            const float dy = (row_valid && fmaf(xv, es, eh) > 0.f) ? __uint_as_float(r[i]) : 0.f;
             v[i] = dy;
-            xh[i] = valid ? dy * ((xv - __ldg(p.e_mean + ch)) * __ldg(p.e_rstd + ch)) : 0.f;
-            float o;
-            if (p.out_mode == OUT_DY) {
-              o = dy;
-            } else {
+            dyx[i] = dy * xv;
+            float o = dy;
+            if (p.out_mode != OUT_DY) {
               const float g0 = (i & 1) ? bf16_hi(gin[i >> 1]) : bf16_lo(gin[i >> 1]);
               o = fmaf(es, dy, g0);
             }
             const uint32_t ob = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(o));
             if (i & 1) packed[i >> 1] |= ob << 16; else packed[i >> 1] = ob;
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(gp);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          }
+          for (int i = 0; i < 4; ++i)
+            *staging_chunk(st_out, cw, row, c + 8 * i) =
+                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           if (p.do_stats) {
             const float cs = warp_column_sums(v, lane);
-            const float cq = warp_column_sums(xh, lane);
-            atomicAdd(&aux->s_stat[0][n0 + c + lane], cs);
-            atomicAdd(&aux->s_stat[1][n0 + c + lane], cq);
+            const float cq = warp_column_sums(dyx, lane);
+            atomicAdd(&aux->s_stat[0][c + lane], cs);
+            atomicAdd(&aux->s_stat[1][c + lane], cq);
           }
         }
       }
@@ -339,33 +411,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_arrive(&aux->tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      // staged tile -> global: one TMA store per 64-channel box (clipped at the tensor edges)
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        for (int bx = 0; bx < n_boxes; ++bx)
+          if (n0 + bx * cw < p.n_total)
+            ptx::tma_store_4d(&tmOut, st_out + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read();
+        if (dgrad) ptx::mbar_arrive(&aux->epi_in_empty);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    if (et == 0) ptx::tma_store_wait_all();
     if (p.do_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 64;  // 0..127
-      const int stat_off = p.epi_mode == EPI_STORE ? p.c_off : 0;
-      for (int c = et; c < p.n_total; c += 128) {
+      for (int c = et; c < p.bn && n0 + c < p.n_total; c += 128) {
         const float a = aux->s_stat[0][c], bq = aux->s_stat[1][c];
-        if (a != 0.f) atomicAdd(p.ch_sum + stat_off + c, a);
-        if (bq != 0.f) atomicAdd(p.ch_sumsq + stat_off + c, bq);
+        if (a != 0.f) atomicAdd(p.ch_sum + n0 + c, a);
+        if (bq != 0.f) atomicAdd(p.ch_sumsq + n0 + c, bq);
       }
     }
   } else {
     // =============================== A-operand transform (pre-activation BatchNorm + ReLU)
     if (PROLOGUE) {
-      const int t = threadIdx.x - 192;  // 0..127
+      const int t = threadIdx.x - 192;  // 0..kXformThreads-1
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
-        for (int tp = 0; tp < taps; ++tp) {
-          const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
+        for (int g = 0; g < groups; ++g) {
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
-            transform_tile_sw128(smA + (size_t)stage * A_BYTES, aux->s_scale + kb * BK, aux->s_shift + kb * BK, t,
-                                 p.t, x0, y0, b0, tx - p.pad_x, ty - p.pad_y);
+            transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
+                                t, p.t, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&aux->xform[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -404,29 +486,34 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const WgradParams p, const int stages) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = 128 * p.n * 2;
+  const int taps = p.taps_x * p.taps_y;
+  const int d_tile = 128 * p.n * 2;                     // one dOut tile
+  const int nd = p.shift_dout ? taps : 1;               // dOut tiles per stage
+  const int b_bytes = nd * d_tile;
   uint8_t* smA = smem;
   uint8_t* smB = smem + (size_t)stages * kWgA_BYTES;
   WgradAux* aux = reinterpret_cast<WgradAux*>(smB + (size_t)stages * b_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
-  const int taps = p.taps_x * p.taps_y;
-  const int total_boxes = taps * p.boxes_per_tap;
+  const int total_boxes = (p.shift_dout ? 1 : taps) * p.boxes_per_tap;
   const int chunk0 = blockIdx.y * p.chunks_per_cta;
-  const int n_local = min(p.chunks_per_cta, p.n_chunks - chunk0);
+  // accumulators held by this CTA: channel chunks (classic) or filter taps (shift_dout)
+  const int n_local = p.shift_dout ? taps : min(p.chunks_per_cta, p.n_chunks - chunk0);
+  const int stages_per_tile = p.shift_dout ? 1 : n_local;
   const int tile_begin = blockIdx.x * p.pix_tiles_per_cta;
   const int tile_end = min(m_tiles, tile_begin + p.pix_tiles_per_cta);
   const int a_row_bytes = p.bkc * 2;
   const int a_box_bytes = 128 * a_row_bytes;
   const int d_boxes = p.n >= 64 ? p.n / 64 : 1;
+  const int th = 1 << p.t.th_log2;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmD);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&aux->full[s], 1);
-      ptx::mbar_init(&aux->xform[s], 128);
+      ptx::mbar_init(&aux->xform[s], kXformThreads);
       ptx::mbar_init(&aux->empty[s], 1);
     }
     ptx::mbar_init(&aux->tmem_full, 1);
@@ -452,7 +539,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int x0, y0, b0;
         tile_origin(p.t, tile, x0, y0, b0);
-        for (int cl = 0; cl < n_local; ++cl) {
+        for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 11);
           ptx::mbar_arrive_expect_tx(&aux->full[stage], kWgA_BYTES + b_bytes);
           uint8_t* a_dst = smA + (size_t)stage * kWgA_BYTES;
@@ -463,13 +550,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tp = kk / p.boxes_per_tap;
               c0 = (kk - tp * p.boxes_per_tap) * p.bkc;
             }
-            const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
-            ptx::tma_load_4d(a_dst + (size_t)i * a_box_bytes, &tmA, &aux->full[stage], c0, x0 + tx - p.pad_x,
-                             y0 + ty - p.pad_y, b0);
+            int ax = x0, ay = y0;
+            if (!p.shift_dout) {
+              const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
+              ax += tx - p.pad_x;
+              ay += ty - p.pad_y;
+            }
+            ptx::tma_load_4d(a_dst + (size_t)i * a_box_bytes, &tmA, &aux->full[stage], c0, ax, ay, b0);
           }
           uint8_t* d_dst = smB + (size_t)stage * b_bytes;
-          for (int j = 0; j < d_boxes; ++j)
-            ptx::tma_load_4d(d_dst + (size_t)j * 16384, &tmD, &aux->full[stage], j * 64, x0, y0, b0);
+          for (int t = 0; t < nd; ++t) {
+            int dx = x0, dy = y0;
+            if (p.shift_dout) {  // dW[t] = sum_q A'[q] * dOut[q - (t - pad)]
+              const int ty = t / p.taps_x, tx = t - ty * p.taps_x;
+              dx -= tx - p.pad_x;
+              dy -= ty - p.pad_y;
+            }
+            for (int j = 0; j < d_boxes; ++j)
+              ptx::tma_load_4d(d_dst + (size_t)t * d_tile + (size_t)j * 16384, &tmD, &aux->full[stage], j * 64, dx, dy, b0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -488,17 +587,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        for (int cl = 0; cl < n_local; ++cl) {
+        for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(p.prologue ? &aux->xform[stage] : &aux->full[stage], phase, 13);
           ptx::tcgen05_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smA + (size_t)stage * kWgA_BYTES);
           const uint32_t d_addr = ptx::smem_u32(smB + (size_t)stage * b_bytes);
-          const uint32_t acc = tmem_base + cl * p.n;
+          for (int t = 0; t < nd; ++t) {
+            const uint32_t acc = tmem_base + (p.shift_dout ? t : cl) * p.n;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_box_bytes, a_sbo, a_swz);
-            const uint64_t db = ptx::make_smem_desc(d_addr + ks * d_kstep, d_lbo, d_sbo, d_swz);
-            ptx::umma_bf16_ss(acc, da, db, idesc, (tile > tile_begin || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_box_bytes, a_sbo, a_swz);
+              const uint64_t db = ptx::make_smem_desc(d_addr + t * d_tile + ks * d_kstep, d_lbo, d_sbo, d_swz);
+              ptx::umma_bf16_ss(acc, da, db, idesc, (tile > tile_begin || ks > 0) ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&aux->empty[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -514,10 +615,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::tcgen05_fence_after();
       const int ib = row / p.bkc, ch_in = row - ib * p.bkc;
       for (int cl = 0; cl < n_local; ++cl) {
-        const int kk = (chunk0 + cl) * p.boxes_per_chunk + ib;
-        const int tp = kk / p.boxes_per_tap;
-        const int ch = (kk - tp * p.boxes_per_tap) * p.bkc + ch_in;
-        bool ok = kk < total_boxes && ch < p.cin;
+        int tp, ch;
+        bool ok;
+        if (p.shift_dout) {
+          tp = cl;
+          ch = row;
+          ok = ch < p.cin;
+        } else {
+          const int kk = (chunk0 + cl) * p.boxes_per_chunk + ib;
+          tp = kk / p.boxes_per_tap;
+          ch = (kk - tp * p.boxes_per_tap) * p.bkc + ch_in;
+          ok = kk < total_boxes && ch < p.cin;
+        }
         long long base = 0, nstride = 0;
         if (p.w_mode == 0) {
           base = (long long)ch * taps + tp;
@@ -552,16 +661,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int x0, y0, b0;
         tile_origin(p.t, tile, x0, y0, b0);
-        for (int cl = 0; cl < n_local; ++cl) {
+        for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(&aux->full[stage], phase, 15);
           for (int i = 0; i < p.boxes_per_chunk; ++i) {
             const int kk = (chunk0 + cl) * p.boxes_per_chunk + i;
             if (kk >= total_boxes) continue;
             const int tp = kk / p.boxes_per_tap;
             const int c0 = (kk - tp * p.boxes_per_tap) * p.bkc;
-            const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
-            transform_tile_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, aux->s_scale + c0,
-                                 aux->s_shift + c0, t, p.t, x0, y0, b0, tx - p.pad_x, ty - p.pad_y);
+            int ax = x0, ay = y0;
+            if (!p.shift_dout) {
+              const int ty = tp / p.taps_x, tx = tp - ty * p.taps_x;
+              ax += tx - p.pad_x;
+              ay += ty - p.pad_y;
+            }
+            transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale + c0,
+                                aux->s_shift + c0, t, p.t, th, ax, ay, b0);
           }
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&aux->xform[stage]);
@@ -580,57 +694,98 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int make_act_tmap(CUtensorMap* tm, const void* base, const PixelTiling& t, int channels, long long ld,
-                         int box_c) {
-  uint64_t dims[4] = {(uint64_t)channels, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.B};
-  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * t.W, (uint64_t)ld * 2 * t.W * t.H};
-  uint32_t box[4] = {(uint32_t)box_c, 1u << t.tw_log2, 1u << t.th_log2, 1u << t.tb_log2};
-  CUtensorMapSwizzle swz = box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                           : box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                             : CU_TENSOR_MAP_SWIZZLE_32B;
-  return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, swz);
+static CUtensorMapSwizzle swizzle_for(int box_c) {
+  return box_c * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : box_c * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                         : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-int launch_conv_gemm(const GemmParams& p, const void* A, long long ldA, const void* Wt, int bk, bool prologue,
-                     cudaStream_t stream) {
+// activation map: dims (channels, W, H, B) with channel stride 1 and pixel stride ld; box (box_c, tw, box_h, tb)
+static int make_act_tmap(CUtensorMap* tm, const void* base, const PixelTiling& t, int channels, long long ld,
+                         int box_c, int box_h) {
+  uint64_t dims[4] = {(uint64_t)channels, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * t.W, (uint64_t)ld * 2 * t.W * t.H};
+  uint32_t box[4] = {(uint32_t)box_c, 1u << t.tw_log2, (uint32_t)box_h, 1u << t.tb_log2};
+  return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                   swizzle_for(box_c));
+}
+
+int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt, void* out, long long ldc,
+                     int c_off, const void* X, long long ldx, int bk, bool prologue, cudaStream_t stream) {
   if (!(bk == 64 || bk == 32)) return set_error(RXB_ERR_INVALID, "conv_gemm: bk must be 32 or 64");
   if (prologue && bk != 64) return set_error(RXB_ERR_INVALID, "conv_gemm: prologue needs bk=64");
-  if (p.bn % 32 || p.bn < 32 || p.bn > 256) return set_error(RXB_ERR_INVALID, "conv_gemm: bn=%d", p.bn);
-  if (p.n_total % 32) return set_error(RXB_ERR_INVALID, "conv_gemm: n_total=%d not a multiple of 32", p.n_total);
-  if (p.n_total > kMaxStatN && p.do_stats) return set_error(RXB_ERR_INVALID, "conv_gemm: n_total too large for stats");
+  if (p.n_total % 32 || p.n_total < 32) return set_error(RXB_ERR_INVALID, "conv_gemm: n_total=%d", p.n_total);
+  if ((ldA * 2) % 16 || (reinterpret_cast<uintptr_t>(A) & 15) || (ldc * 2) % 16 || (c_off * 2) % 16 ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: tensors must be 16-byte aligned with channel strides multiple of 8");
+  if ((p.cin * 2) % 16) return set_error(RXB_ERR_INVALID, "conv_gemm: cin must be a multiple of 8");
+  const bool dgrad = p.epi_mode == EPI_DGRAD_BN;
+  if (dgrad && (!X || (ldx * 2) % 16 || (reinterpret_cast<uintptr_t>(X) & 15)))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs an aligned X");
+
+  p.bn = p.n_total < kMaxBN ? p.n_total : kMaxBN;
+  p.n_tiles = ceil_div(p.n_total, p.bn);
+  p.kb_per_tap = ceil_div(p.cin, bk);
   if (prologue && p.kb_per_tap * bk > kMaxPrologueC + 64) return set_error(RXB_ERR_INVALID, "conv_gemm: cin too large");
-  if ((ldA * 2) % 16 || (reinterpret_cast<uintptr_t>(A) & 15))
-    return set_error(RXB_ERR_INVALID, "conv_gemm: A not 16-byte aligned / ldA not a multiple of 8");
-  CUtensorMap tmA, tmB;
-  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk);
+  // tiling: multi-row filters prefer tall tiles so the row halo is cheap
+  p.t = make_tiling(p.B, p.H, p.W);
+  p.halo = 0;
+  if (p.taps_y > 1) {
+    PixelTiling tall = make_tiling_tall(p.B, p.H, p.W);
+    if (tall.tb_log2 == 0 && tall.tw_log2 == 3) {
+      p.t = tall;
+      p.halo = 1;
+    }
+  }
+  const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
+  const int box_h = p.halo ? th + p.taps_y - 1 : th;
+  p.rows_a = p.halo ? box_h * tw : 128;
+  if (box_h > 256) return set_error(RXB_ERR_INVALID, "conv_gemm: halo box too tall");
+
+  CUtensorMap tmA, tmB, tmOut, tmX;
+  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h);
   if (rc) return rc;
   {
     const int taps = p.taps_x * p.taps_y;
     uint64_t dims[3] = {(uint64_t)p.cin, (uint64_t)p.n_total, (uint64_t)taps};
     uint64_t strides[2] = {(uint64_t)p.cin * 2, (uint64_t)p.cin * 2 * p.n_total};
     uint32_t box[3] = {(uint32_t)bk, (uint32_t)p.bn, 1};
-    if ((p.cin * 2) % 16) return set_error(RXB_ERR_INVALID, "conv_gemm: cin must be a multiple of 8");
     rc = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(Wt), dims, strides, box,
                    bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
-  const int a_bytes = 128 * bk * 2, b_bytes = p.bn * bk * 2;
-  const size_t budget = 225 * 1024;
-  int stages = (int)((budget - sizeof(GemmAux) - 1024) / (size_t)(a_bytes + b_bytes));
+  const int cw = p.bn >= 64 ? 64 : 32;
+  rc = make_act_tmap(&tmOut, static_cast<__nv_bfloat16*>(out) + c_off, p.t, p.n_total, ldc, cw, th);
+  if (rc) return rc;
+  if (dgrad) {
+    rc = make_act_tmap(&tmX, X, p.t, p.n_total, ldx, cw, th);
+    if (rc) return rc;
+  } else {
+    tmX = tmOut;
+  }
+
+  const int row_bytes = bk * 2;
+  const int a_stage = (p.rows_a * row_bytes + 1023) & ~1023;
+  const int b_stage = (p.halo ? p.taps_y : 1) * p.bn * row_bytes;
+  const int stage_tile = 128 * ceil_div(p.bn, cw) * cw * 2;
+  const size_t fixed = sizeof(GemmAux) + 1024 + (size_t)stage_tile * (dgrad ? 2 : 1);
+  const size_t budget = 226 * 1024;
+  int stages = (int)((budget - fixed) / (size_t)(a_stage + b_stage));
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
-  const size_t smem = (size_t)stages * (a_bytes + b_bytes) + sizeof(GemmAux) + 1024;
-  const int total_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b * p.n_tiles;
-  int grid = num_sms();
-  if (grid > total_tiles) grid = total_tiles;
-  if (grid <= 0) return RXB_OK;
+  const size_t smem = (size_t)stages * (a_stage + b_stage) + fixed;
+  const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
+  int gx = num_sms() / p.n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > m_tiles) gx = m_tiles;
+  if (gx <= 0) return RXB_OK;
+  dim3 grid(gx, p.n_tiles);
 
   RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
 #define RXB_LAUNCH_GEMM(BK_, PRO_)                                                                             \
   do {                                                                                                         \
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)smem));                                                                 \
-    conv_gemm_kernel<BK_, PRO_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p, stages);                    \
+    conv_gemm_kernel<BK_, PRO_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmX, p, stages);        \
   } while (0)
   if (bk == 64 && prologue) RXB_LAUNCH_GEMM(64, true);
   else if (bk == 64) RXB_LAUNCH_GEMM(64, false);
@@ -649,10 +804,18 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   const int taps = p.taps_x * p.taps_y;
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
-  p.n_chunks = ceil_div(taps * p.boxes_per_tap, p.boxes_per_chunk);
-  p.chunks_per_cta = 512 / p.n;
-  if (p.chunks_per_cta > p.n_chunks) p.chunks_per_cta = p.n_chunks;
-  const int chunk_groups = ceil_div(p.n_chunks, p.chunks_per_cta);
+  p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;
+  int chunk_groups;
+  if (p.shift_dout) {
+    p.n_chunks = 1;
+    p.chunks_per_cta = 1;
+    chunk_groups = 1;
+  } else {
+    p.n_chunks = ceil_div(taps * p.boxes_per_tap, p.boxes_per_chunk);
+    p.chunks_per_cta = 512 / p.n;
+    if (p.chunks_per_cta > p.n_chunks) p.chunks_per_cta = p.n_chunks;
+    chunk_groups = ceil_div(p.n_chunks, p.chunks_per_cta);
+  }
   if (p.prologue && p.boxes_per_tap * p.bkc > kMaxPrologueC + 64)
     return set_error(RXB_ERR_INVALID, "conv_wgrad: cin too large");
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
@@ -663,13 +826,14 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   pix_ctas = ceil_div(m_tiles, p.pix_tiles_per_cta);
 
   CUtensorMap tmA, tmD;
-  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc);
+  const int th = 1 << p.t.th_log2;
+  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc, th);
   if (rc) return rc;
-  rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32);
+  rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32, th);
   if (rc) return rc;
 
-  const int b_bytes = 128 * p.n * 2;
-  const size_t budget = 225 * 1024;
+  const int b_bytes = (p.shift_dout ? taps : 1) * 128 * p.n * 2;
+  const size_t budget = 226 * 1024;
   int stages = (int)((budget - sizeof(WgradAux) - 1024) / (size_t)(kWgA_BYTES + b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_wgrad: tile too large for shared memory");

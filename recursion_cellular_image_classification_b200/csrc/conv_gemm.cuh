@@ -13,47 +13,44 @@ struct PixelTiling {
   int tw_log2, th_log2, tb_log2;
   int tiles_x, tiles_y, tiles_b;
 };
-PixelTiling make_tiling(int B, int H, int W);
+PixelTiling make_tiling(int B, int H, int W);       // wide tiles (tw as large as possible)
+PixelTiling make_tiling_tall(int B, int H, int W);  // tw <= 8: tall tiles for the row-halo tap reuse
 
 enum EpiMode {
-  EPI_STORE = 0,     // out[p, c_off+n] = bf16(acc) ; optional per-channel sum / sum-of-squares
-  EPI_DGRAD_BN = 1,  // dy = acc * [x*es+et > 0] ; stats sum(dy), sum(dy*xhat) ; out per out_mode
+  EPI_STORE = 0,     // out[p, c_off+n] = bf16(acc) ; optional per-channel sum / sum-of-squares of the stored value
+  EPI_DGRAD_BN = 1,  // dy = acc * [x*es+et > 0] ; sums: sum(dy), sum(dy*x) ; out per out_mode
 };
 enum OutMode { OUT_DY = 0, OUT_G_WRITE = 1, OUT_G_ACCUM = 2 };
 
 struct GemmParams {
-  PixelTiling t;
-  int n_tiles;      // tiles along N
-  int bn;           // N per tile (multiple of 32, <= 256)
+  int B, H, W;      // pixel space shared by A and the output (stride-1 convolutions)
   int n_total;      // valid N (multiple of 32)
   int taps_x, taps_y, pad_x, pad_y;
-  int kb_per_tap;   // k-blocks (of BK channels) per tap
   int cin;          // valid A channels per tap
   int epi_mode;
   int out_mode;
   int do_stats;
-  // EPI_STORE
-  __nv_bfloat16* out;
-  long long ldc;
-  int c_off;
-  float* ch_sum;    // [>= c_off + n_total] (EPI_STORE) or [n_total] (EPI_DGRAD_BN)
-  float* ch_sumsq;
+  float* ch_sum;    // [n_total] (EPI_STORE: of the channel range being written; DGRAD: sum dy)
+  float* ch_sumsq;  // [n_total] (EPI_STORE: sum of squares; DGRAD: sum dy * x, x = the raw activation)
   // prologue (A := relu(A*scale + shift)), indexed by A channel
   const float* scale;
   const float* shift;
-  // EPI_DGRAD_BN: activation the BN saw, and that BN's folded parameters per N channel
-  const __nv_bfloat16* X;
-  long long ldx;
+  // EPI_DGRAD_BN: folded BatchNorm of the consumer, per N channel
   const float* e_scale;
   const float* e_shift;
-  const float* e_mean;
-  const float* e_rstd;
+  // ---- filled by launch_conv_gemm
+  PixelTiling t;
+  int n_tiles, bn, kb_per_tap;
+  int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
+  int rows_a;       // pixel rows of one A stage (128, or (th+taps_y-1)*tw with halo)
 };
 
 // A: bf16 activation [B,H,W,ldA] (first `cin` channels used per tap); Wt: bf16 [taps][n_total][cin].
+// out: bf16 [B,H,W,ldc], written (or read-modified-written) at channels c_off..c_off+n_total.
+// X (EPI_DGRAD_BN): the activation the consumer's BatchNorm saw, bf16 [B,H,W,ldx], channels 0..n_total.
 // bk = 64 (128B swizzle) or 32 (64B swizzle).
-int launch_conv_gemm(const GemmParams& p, const void* A, long long ldA, const void* Wt, int bk, bool prologue,
-                     cudaStream_t stream);
+int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt, void* out, long long ldc,
+                     int c_off, const void* X, long long ldx, int bk, bool prologue, cudaStream_t stream);
 
 struct WgradParams {
   PixelTiling t;
@@ -68,6 +65,7 @@ struct WgradParams {
   int n_off;            // first dOut channel of this launch (N tiling for Cout > 256)
   int pix_tiles_per_cta;
   int prologue;
+  int shift_dout;       // 1: multi-tap with cin <= 128: A' tile loaded+transformed ONCE per pixel tile, dOut shifted per tap
   const float* scale;
   const float* shift;
   float* dW;            // fp32, torch OIHW [Cout_total][cin_w][taps_y_w][taps_x_w], atomically accumulated

@@ -301,29 +301,32 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
 }
 
 // ------------------------------------------------------------------------------------------------ BN bwd finalize
-__global__ void bn_bwd_finalize_kernel(int mode, float* __restrict__ dsum, float* __restrict__ dsq,
-                                       const float* __restrict__ scale, float count, int C,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ corrA, float* __restrict__ corrB) {
+__global__ void bn_bwd_finalize_kernel(int mode, int q_is_raw, float* __restrict__ dsum, float* __restrict__ dsq,
+                                       BnFold f, float count, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ corrA,
+                                       float* __restrict__ corrB) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float s = dsum[c], q = dsq[c];
+  const float s = dsum[c];
+  float q = dsq[c];
+  // the dgrad epilogue reduces sum(dy * x) with the raw activation: sum(dy*xhat) = rstd * (sum(dy*x) - mean*sum(dy))
+  if (q_is_raw) q = f.rstd[c] * (q - f.mean[c] * s);
   dgamma[c] = q;
   dbeta[c] = s;
   const float m1 = s / count, m2 = q / count;
   if (mode == 0) {
-    corrA[c] += scale[c] * m1;
-    corrB[c] += scale[c] * m2;
+    corrA[c] += f.scale[c] * m1;
+    corrB[c] += f.scale[c] * m2;
   } else {
     dsum[c] = m1;
     dsq[c] = m2;
   }
 }
 
-int bn_bwd_finalize(int mode, float* dsum, float* dsq, const float* scale, float count, int C, float* dgamma,
+int bn_bwd_finalize(int mode, int q_is_raw, float* dsum, float* dsq, BnFold f, float count, int C, float* dgamma,
                     float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mode, dsum, dsq, scale, count, C, dgamma, dbeta, corrA,
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mode, q_is_raw, dsum, dsq, f, count, C, dgamma, dbeta, corrA,
                                                           corrB);
   RXB_LAUNCH_OK();
   return RXB_OK;

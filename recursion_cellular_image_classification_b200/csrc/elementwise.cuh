@@ -40,11 +40,12 @@ int final_bn_relu_gap(const __nv_bfloat16* X, int ldx, int B, int HW, int C, con
 int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int ldx, int B, int H, int W, int C,
                      BnFold f, __nv_bfloat16* G, float* dsum, float* dsq, cudaStream_t st);
 
-// After the reductions of one BatchNorm's backward are complete:
-//   dgamma = dsq ; dbeta = dsum
+// After the reductions of one BatchNorm's backward are complete (dsum = sum dy; dsq = sum dy*xhat, or
+// sum dy*x with the raw activation when q_is_raw — converted here with the fold's mean/rstd):
+//   dgamma = sum dy*xhat ; dbeta = sum dy
 //   mode 0 (consumer of a concat buffer): corrA[c] += scale*dsum/M ; corrB[c] += scale*dsq/M
 //   mode 1 (single consumer):             dsum[c] = dsum/M ; dsq[c] = dsq/M    (consumed by bn_bwd_apply)
-int bn_bwd_finalize(int mode, float* dsum, float* dsq, const float* scale, float count, int C, float* dgamma,
+int bn_bwd_finalize(int mode, int q_is_raw, float* dsum, float* dsq, BnFold f, float count, int C, float* dgamma,
                     float* dbeta, float* corrA, float* corrB, cudaStream_t st);
 
 // dx[p,c] = scale[c] * (dy[p,c] - m1[c] - xhat[p,c]*m2[c]) in place on dy (bf16 [M,C] dense).

@@ -191,3 +191,29 @@ def conv_wgrad(A, dOut, Cin, Cout, taps=(1, 1), pad=(0, 0), scale=None, shift=No
     check(load().rxb_conv_wgrad(ctypes.byref(d), ptr(A), ptr(scale), ptr(shift), ptr(dOut), ldD, ptr(dW),
                                 stream_ptr()))
     return dW
+
+
+OUT_DY, OUT_G_WRITE, OUT_G_ACCUM = 0, 1, 2
+
+
+def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=None, Cin=None, pad=(0, 0)):
+    """Data gradient fused with the ReLU/BatchNorm backward of the layer that produced the conv input.
+    dOut bf16 [B,H,W,ldD]; Wt bf16 [ty,tx,Cout,Cin] = the dgrad operand (tap-flipped, transposed weights);
+    X bf16 [B,H,W,ldX] raw activation whose relu(bn(.)) fed the conv (channels 0..Cout).
+    Returns (out bf16 [B,H,W,ldC], sum_dy f32 [Cout], sum_dyx f32 [Cout])."""
+    require_gpu()
+    dOut = _cuda(dOut, torch.bfloat16)
+    Wt = _cuda(Wt, torch.bfloat16)
+    X = _cuda(X, torch.bfloat16)
+    B, H, W, ldD = dOut.shape
+    ty, tx, Cout_w, Cin_w = Wt.shape
+    Cin = Cin_w if Cin is None else Cin
+    if out is None:
+        out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=dOut.device)
+    ldC = out.shape[-1]
+    s1 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
+    s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
+    d = _desc(B, H, W, Cin, ldD, Cout, ldC, 0, (ty, tx), pad, False, True)
+    check(load().rxb_conv_dgrad_bn(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1], ptr(_cuda(bn_scale)),
+                                   ptr(_cuda(bn_shift)), out_mode, ptr(out), ptr(s1), ptr(s2), stream_ptr()))
+    return out, s1, s2

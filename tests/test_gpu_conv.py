@@ -110,3 +110,51 @@ def test_conv_wgrad_matches_torch(cuda, B, H, W, Cin, ldA, Cout, k, prologue):
                          shift=None if shift is None else shift.to(cuda)).cpu()
     err = (got - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item() + 1e-3, "max err %g vs %g" % (err, ref.abs().max().item())
+
+
+DG_CASES = [
+    # B, H, W, Cd (dOut channels), Cx (result channels), ldX, k, out_mode
+    (2, 16, 16, 32, 128, 128, 3, 0),       # dense-layer 3x3 dgrad -> dy2
+    (2, 12, 20, 32, 128, 128, 3, 0),       # non power-of-two image: tiles hang over the edge
+    (2, 16, 16, 128, 96, 256, 1, 2),       # dense-layer 1x1 dgrad accumulating into the concat gradient
+    (3, 8, 8, 128, 224, 256, 1, 1),
+    (2, 64, 64, 32, 128, 128, 3, 0),
+    (1, 128, 128, 128, 160, 256, 1, 2),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cd,Cx,ldX,k,out_mode", DG_CASES)
+def test_conv_dgrad_bn_matches_torch(cuda, B, H, W, Cd, Cx, ldX, k, out_mode):
+    """rxb_conv_dgrad_bn == conv_transpose-free restatement: acc = conv(dOut, Wt) ; dy = acc*[x*s+h>0] ;
+    sums of dy and dy*x ; out per out_mode."""
+    gen = torch.Generator().manual_seed(B * 31 + H + Cd + Cx + k)
+    dOut = _rand_bf16((B, H, W, Cd), gen)
+    Wt = _rand_bf16((Cx, Cd, k, k), gen, scale=(Cd * k * k) ** -0.5)   # operand as the kernel contracts it
+    X = _rand_bf16((B, H, W, ldX), gen)
+    s = torch.rand(Cx, generator=gen) + 0.5
+    h = torch.randn(Cx, generator=gen) * 0.3
+    G0 = _rand_bf16((B, H, W, ldX), gen)
+    pad = {1: 0, 3: 1}[k]
+    acc = _ref_conv(dOut, Wt, pad)                                   # [B,H,W,Cx] fp32
+    xv = X[..., :Cx].float()
+    dy = acc * ((xv * s + h) > 0)
+    if out_mode == 0:
+        ref = dy
+    elif out_mode == 1:
+        ref = s * dy
+    else:
+        ref = G0[..., :Cx].float() + s * dy
+    out = G0.clone().to(cuda)
+    out, s1, s2 = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
+                                    out_mode=out_mode, out=out, pad=(pad, pad))
+    torch.cuda.synchronize()
+    got = out[..., :Cx].float().cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), "max err %g vs %g" % (err, ref.abs().max().item())
+    assert torch.equal(out[..., Cx:].cpu(), G0[..., Cx:]), "channels beyond Cout must stay untouched"
+    d64 = dy.double().reshape(-1, Cx)
+    x64 = xv.double().reshape(-1, Cx)
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=2e-3,
+                               atol=2e-3 * d64.abs().sum(0).max().item())
+    np.testing.assert_allclose(s2.cpu().numpy(), (d64 * x64).sum(0).numpy(), rtol=2e-3,
+                               atol=2e-3 * (d64 * x64).abs().sum(0).max().item())
