@@ -150,12 +150,20 @@ int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16 
  * (torch autograd runs conv dgrad, threshold_backward and batch_norm_backward as separate kernels):
  *   acc[p, k] = sum_{tap,n} dOut(p shifted)[n] * Wt[tap][k][n]      (Wt: the dgrad operand layout, [taps][k][n])
  *   dy        = acc * [X[p,k]*bn_scale[k] + bn_shift[k] > 0]
- *   sum_dy[k] += sum_p dy ;  sum_dyx[k] += sum_p dy * X[p,k]
- *   out_mode 0: out = dy ; 1: out = bn_scale*dy ; 2: out += bn_scale*dy      (bf16 [B,H,W,ldC], channels 0..Cout)
- * In the descriptor Cin is the contraction size (channels of dOut per tap), Cout the width of the result. */
+ *   sum_dy[k] += sum_p dy
+ *   out_mode 0: out = dy ; 1: out = bn_scale*dy ; 2: out += bn_scale*dy      (bf16 [B,H,W,ldC], channels 0..Cout;
+ *   mode 2 is an L2 reduce-add issued by TMA: the running gradient is never loaded into the SM)
+ * In the descriptor Cin is the contraction size (channels of dOut per tap), Cout (>= 64) the width of the result.
+ * The second BatchNorm-backward reduction, sum_p dy*X, is not reduced here: see rxb_bn_sum_dyx_from_wdw. */
 int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
                       int ldX, const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16,
-                      float* sum_dy, float* sum_dyx, rxb_stream_t stream);
+                      float* sum_dy, rxb_stream_t stream);
+/* sum_dyx[c] = sum_p dy[p,c]*X[p,c] for the BatchNorm in front of a convolution, from that convolution's weights and
+ * finished weight gradient (fp32 OIHW [Cout][Cin][taps]):  with z = bn_scale*x + bn_shift,
+ *   sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap]   (both equal sum_p dL/dA' * A', A' = relu(z)),
+ * so sum_dyx = (W.dW - bn_shift*sum_dy) / bn_scale.  Replaces one of torch's batch_norm_backward reductions. */
+int rxb_bn_sum_dyx_from_wdw(const float* W, const float* dW, int Cout, int Cin, int taps, const float* bn_scale,
+                            const float* bn_shift, const float* sum_dy, float* sum_dyx, rxb_stream_t stream);
 /* dW[tap][n][k] += sum_p dOut[p, n] * A'(p shifted by tap)[k]  (fp32 atomics into dW). */
 int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,
                    const void* dOut_bf16, int ldD, float* dW, rxb_stream_t stream);

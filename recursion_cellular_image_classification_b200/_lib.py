@@ -56,7 +56,9 @@ SIGNATURES = {
     "rxb_conv_fwd": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p]),
     "rxb_conv_dgrad_bn": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_int, c_void_p, c_void_p, c_void_p]),
+    "rxb_bn_sum_dyx_from_wdw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
     "rxb_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p]),
     "rxb_dn121_param_count": (c_int64, [ctypes.POINTER(Dn121Config)]),

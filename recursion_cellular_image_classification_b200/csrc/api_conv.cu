@@ -1,5 +1,6 @@
 // api_conv.cu — C-ABI wrappers of the implicit-GEMM convolution kernels (rxb_conv_fwd / rxb_conv_wgrad).
 #include "conv_gemm.cuh"
+#include "elementwise.cuh"
 
 namespace rxb {
 
@@ -42,12 +43,12 @@ int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16,
 
 int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16, int ldX,
                       const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16, float* sum_dy,
-                      float* sum_dyx, rxb_stream_t stream) {
+                      rxb_stream_t stream) {
   using namespace rxb;
-  RXB_CHECK_ARG(d && dOut_bf16 && Wt_bf16 && X_bf16 && bn_scale && bn_shift && out_bf16 && sum_dy && sum_dyx,
+  RXB_CHECK_ARG(d && dOut_bf16 && Wt_bf16 && X_bf16 && bn_scale && bn_shift && out_bf16 && sum_dy,
                 "rxb_conv_dgrad_bn: null pointer");
   RXB_CHECK_ARG(d->Cin > 0 && d->Cin % 8 == 0 && d->ldA >= d->Cin && d->ldA % 8 == 0, "rxb_conv_dgrad_bn: bad Cin/ldA");
-  RXB_CHECK_ARG(d->Cout >= 32 && d->Cout % 32 == 0 && d->ldC >= d->Cout && ldX >= d->Cout, "rxb_conv_dgrad_bn: bad Cout");
+  RXB_CHECK_ARG(d->Cout >= 64 && d->Cout % 32 == 0 && d->ldC >= d->Cout && ldX >= d->Cout, "rxb_conv_dgrad_bn: bad Cout");
   RXB_CHECK_ARG(out_mode >= OUT_DY && out_mode <= OUT_G_ACCUM, "rxb_conv_dgrad_bn: bad out_mode");
   int rc = rxb_check_device();
   if (rc) return rc;
@@ -60,11 +61,21 @@ int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void*
   p.out_mode = out_mode;
   p.do_stats = 1;
   p.ch_sum = sum_dy;
-  p.ch_sumsq = sum_dyx;
+  p.ch_sumsq = nullptr;
   p.e_scale = bn_scale;
   p.e_shift = bn_shift;
   return launch_conv_gemm(p, dOut_bf16, d->ldA, Wt_bf16, out_bf16, d->ldC, 0, X_bf16, ldX, d->Cin <= 32 ? 32 : 64, false,
                           as_stream(stream));
+}
+
+int rxb_bn_sum_dyx_from_wdw(const float* W, const float* dW, int Cout, int Cin, int taps, const float* bn_scale,
+                            const float* bn_shift, const float* sum_dy, float* sum_dyx, rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(W && dW && bn_scale && bn_shift && sum_dy && sum_dyx, "rxb_bn_sum_dyx_from_wdw: null pointer");
+  RXB_CHECK_ARG(Cout > 0 && Cin > 0 && taps > 0, "rxb_bn_sum_dyx_from_wdw: bad shape");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+  return sum_dyx_from_wdw_launch(W, dW, Cout, Cin, taps, bn_scale, bn_shift, sum_dy, sum_dyx, as_stream(stream));
 }
 
 int rxb_conv_wgrad(const rxb_conv_desc* d, const void* A_bf16, const float* scale, const float* shift,

@@ -26,13 +26,16 @@
 // Reference: torchvision densenet121 as swapped in for TwoSitesNN's trunk (reference
 // cell_classifier/models.py:16-29, 45); the convs there are cuDNN calls.
 #include "conv_gemm.cuh"
+#include <stdlib.h>
 
 namespace rxb {
 
-constexpr int kXformThreads = 256;                     // 8 A-operand transform warps
-constexpr int kGemmThreads = 192 + kXformThreads;      // + TMA, MMA, 4 epilogue warps
+constexpr int kXformThreads = 256;                     // warps 6-13: A-operand transform, or the dgrad epilogue
+constexpr int kGemmThreads = 192 + kXformThreads;      // + TMA, MMA, 4 store-epilogue warps
 constexpr int kMaxStages = 8;
-constexpr int kAccStride = 256;   // TMEM columns per accumulator stage
+constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (bn <= 128)
+constexpr int kGramCol = 256;     // TMEM columns [256,384): running Gram matrix of the stored tiles (diag = sum of squares)
+constexpr int kSumCol = 384;      // TMEM columns [384,400): running column sums of the stored tiles
 constexpr int kMaxPrologueC = 1024;
 constexpr int kMaxBN = 128;
 
@@ -47,8 +50,12 @@ struct __align__(16) GemmAux {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t epi_in_full;
-  uint64_t epi_in_empty;
+  uint64_t epi_in_full[2];
+  uint64_t epi_in_empty[2];
+  uint64_t stg_full[2];    // staged output tile complete in shared memory (epilogue -> MMA warp)
+  uint64_t stg_free[2];    // statistics MMAs over the staged tile complete (MMA warp -> epilogue)
+  uint64_t b_full;         // resident weights landed
+  uint64_t stats_done;
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -169,7 +176,7 @@ template <int BK, bool PROLOGUE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
-                 const GemmParams p, const int stages) {
+                 const GemmParams p) {
   static_assert(BK == 64 || BK == 32, "BK");
   static_assert(!PROLOGUE || BK == 64, "the in-smem BatchNorm+ReLU transform is written for 128B rows");
   constexpr int ROW_BYTES = BK * 2;
@@ -178,28 +185,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  const int taps = p.taps_x * p.taps_y;
   const int tps = p.halo ? p.taps_y : 1;                       // row taps served by one stage
   const int a_tx = p.rows_a * ROW_BYTES;                       // bytes TMA delivers per A stage
   const int a_stage = (a_tx + 1023) & ~1023;
-  const int b_tap = p.bn * ROW_BYTES;                          // one tap's weight tile
+  const int b_tap = p.bn * ROW_BYTES;                          // one (tap, k-block) weight tile
   const int b_stage = tps * b_tap;
+  const int b_total = p.b_resident ? taps * p.kb_per_tap * b_tap : stages * b_stage;
   const int cw = p.bn >= 64 ? 64 : 32;                         // channels per staging / store box
   const int n_boxes = (p.bn + cw - 1) / cw;
   const int stage_tile = 128 * n_boxes * cw * 2;
+  const bool dgrad = p.epi_mode == EPI_DGRAD_BN;
   uint8_t* smA = smem;
   uint8_t* smB = smA + (size_t)stages * a_stage;
-  uint8_t* st_out = smB + (size_t)stages * b_stage;
-  uint8_t* st_x = st_out + stage_tile;
-  GemmAux* aux = reinterpret_cast<GemmAux*>(st_x + (p.epi_mode == EPI_DGRAD_BN ? stage_tile : 0));
+  uint8_t* st_out = smB + b_total;
+  uint8_t* st_x = st_out + p.n_stg * stage_tile;
+  uint8_t* ones = st_x + (dgrad ? 2 * stage_tile : 0);        // 1 KB of bf16 1.0: B operand of the column-sum MMA
+  GemmAux* aux = reinterpret_cast<GemmAux*>(ones + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
+  const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int n0 = blockIdx.y * p.bn;
-  const int groups = p.halo ? p.taps_x : p.taps_x * p.taps_y;
+  const int groups = p.halo ? p.taps_x : taps;
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
-  const bool dgrad = p.epi_mode == EPI_DGRAD_BN;
-  const bool accum = dgrad && p.out_mode == OUT_G_ACCUM;
+  const int n_epi_threads = dgrad ? 256 : 128;                 // dgrad: warps 6-13 ; store: warps 2-5
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
@@ -214,10 +226,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
-      ptx::mbar_init(&aux->tmem_empty[a], 128);
+      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads);
+      ptx::mbar_init(&aux->epi_in_full[a], 1);
+      ptx::mbar_init(&aux->epi_in_empty[a], 1);
+      ptx::mbar_init(&aux->stg_full[a], 1);
+      ptx::mbar_init(&aux->stg_free[a], 1);
     }
-    ptx::mbar_init(&aux->epi_in_full, 1);
-    ptx::mbar_init(&aux->epi_in_empty, 1);
+    ptx::mbar_init(&aux->b_full, 1);
+    ptx::mbar_init(&aux->stats_done, 1);
     ptx::fence_barrier_init();
   }
   if (PROLOGUE) {
@@ -234,6 +250,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     aux->e_scale[c] = in ? p.e_scale[n0 + c] : 0.f;
     aux->e_shift[c] = in ? p.e_shift[n0 + c] : 0.f;
   }
+  if (p.mma_stats) {
+    for (int i = threadIdx.x; i < 256; i += kGemmThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    ptx::fence_proxy_async_smem();
+  }
   if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -243,90 +263,158 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // =============================== TMA producer
     if (lane == 0) {
+      if (p.b_resident) {
+        // the whole weight panel of this N tile stays in shared memory for the life of the CTA
+        ptx::mbar_arrive_expect_tx(&aux->b_full, taps * p.kb_per_tap * b_tap);
+        for (int tap = 0; tap < taps; ++tap)
+          for (int kb = 0; kb < p.kb_per_tap; ++kb)
+            ptx::tma_load_3d(smB + (size_t)(tap * p.kb_per_tap + kb) * b_tap, &tmB, &aux->b_full, kb * BK, n0, tap);
+      }
       int stage = 0;
-      uint32_t phase = 0, ephase = 0;
-      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
+      uint32_t phase = 0;
+      int it = 0;
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
+        if (dgrad) {
+          // input of this tile's epilogue: the activation tile the consumer's BatchNorm saw (double-buffered)
+          const int xb = it & 1;
+          ptx::mbar_wait(&aux->epi_in_empty[xb], ((it >> 1) & 1) ^ 1, 6);
+          ptx::mbar_arrive_expect_tx(&aux->epi_in_full[xb], stage_tile);
+          for (int bx = 0; bx < n_boxes; ++bx)
+            ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, &aux->epi_in_full[xb],
+                             n0 + bx * cw, x0, y0, b0);
+        }
         for (int g = 0; g < groups; ++g) {
           const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 1);
-            ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + b_stage);
+            ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + (p.b_resident ? 0 : b_stage));
             ptx::tma_load_4d(smA + (size_t)stage * a_stage, &tmA, &aux->full[stage], kb * BK, x0 + gx - p.pad_x,
                              y0 + gy - p.pad_y, b0);
-            for (int ty = 0; ty < tps; ++ty) {
-              const int tap = p.halo ? ty * p.taps_x + gx : g;
-              ptx::tma_load_3d(smB + (size_t)stage * b_stage + ty * b_tap, &tmB, &aux->full[stage], kb * BK, n0, tap);
+            if (!p.b_resident) {
+              for (int ty = 0; ty < tps; ++ty) {
+                const int tap = p.halo ? ty * p.taps_x + gx : g;
+                ptx::tma_load_3d(smB + (size_t)stage * b_stage + ty * b_tap, &tmB, &aux->full[stage], kb * BK, n0, tap);
+              }
             }
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-        }
-        if (dgrad) {
-          // inputs of this tile's epilogue: the activation tile, and the running gradient tile to accumulate into
-          ptx::mbar_wait(&aux->epi_in_empty, ephase ^ 1, 6);
-          ptx::mbar_arrive_expect_tx(&aux->epi_in_full, accum ? 2 * stage_tile : stage_tile);
-          for (int bx = 0; bx < n_boxes; ++bx) {
-            ptx::tma_load_4d(st_x + bx * (128 * cw * 2), &tmX, &aux->epi_in_full, n0 + bx * cw, x0, y0, b0);
-            if (accum)
-              ptx::tma_load_4d(st_out + bx * (128 * cw * 2), &tmOut, &aux->epi_in_full, n0 + bx * cw, x0, y0, b0);
-          }
-          ephase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer
-    if (lane == 0) {
+    // =============================== MMA issuer: the whole warp walks the pipeline (so every address is warp-uniform);
+    // one elected lane issues the tcgen05 instructions
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.bn, 0, 0);
-      const uint32_t row_tap = (uint32_t)tw * ROW_BYTES;  // one image row of the box
+      const uint32_t row_tap16 = ((uint32_t)tw * ROW_BYTES) >> 4;  // one image row of the box, in descriptor units
+      const uint64_t desc0 = ptx::make_smem_desc(0, 16, kSBO, kSwz);
+      const uint32_t d_hi = ptx::desc_hi(desc0), d_lo0 = ptx::desc_lo(desc0);
+      const uint32_t smA16 = ptx::smem_u32(smA) >> 4, smB16 = ptx::smem_u32(smB) >> 4;
+      const uint32_t a_stage16 = (uint32_t)a_stage >> 4, b_stage16 = (uint32_t)b_stage >> 4, b_tap16 = (uint32_t)b_tap >> 4;
+      // Column statistics of the stored tiles on the tensor pipe: with S = the staged bf16 tile [128 px][128 ch],
+      //   Gram += S^T S  (diagonal = per-channel sum of squares)      sums += S^T 1  (per-channel sum)
+      // both MN-major operands straight from the staging buffer the TMA store reads.
+      const uint32_t idesc_gram = ptx::make_idesc_bf16(128, 128, 1, 1);
+      const uint32_t idesc_sum = ptx::make_idesc_bf16(128, 16, 1, 0);
+      const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(ones), 128, 256, ptx::kSwizzleNone);
+      auto issue_stats = [&](int j) {
+        const int sb = p.n_stg == 2 ? (j & 1) : 0;
+        const int use = p.n_stg == 2 ? (j >> 1) : j;
+        ptx::mbar_wait(&aux->stg_full[sb], use & 1, 8);
+        ptx::tcgen05_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t ds0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
+                                                   ptx::kSwizzle128B);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t ds = ds0 + (uint64_t)(ks * (2048 >> 4));
+            const uint32_t accumulate = (j > 0 || ks > 0) ? 1u : 0u;
+            if (!dgrad) ptx::umma_bf16_ss(tmem_base + kGramCol, ds, ds, idesc_gram, accumulate);
+            ptx::umma_bf16_ss(tmem_base + kSumCol, ds, d_ones, idesc_sum, accumulate);
+          }
+          ptx::umma_commit(&aux->stg_free[sb]);
+        }
+        __syncwarp();
+      };
+      if (p.b_resident) {
+        ptx::mbar_wait(&aux->b_full, 0, 9);
+        ptx::tcgen05_fence_after();
+      }
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
+      int it = 0;
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
         ptx::mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1, 2);
         ptx::tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        uint32_t first = 1;
+        uint32_t accumulate = 0;
         for (int g = 0; g < groups; ++g) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(PROLOGUE ? &aux->xform[stage] : &aux->full[stage], phase, 3);
             ptx::tcgen05_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(smA + (size_t)stage * a_stage);
-            const uint32_t b_addr = ptx::smem_u32(smB + (size_t)stage * b_stage);
-            for (int ty = 0; ty < tps; ++ty) {
+            if (ptx::elect_one()) {
+              const uint32_t a_lo = d_lo0 + smA16 + (uint32_t)stage * a_stage16;
+              for (int ty = 0; ty < tps; ++ty) {
+                const int tap = p.halo ? ty * p.taps_x + g : g;
+                const uint32_t b_lo = d_lo0 + smB16 + (p.b_resident ? (uint32_t)(tap * p.kb_per_tap + kb) * b_tap16
+                                                                    : (uint32_t)stage * b_stage16 + (uint32_t)ty * b_tap16);
+                const uint32_t a_lo_t = a_lo + (uint32_t)ty * row_tap16;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t da = ptx::make_smem_desc(a_addr + ty * row_tap + k * 32, 16, kSBO, kSwz);
-                const uint64_t db = ptx::make_smem_desc(b_addr + ty * b_tap + k * 32, 16, kSBO, kSwz);
-                ptx::umma_bf16_ss(d_tmem, da, db, idesc, first ? 0u : 1u);
-                first = 0;
+                for (int k = 0; k < BK / 16; ++k) {
+                  ptx::umma_bf16_ss_parts(d_tmem, a_lo_t + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, accumulate);
+                  accumulate = 1;
+                }
               }
+              ptx::umma_commit(&aux->empty[stage]);
             }
-            ptx::umma_commit(&aux->empty[stage]);
+            __syncwarp();
+            accumulate = 1;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
-        ptx::umma_commit(&aux->tmem_full[acc]);
+        if (ptx::elect_one()) ptx::umma_commit(&aux->tmem_full[acc]);
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        if (p.mma_stats && it > 0) issue_stats(it - 1);   // the previous tile's epilogue ran under this tile's main loop
+      }
+      if (p.mma_stats) {
+        if (it > 0) issue_stats(it - 1);
+        if (ptx::elect_one()) ptx::umma_commit(&aux->stats_done);
+        __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // =============================== epilogue: TMEM lanes (warp & 3) * 32 ..
+  } else if (dgrad ? warp >= 6 : warp < 6) {
+    // =============================== epilogue: TMEM lanes (warp & 3) * 32 .. ; dgrad: two warps per lane quarter,
+    // each taking half of the columns
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int half = dgrad ? (warp - 6) >> 2 : 0;
+    const int cols_per = dgrad ? p.bn >> 1 : p.bn;
+    const int c_begin = half * cols_per, c_end = c_begin + cols_per;
+    const bool leader = threadIdx.x == (dgrad ? 192 : 64);
+    const uint32_t bar_threads = (uint32_t)n_epi_threads;
     int acc = 0;
-    uint32_t acc_phase = 0, ephase = 0;
-    for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
       int x0, y0, b0;
       tile_origin(p.t, m_tile, x0, y0, b0);
-      if (dgrad) {
-        ptx::mbar_wait(&aux->epi_in_full, ephase, 7);
-        ephase ^= 1;
+      const int sb = p.n_stg == 2 ? (it & 1) : 0;
+      uint8_t* so = st_out + (size_t)sb * stage_tile;
+      // the staging buffer is free once the TMA store issued n_stg tiles ago has read it and (statistics on the
+      // tensor pipe) the MMAs over it have completed
+      if (leader) {
+        if (p.n_stg == 2) ptx::tma_store_wait_read_pending<1>(); else ptx::tma_store_wait_read_pending<0>();
       }
+      if (p.mma_stats && it >= p.n_stg) ptx::mbar_wait(&aux->stg_free[sb], ((p.n_stg == 2 ? it >> 1 : it) - 1) & 1, 10);
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      const uint8_t* sx = st_x + (size_t)(it & 1) * stage_tile;
+      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[it & 1], (it >> 1) & 1, 7);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
       const int r2 = row >> p.t.tw_log2;
@@ -334,26 +422,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              b0 + (r2 >> p.t.th_log2) < p.t.B;
       ptx::mbar_wait(&aux->tmem_full[acc], acc_phase, 4);
       ptx::tcgen05_fence_after();
-      for (int c = 0; c < p.bn; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         if (n0 + c >= p.n_total) break;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c, r);
         ptx::tmem_ld_wait();
-        float v[32];
         uint32_t packed[16];
         if (!dgrad) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             packed[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            v[2 * i] = row_valid ? bf16_lo(packed[i]) : 0.f;
-            v[2 * i + 1] = row_valid ? bf16_hi(packed[i]) : 0.f;
+            if (p.do_stats && !row_valid) packed[i] = 0u;
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *staging_chunk(st_out, cw, row, c + 8 * i) =
+            *staging_chunk(so, cw, row, c + 8 * i) =
                 make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          if (p.do_stats) {
-            float sq[32];
+          if (p.do_stats && !p.mma_stats) {
+            float v[32], sq[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[2 * i] = bf16_lo(packed[i]);
+              v[2 * i + 1] = bf16_hi(packed[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
             const float cs = warp_column_sums(v, lane);
@@ -362,78 +453,94 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             atomicAdd(&aux->s_stat[1][c + lane], cq);
           }
         } else {
-          // fused ReLU / BatchNorm backward: dy = acc * [x*es+et > 0]
-          uint32_t xin[16], gin[16];
+          // fused ReLU / BatchNorm backward: dy = acc * [x*es+eh > 0]; staged value = dy (OUT_DY) or es*dy (G modes)
+          uint32_t xin[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 t4 = *staging_chunk(st_x, cw, row, c + 8 * i);
+            const uint4 t4 = *staging_chunk(const_cast<uint8_t*>(sx), cw, row, c + 8 * i);
             xin[4 * i] = t4.x; xin[4 * i + 1] = t4.y; xin[4 * i + 2] = t4.z; xin[4 * i + 3] = t4.w;
           }
-          if (accum) {
+          const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + c);
+          const float4* eh4 = reinterpret_cast<const float4*>(aux->e_shift + c);
+          const bool scaled = p.out_mode != OUT_DY;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 t4 = *staging_chunk(st_out, cw, row, c + 8 * i);
-              gin[4 * i] = t4.x; gin[4 * i + 1] = t4.y; gin[4 * i + 2] = t4.z; gin[4 * i + 3] = t4.w;
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 es = es4[i4], eh = eh4[i4];
+            const float esv[4] = {es.x, es.y, es.z, es.w}, ehv[4] = {eh.x, eh.y, eh.z, eh.w};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              const float xv = (i & 1) ? bf16_hi(xin[i >> 1]) : bf16_lo(xin[i >> 1]);
+              const float a = scaled ? __uint_as_float(r[i]) * esv[e] : __uint_as_float(r[i]);
+              o[e] = (row_valid && fmaf(xv, esv[e], ehv[e]) > 0.f) ? a : 0.f;
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) gin[i] = 0u;
-          }
-          float dyx[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float xv = (i & 1) ? bf16_hi(xin[i >> 1]) : bf16_lo(xin[i >> 1]);
-            const float es = aux->e_scale[c + i], eh = aux->e_shift[c + i];
-            const float dy = (row_valid && fmaf(xv, es, eh) > 0.f) ? __uint_as_float(r[i]) : 0.f;
-            v[i] = dy;
-            dyx[i] = dy * xv;
-            float o = dy;
-            if (p.out_mode != OUT_DY) {
-              const float g0 = (i & 1) ? bf16_hi(gin[i >> 1]) : bf16_lo(gin[i >> 1]);
-              o = fmaf(es, dy, g0);
-            }
-            const uint32_t ob = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(o));
-            if (i & 1) packed[i >> 1] |= ob << 16; else packed[i >> 1] = ob;
+            packed[2 * i4] = pack_bf16x2(o[0], o[1]);
+            packed[2 * i4 + 1] = pack_bf16x2(o[2], o[3]);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *staging_chunk(st_out, cw, row, c + 8 * i) =
+            *staging_chunk(so, cw, row, c + 8 * i) =
                 make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          if (p.do_stats) {
-            const float cs = warp_column_sums(v, lane);
-            const float cq = warp_column_sums(dyx, lane);
-            atomicAdd(&aux->s_stat[0][c + lane], cs);
-            atomicAdd(&aux->s_stat[1][c + lane], cq);
-          }
         }
       }
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(&aux->tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      // staged tile -> global: one TMA store per 64-channel box (clipped at the tensor edges)
+      // staged tile -> global: one TMA store (or L2 reduce-add into the running gradient) per 64-channel box,
+      // clipped at the tensor edges
       ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        for (int bx = 0; bx < n_boxes; ++bx)
-          if (n0 + bx * cw < p.n_total)
-            ptx::tma_store_4d(&tmOut, st_out + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      if (leader) {
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          if (n0 + bx * cw >= p.n_total) break;
+          if (dgrad && p.out_mode == OUT_G_ACCUM)
+            ptx::tma_reduce_add_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+          else
+            ptx::tma_store_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+        }
         ptx::tma_store_commit();
-        ptx::tma_store_wait_read();
-        if (dgrad) ptx::mbar_arrive(&aux->epi_in_empty);
+        if (p.mma_stats) ptx::mbar_arrive(&aux->stg_full[sb]);
+        if (dgrad) ptx::mbar_arrive(&aux->epi_in_empty[it & 1]);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    if (et == 0) ptx::tma_store_wait_all();
-    if (p.do_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = et; c < p.bn && n0 + c < p.n_total; c += 128) {
+    if (leader) ptx::tma_store_wait_all();
+    if (p.do_stats && p.mma_stats) {
+      // per-channel totals of this CTA from TMEM: lane = channel; Gram diagonal and the sums column
+      if (half == 0 && my_tiles > 0) {
+        ptx::mbar_wait(&aux->stats_done, 0, 12);
+        ptx::tcgen05_fence_after();
+        const int ch = n0 + row;
+        uint32_t s16[16];
+        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kSumCol, s16);
+        ptx::tmem_ld_wait();
+        float total = __uint_as_float(s16[0]);
+        if (dgrad) {
+          if (p.out_mode != OUT_DY) {  // the staged value was es*dy
+            const float es = aux->e_scale[row];
+            total = es != 0.f ? total / es : 0.f;
+          }
+        } else {
+          uint32_t g[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kGramCol + q * 32, g);
+          ptx::tmem_ld_wait();
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq = lane == i ? __uint_as_float(g[i]) : sq;
+          if (ch < p.n_total && sq != 0.f) atomicAdd(p.ch_sumsq + ch, sq);
+        }
+        if (ch < p.n_total && total != 0.f) atomicAdd(p.ch_sum + ch, total);
+      }
+    } else if (p.do_stats) {
+      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      for (int c = threadIdx.x - 64; c < p.bn && n0 + c < p.n_total; c += 128) {
         const float a = aux->s_stat[0][c], bq = aux->s_stat[1][c];
         if (a != 0.f) atomicAdd(p.ch_sum + n0 + c, a);
         if (bq != 0.f) atomicAdd(p.ch_sumsq + n0 + c, bq);
       }
     }
-  } else {
+  } else if (warp >= 6) {
     // =============================== A-operand transform (pre-activation BatchNorm + ReLU)
     if (PROLOGUE) {
       const int t = threadIdx.x - 192;  // 0..kXformThreads-1
@@ -574,38 +681,47 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp walks the pipeline; one elected lane issues (keeps the descriptor arithmetic warp-uniform)
+    {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.n, 1, 1);
       const uint32_t a_swz = p.bkc == 64 ? ptx::kSwizzle128B : ptx::kSwizzle64B;
       const uint32_t a_sbo = 8 * a_row_bytes;
-      const uint32_t a_kstep = 16 * a_row_bytes;
+      const uint32_t a_kstep16 = (16 * a_row_bytes) >> 4;
       const uint32_t d_row_bytes = p.n >= 64 ? 128 : 64;
       const uint32_t d_swz = p.n >= 64 ? ptx::kSwizzle128B : ptx::kSwizzle64B;
       const uint32_t d_sbo = 8 * d_row_bytes;
-      const uint32_t d_kstep = 16 * d_row_bytes;
+      const uint32_t d_kstep16 = (16 * d_row_bytes) >> 4;
       const uint32_t d_lbo = 128 * d_row_bytes;
+      const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smA), a_box_bytes, a_sbo, a_swz);
+      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smB), d_lbo, d_sbo, d_swz);
+      const uint32_t a_hi = ptx::desc_hi(da0), b_hi = ptx::desc_hi(db0);
+      const uint32_t a_stage16 = kWgA_BYTES >> 4, b_stage16 = (uint32_t)b_bytes >> 4, d_tile16 = (uint32_t)d_tile >> 4;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(p.prologue ? &aux->xform[stage] : &aux->full[stage], phase, 13);
           ptx::tcgen05_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smA + (size_t)stage * kWgA_BYTES);
-          const uint32_t d_addr = ptx::smem_u32(smB + (size_t)stage * b_bytes);
-          for (int t = 0; t < nd; ++t) {
-            const uint32_t acc = tmem_base + (p.shift_dout ? t : cl) * p.n;
+          if (ptx::elect_one()) {
+            const uint32_t a_lo = ptx::desc_lo(da0) + (uint32_t)stage * a_stage16;
+            const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)stage * b_stage16;
+            const uint32_t accumulate = tile > tile_begin ? 1u : 0u;
+            for (int t = 0; t < nd; ++t) {
+              const uint32_t acc = tmem_base + (p.shift_dout ? t : cl) * p.n;
+              const uint32_t b_lo_t = b_lo + (uint32_t)t * d_tile16;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_box_bytes, a_sbo, a_swz);
-              const uint64_t db = ptx::make_smem_desc(d_addr + t * d_tile + ks * d_kstep, d_lbo, d_sbo, d_swz);
-              ptx::umma_bf16_ss(acc, da, db, idesc, (tile > tile_begin || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 8; ++ks)
+                ptx::umma_bf16_ss_parts(acc, a_lo + ks * a_kstep16, a_hi, b_lo_t + ks * d_kstep16, b_hi, idesc,
+                                        ks > 0 ? 1u : accumulate);
             }
+            ptx::umma_commit(&aux->empty[stage]);
           }
-          ptx::umma_commit(&aux->empty[stage]);
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
-      ptx::umma_commit(&aux->tmem_full);
+      if (ptx::elect_one()) ptx::umma_commit(&aux->tmem_full);
+      __syncwarp();
     }
   } else if (warp < 6) {
     const int q = warp & 3;
@@ -722,7 +838,12 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (dgrad && (!X || (ldx * 2) % 16 || (reinterpret_cast<uintptr_t>(X) & 15)))
     return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs an aligned X");
 
-  p.bn = p.n_total < kMaxBN ? p.n_total : kMaxBN;
+  if (dgrad && prologue) return set_error(RXB_ERR_INVALID, "conv_gemm: the dgrad epilogue has no A prologue");
+  if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
+  // dgrad, and stores of >= 128 channels with statistics, run 128-wide N tiles whose column sums come from the
+  // tensor pipe (columns past n_total are zero weights / clipped stores)
+  p.bn = (dgrad || p.n_total >= kMaxBN) ? kMaxBN : p.n_total;
+  p.mma_stats = (dgrad || (p.do_stats && p.bn == kMaxBN)) ? 1 : 0;
   p.n_tiles = ceil_div(p.n_total, p.bn);
   p.kb_per_tap = ceil_div(p.cin, bk);
   if (prologue && p.kb_per_tap * bk > kMaxPrologueC + 64) return set_error(RXB_ERR_INVALID, "conv_gemm: cin too large");
@@ -744,8 +865,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   CUtensorMap tmA, tmB, tmOut, tmX;
   int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h);
   if (rc) return rc;
+  const int taps = p.taps_x * p.taps_y;
   {
-    const int taps = p.taps_x * p.taps_y;
     uint64_t dims[3] = {(uint64_t)p.cin, (uint64_t)p.n_total, (uint64_t)taps};
     uint64_t strides[2] = {(uint64_t)p.cin * 2, (uint64_t)p.cin * 2 * p.n_total};
     uint32_t box[3] = {(uint32_t)bk, (uint32_t)p.bn, 1};
@@ -763,21 +884,40 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     tmX = tmOut;
   }
 
+  // ---- shared-memory plan: [A stages][B: resident panel or per-stage][staging x n_stg][x tile x 2 (dgrad)][ones][aux]
   const int row_bytes = bk * 2;
-  const int a_stage = (p.rows_a * row_bytes + 1023) & ~1023;
-  const int b_stage = (p.halo ? p.taps_y : 1) * p.bn * row_bytes;
-  const int stage_tile = 128 * ceil_div(p.bn, cw) * cw * 2;
-  const size_t fixed = sizeof(GemmAux) + 1024 + (size_t)stage_tile * (dgrad ? 2 : 1);
-  const size_t budget = 226 * 1024;
-  int stages = (int)((budget - fixed) / (size_t)(a_stage + b_stage));
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
-  const size_t smem = (size_t)stages * (a_stage + b_stage) + fixed;
+  const long long a_stage = (p.rows_a * row_bytes + 1023) & ~1023;
+  const long long b_tap = (long long)p.bn * row_bytes;
+  const long long b_stage = (p.halo ? p.taps_y : 1) * b_tap;
+  const long long b_panel = (long long)taps * p.kb_per_tap * b_tap;
+  const long long stage_tile = 128ll * ceil_div(p.bn, cw) * cw * 2;
+  const long long fixed = (long long)sizeof(GemmAux) + 1024 /*alignment*/ + 1024 /*ones*/ + (dgrad ? 2 * stage_tile : 0);
+  const long long budget = 227 * 1024;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int gx = num_sms() / p.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > m_tiles) gx = m_tiles;
   if (gx <= 0) return RXB_OK;
+  p.b_resident = 0;
+  p.n_stg = 1;
+  long long per_stage = a_stage + b_stage, avail = budget - fixed - stage_tile;
+  static const int dbg_no_resident = getenv("RXB_DBG_NO_RESIDENT") ? atoi(getenv("RXB_DBG_NO_RESIDENT")) : 0;
+  static const int dbg_one_stg = getenv("RXB_DBG_ONE_STG") ? atoi(getenv("RXB_DBG_ONE_STG")) : 0;
+  const bool allow_res = !(dbg_no_resident == 1 || (dbg_no_resident == 2 && p.bn < 128));
+  if (allow_res && b_panel <= 96 * 1024 && m_tiles > gx && (avail - b_panel) / a_stage >= 3) {
+    p.b_resident = 1;
+    per_stage = a_stage;
+    avail -= b_panel;
+  }
+  if (!dbg_one_stg && (avail - stage_tile) / per_stage >= 4) {
+    p.n_stg = 2;
+    avail -= stage_tile;
+  }
+  long long stages = avail / per_stage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
+  p.stages = (int)stages;
+  const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) + p.n_stg * stage_tile + fixed);
   dim3 grid(gx, p.n_tiles);
 
   RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
@@ -785,7 +925,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   do {                                                                                                         \
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)smem));                                                                 \
-    conv_gemm_kernel<BK_, PRO_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmX, p, stages);        \
+    conv_gemm_kernel<BK_, PRO_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmX, p);                \
   } while (0)
   if (bk == 64 && prologue) RXB_LAUNCH_GEMM(64, true);
   else if (bk == 64) RXB_LAUNCH_GEMM(64, false);

@@ -18,7 +18,7 @@ PixelTiling make_tiling_tall(int B, int H, int W);  // tw <= 8: tall tiles for t
 
 enum EpiMode {
   EPI_STORE = 0,     // out[p, c_off+n] = bf16(acc) ; optional per-channel sum / sum-of-squares of the stored value
-  EPI_DGRAD_BN = 1,  // dy = acc * [x*es+et > 0] ; sums: sum(dy), sum(dy*x) ; out per out_mode
+  EPI_DGRAD_BN = 1,  // dy = acc * [x*es+et > 0] ; ch_sum += sum(dy) ; out per out_mode (G modes store es*dy)
 };
 enum OutMode { OUT_DY = 0, OUT_G_WRITE = 1, OUT_G_ACCUM = 2 };
 
@@ -31,7 +31,8 @@ struct GemmParams {
   int out_mode;
   int do_stats;
   float* ch_sum;    // [n_total] (EPI_STORE: of the channel range being written; DGRAD: sum dy)
-  float* ch_sumsq;  // [n_total] (EPI_STORE: sum of squares; DGRAD: sum dy * x, x = the raw activation)
+  float* ch_sumsq;  // [n_total] (EPI_STORE: sum of squares; DGRAD: unused - sum(dy*x) follows from W.dW, see
+                    //  bn_bwd_finalize)
   // prologue (A := relu(A*scale + shift)), indexed by A channel
   const float* scale;
   const float* shift;
@@ -43,6 +44,10 @@ struct GemmParams {
   int n_tiles, bn, kb_per_tap;
   int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
   int rows_a;       // pixel rows of one A stage (128, or (th+taps_y-1)*tw with halo)
+  int stages;       // A (and streamed B) pipeline depth
+  int n_stg;        // output staging buffers (1 or 2)
+  int b_resident;   // 1: the whole [taps][k-blocks] weight panel of the N tile is loaded once per CTA
+  int mma_stats;    // 1: per-channel sums of the stored tile are accumulated by tcgen05.mma over the staging buffer
 };
 
 // A: bf16 activation [B,H,W,ldA] (first `cin` channels used per tap); Wt: bf16 [taps][n_total][cin].

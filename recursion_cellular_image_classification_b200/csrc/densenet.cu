@@ -281,7 +281,7 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
                           pro != nullptr, st);
 }
 
-// dgrad with the fused ReLU/BatchNorm backward epilogue (reductions: bn.dsum = sum dy, bn.dsq = sum dy*x)
+// dgrad with the fused ReLU/BatchNorm backward epilogue (reduction: bn.dsum = sum dy; sum dy*x follows from W.dW)
 static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* dOut, int ldD, int cout,
                          const ConvLayer& cv, int Nprime, int taps, int pad, const __nv_bfloat16* X, int ldx,
                          const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st) {
@@ -396,7 +396,7 @@ static int backward_head(rxb_dn121& n, cudaStream_t st) {
   // norm5 -> relu -> global average pool backward: first writer of G_4
   RXB_TRY(bn_relu_bwd_to_G(1, n.dfeat, b3.X, b3.Ctot, c.B, b3.H, b3.W, b3.Ctot, n.bn5.fold, b3.G, n.bn5.dsum,
                            n.bn5.dsq, st));
-  RXB_TRY(bn_bwd_finalize(0, 0, n.bn5.dsum, n.bn5.dsq, n.bn5.fold, (float)b3.M, b3.Ctot,
+  RXB_TRY(bn_bwd_finalize(0, nullptr, nullptr, 0, 0, n.bn5.dsum, n.bn5.dsq, n.bn5.fold, (float)b3.M, b3.Ctot,
                           n.grads + n.bn5.gamma_off, n.grads + n.bn5.beta_off, b3.corrA, b3.corrB, st));
   return RXB_OK;
 }
@@ -415,7 +415,8 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
                            n.grads + L.c2.w_off, 0, st));
     RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
                           n.dy2, kBott, st));
-    RXB_TRY(bn_bwd_finalize(1, 1, L.bn2.dsum, L.bn2.dsq, L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
+    RXB_TRY(bn_bwd_finalize(1, n.params + L.c2.w_off, n.grads + L.c2.w_off, kGrowth, 9, L.bn2.dsum, L.bn2.dsq,
+                            L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
                             n.grads + L.bn2.beta_off, nullptr, nullptr, st));
     RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st));  // dy2 := dY
     // 1x1 conv
@@ -423,7 +424,8 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
                            n.grads + L.c1.w_off, 0, st));
     RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
                           OUT_G_ACCUM, blk.G, blk.Ctot, st));
-    RXB_TRY(bn_bwd_finalize(0, 1, L.bn1.dsum, L.bn1.dsq, L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
+    RXB_TRY(bn_bwd_finalize(0, n.params + L.c1.w_off, n.grads + L.c1.w_off, kBott, 1, L.bn1.dsum, L.bn1.dsq,
+                            L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
                             n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, st));
   }
   // exact gradient of the block's input channels
@@ -444,12 +446,14 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
       RXB_TRY(launch_conv_gemm(p, n.dX0, blk.C0, n.arena + t.conv.dgrad_off, n.dP, pb.Ctot, 0, nullptr, 0, 64, false, st));
     }
     RXB_TRY(bn_relu_bwd_to_G(0, n.dP, pb.X, pb.Ctot, c.B, pb.H, pb.W, pb.Ctot, t.bn.fold, pb.G, t.bn.dsum, t.bn.dsq, st));
-    RXB_TRY(bn_bwd_finalize(0, 0, t.bn.dsum, t.bn.dsq, t.bn.fold, (float)pb.M, pb.Ctot, n.grads + t.bn.gamma_off,
+    RXB_TRY(bn_bwd_finalize(0, nullptr, nullptr, 0, 0, t.bn.dsum, t.bn.dsq, t.bn.fold, (float)pb.M, pb.Ctot,
+                            n.grads + t.bn.gamma_off,
                             n.grads + t.bn.beta_off, pb.corrA, pb.corrB, st));
   } else {
     RXB_TRY(stem_pool_bwd(n.dX0, n.pool_idx, n.S0, c.B, n.Hs, n.Ws, n.bn0.fold, n.dy0, n.bn0.dsum, n.bn0.dsq, st));
     const float cnt = (float)((long long)c.B * n.Hs * n.Ws);
-    RXB_TRY(bn_bwd_finalize(1, 0, n.bn0.dsum, n.bn0.dsq, n.bn0.fold, cnt, 64, n.grads + n.bn0.gamma_off,
+    RXB_TRY(bn_bwd_finalize(1, nullptr, nullptr, 0, 0, n.bn0.dsum, n.bn0.dsq, n.bn0.fold, cnt, 64,
+                            n.grads + n.bn0.gamma_off,
                             n.grads + n.bn0.beta_off, nullptr, nullptr, st));
     RXB_TRY(bn_bwd_apply(n.dy0, n.S0, (long long)c.B * n.Hs * n.Ws, 64, n.bn0.fold, n.bn0.dsum, n.bn0.dsq, st));
     RXB_TRY(conv_wgrad_any(c.B, n.Hs, n.Ws, static_cast<const __nv_bfloat16*>(input), 32, 32, 4, 2, nullptr, n.dy0, 64,

@@ -301,16 +301,49 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
 }
 
 // ------------------------------------------------------------------------------------------------ BN bwd finalize
-__global__ void bn_bwd_finalize_kernel(int mode, int q_is_raw, float* __restrict__ dsum, float* __restrict__ dsq,
-                                       BnFold f, float count, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ corrA,
-                                       float* __restrict__ corrB) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// sum_p dy*x of input channel c from the finished weight gradient of the conv that consumed relu(scale*x+shift):
+// sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap] with z = scale*x+shift, so sum dy*x = (W.dW - shift*sum dy)/scale.
+// One warp per channel (the K*taps products are strided through the OIHW tensors); every lane returns the result.
+__device__ __forceinline__ float sum_dyx_from_wdw(const float* __restrict__ W, const float* __restrict__ dW, int K, int C,
+                                                  int taps, int c, float es, float eh, float sum_dy, int lane) {
+  float t = 0.f;
+  const int n = K * taps;
+  for (int i = lane; i < n; i += 32) {
+    const int k = i / taps, tp = i - k * taps;
+    const long long at = ((long long)k * C + c) * taps + tp;
+    t = fmaf(__ldg(W + at), __ldg(dW + at), t);
+  }
+  t = warp_sum(t);
+  return es != 0.f ? (t - eh * sum_dy) / es : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+sum_dyx_from_wdw_kernel(const float* __restrict__ W, const float* __restrict__ dW, int K, int C, int taps,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ sum_dy, float* __restrict__ out) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane);
+  if (lane == 0) out[c] = r;
+}
+
+// one warp per channel
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __restrict__ dW, int K, int taps,
+                       float* __restrict__ dsum, float* __restrict__ dsq, BnFold f, float count, int C,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ corrA,
+                       float* __restrict__ corrB) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   const float s = dsum[c];
-  float q = dsq[c];
-  // the dgrad epilogue reduces sum(dy * x) with the raw activation: sum(dy*xhat) = rstd * (sum(dy*x) - mean*sum(dy))
-  if (q_is_raw) q = f.rstd[c] * (q - f.mean[c] * s);
+  float q;
+  if (W) {
+    const float raw = sum_dyx_from_wdw(W, dW, K, C, taps, c, f.scale[c], f.shift[c], s, lane);
+    q = f.rstd[c] * (raw - f.mean[c] * s);                       // sum dy*xhat
+  } else {
+    q = dsq[c];
+  }
+  if (lane != 0) return;
   dgamma[c] = q;
   dbeta[c] = s;
   const float m1 = s / count, m2 = q / count;
@@ -323,11 +356,11 @@ __global__ void bn_bwd_finalize_kernel(int mode, int q_is_raw, float* __restrict
   }
 }
 
-int bn_bwd_finalize(int mode, int q_is_raw, float* dsum, float* dsq, BnFold f, float count, int C, float* dgamma,
-                    float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
+int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, float* dsum, float* dsq, BnFold f,
+                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mode, q_is_raw, dsum, dsq, f, count, C, dgamma, dbeta, corrA,
-                                                          corrB);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(mode, W, dW, K, taps, dsum, dsq, f, count, C, dgamma, dbeta,
+                                                        corrA, corrB);
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -605,6 +638,14 @@ int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* j
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
   repack_kernel<<<dim3(gx, n_jobs), 256, 0, st>>>(params, arena, jobs_dev);
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
+                            const float* shift, const float* sum_dy, float* out, cudaStream_t st) {
+  RXB_PROF(st, PROF_ELEMENTWISE);
+  sum_dyx_from_wdw_kernel<<<ceil_div(C, 8), 256, 0, st>>>(W, dW, K, C, taps, scale, shift, sum_dy, out);
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

@@ -40,13 +40,20 @@ int final_bn_relu_gap(const __nv_bfloat16* X, int ldx, int B, int HW, int C, con
 int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int ldx, int B, int H, int W, int C,
                      BnFold f, __nv_bfloat16* G, float* dsum, float* dsq, cudaStream_t st);
 
-// After the reductions of one BatchNorm's backward are complete (dsum = sum dy; dsq = sum dy*xhat, or
-// sum dy*x with the raw activation when q_is_raw — converted here with the fold's mean/rstd):
+// After the reductions of one BatchNorm's backward are complete (dsum = sum dy; dsq = sum dy*xhat):
 //   dgamma = sum dy*xhat ; dbeta = sum dy
 //   mode 0 (consumer of a concat buffer): corrA[c] += scale*dsum/M ; corrB[c] += scale*dsq/M
 //   mode 1 (single consumer):             dsum[c] = dsum/M ; dsq[c] = dsq/M    (consumed by bn_bwd_apply)
-int bn_bwd_finalize(int mode, int q_is_raw, float* dsum, float* dsq, BnFold f, float count, int C, float* dgamma,
-                    float* dbeta, float* corrA, float* corrB, cudaStream_t st);
+// When W/dW are given (the conv that consumed relu(bn(x)), fp32 OIHW [K][C][taps] weights and their finished
+// gradient), dsq is not read: with z = scale*x+shift and dz = dy,  sum_p dy*z = sum_{k,tap} W*dW  per input
+// channel (both sides equal sum_p dL/dA' * A'), hence sum dy*x = (W.dW - shift*sum dy)/scale.  The dgrad kernel
+// therefore only reduces sum dy.
+int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, float* dsum, float* dsq, BnFold f,
+                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, cudaStream_t st);
+
+// out[c] = sum_p dy*x per input channel from W.dW (see above); the standalone form behind rxb_bn_sum_dyx_from_wdw.
+int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
+                            const float* shift, const float* sum_dy, float* out, cudaStream_t st);
 
 // dx[p,c] = scale[c] * (dy[p,c] - m1[c] - xhat[p,c]*m2[c]) in place on dy (bf16 [M,C] dense).
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,

@@ -200,7 +200,8 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     """Data gradient fused with the ReLU/BatchNorm backward of the layer that produced the conv input.
     dOut bf16 [B,H,W,ldD]; Wt bf16 [ty,tx,Cout,Cin] = the dgrad operand (tap-flipped, transposed weights);
     X bf16 [B,H,W,ldX] raw activation whose relu(bn(.)) fed the conv (channels 0..Cout).
-    Returns (out bf16 [B,H,W,ldC], sum_dy f32 [Cout], sum_dyx f32 [Cout])."""
+    Returns (out bf16 [B,H,W,ldC], sum_dy f32 [Cout]); the second BatchNorm-backward reduction comes from
+    bn_sum_dyx_from_wdw."""
     require_gpu()
     dOut = _cuda(dOut, torch.bfloat16)
     Wt = _cuda(Wt, torch.bfloat16)
@@ -212,8 +213,20 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
         out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=dOut.device)
     ldC = out.shape[-1]
     s1 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
-    s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
     d = _desc(B, H, W, Cin, ldD, Cout, ldC, 0, (ty, tx), pad, False, True)
     check(load().rxb_conv_dgrad_bn(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1], ptr(_cuda(bn_scale)),
-                                   ptr(_cuda(bn_shift)), out_mode, ptr(out), ptr(s1), ptr(s2), stream_ptr()))
-    return out, s1, s2
+                                   ptr(_cuda(bn_shift)), out_mode, ptr(out), ptr(s1), stream_ptr()))
+    return out, s1
+
+
+def bn_sum_dyx_from_wdw(W, dW, bn_scale, bn_shift, sum_dy):
+    """sum_p dy*x per input channel of a conv from its fp32 OIHW weights and finished weight gradient."""
+    require_gpu()
+    W = _cuda(W, torch.float32)
+    dW = _cuda(dW, torch.float32)
+    Cout, Cin = W.shape[0], W.shape[1]
+    taps = W.numel() // (Cout * Cin)
+    out = torch.empty(Cin, dtype=torch.float32, device=W.device)
+    check(load().rxb_bn_sum_dyx_from_wdw(ptr(W), ptr(dW), Cout, Cin, taps, ptr(_cuda(bn_scale)), ptr(_cuda(bn_shift)),
+                                         ptr(_cuda(sum_dy)), ptr(out), stream_ptr()))
+    return out

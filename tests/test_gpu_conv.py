@@ -145,16 +145,50 @@ def test_conv_dgrad_bn_matches_torch(cuda, B, H, W, Cd, Cx, ldX, k, out_mode):
     else:
         ref = G0[..., :Cx].float() + s * dy
     out = G0.clone().to(cuda)
-    out, s1, s2 = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
-                                    out_mode=out_mode, out=out, pad=(pad, pad))
+    out, s1 = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
+                                out_mode=out_mode, out=out, pad=(pad, pad))
     torch.cuda.synchronize()
     got = out[..., :Cx].float().cpu()
     err = (got - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item(), "max err %g vs %g" % (err, ref.abs().max().item())
     assert torch.equal(out[..., Cx:].cpu(), G0[..., Cx:]), "channels beyond Cout must stay untouched"
     d64 = dy.double().reshape(-1, Cx)
-    x64 = xv.double().reshape(-1, Cx)
-    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=2e-3,
-                               atol=2e-3 * d64.abs().sum(0).max().item())
-    np.testing.assert_allclose(s2.cpu().numpy(), (d64 * x64).sum(0).numpy(), rtol=2e-3,
-                               atol=2e-3 * (d64 * x64).abs().sum(0).max().item())
+    # the kernel sums the bf16-rounded staged tile on the tensor pipe (fp32 accumulate)
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=4e-3,
+                               atol=4e-3 * d64.abs().sum(0).max().item())
+
+
+@pytest.mark.parametrize("k,Cin,Cout", [(1, 96, 128), (3, 128, 32)])
+def test_bn_backward_sums_from_wdw(cuda, k, Cin, Cout):
+    """The BatchNorm-backward reduction sum(dy*x) recovered from W.dW equals the direct reduction: forward
+    A' = relu(s*x+h) -> conv(W); wgrad gives dW; dgrad gives dy and sum(dy); sum(dy*x) = (W.dW - h*sum dy)/s."""
+    B, H, W_ = 2, 16, 16
+    gen = torch.Generator().manual_seed(100 + k)
+    X = _rand_bf16((B, H, W_, Cin), gen)
+    s = torch.rand(Cin, generator=gen) + 0.5
+    h = torch.randn(Cin, generator=gen) * 0.3
+    Wc = _rand_bf16((Cout, Cin, k, k), gen, scale=(Cin * k * k) ** -0.5)       # forward weights (bf16-exact)
+    dOut = _rand_bf16((B, H, W_, Cout), gen)
+    pad = k // 2
+    dW = ops.conv_wgrad(X.to(cuda), dOut.to(cuda), Cin, Cout, taps=(k, k), pad=(pad, pad), scale=s.to(cuda),
+                        shift=h.to(cuda))
+    # dgrad operand: Wt[tap_flipped][cin][cout]
+    Wd = Wc.flip(2, 3).permute(1, 0, 2, 3).contiguous()                          # [Cin, Cout, k, k]
+    out, s1 = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wd).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cin,
+                                out_mode=0, pad=(pad, pad))
+    s2 = ops.bn_sum_dyx_from_wdw(Wc.float().to(cuda), dW, s.to(cuda), h.to(cuda), s1)
+    torch.cuda.synchronize()
+    # reference in fp64 through autograd
+    x = X.double().permute(0, 3, 1, 2).requires_grad_(True)
+    z = x * s.double().view(1, -1, 1, 1) + h.double().view(1, -1, 1, 1)
+    a = torch.relu(z).detach().to(torch.bfloat16).double() + (torch.relu(z) - torch.relu(z).detach())  # bf16 value, relu grad
+    y = F.conv2d(a, Wc.double(), padding=pad)
+    z.retain_grad()
+    y.backward(dOut.double().permute(0, 3, 1, 2))
+    dy = z.grad                                                                   # [B,Cin,H,W]
+    ref_s1 = dy.sum((0, 2, 3))
+    ref_s2 = (dy * x.detach()).sum((0, 2, 3))
+    scale1 = dy.abs().sum((0, 2, 3)).max().item()
+    np.testing.assert_allclose(s1.cpu().numpy(), ref_s1.numpy(), rtol=4e-3, atol=4e-3 * scale1)
+    scale2 = (dy * x.detach()).abs().sum((0, 2, 3)).max().item()
+    np.testing.assert_allclose(s2.cpu().numpy(), ref_s2.numpy(), rtol=1e-2, atol=1e-2 * scale2)
