@@ -107,31 +107,37 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
 // (bx, by, bb) is the image coordinate of box row 0; box rows run x fastest, then y (box_h rows), then image.
 // Rows whose pixel lies outside the image keep the zeros TMA wrote (conv zero padding); boxes entirely
 // inside the image take the path without per-row coordinate arithmetic.
-__device__ __forceinline__ void transform_chunk(uint4* p, const float (&s)[8], const float (&h)[8]) {
+// relu(x*s + h) on two packed bf16 lanes in ONE instruction (single rounding of the exact fused result; the
+// BatchNorm scale/shift are rounded to bf16 like every other GEMM operand).
+__device__ __forceinline__ uint32_t fma_relu_bf16x2(uint32_t x, uint32_t s, uint32_t h) {
+  uint32_t d;
+  asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
+  return d;
+}
+
+__device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4], const uint32_t (&h)[4]) {
   uint4 v = *p;
-  uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float lo = fmaxf(fmaf(bf16_lo(w[e]), s[2 * e], h[2 * e]), 0.f);
-    float hi = fmaxf(fmaf(bf16_hi(w[e]), s[2 * e + 1], h[2 * e + 1]), 0.f);
-    w[e] = pack_bf16x2(lo, hi);
-  }
-  *p = make_uint4(w[0], w[1], w[2], w[3]);
+  v.x = fma_relu_bf16x2(v.x, s[0], h[0]);
+  v.y = fma_relu_bf16x2(v.y, s[1], h[1]);
+  v.z = fma_relu_bf16x2(v.z, s[2], h[2]);
+  v.w = fma_relu_bf16x2(v.w, s[3], h[3]);
+  *p = v;
 }
 
 __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
                                                     const PixelTiling& til, int box_h, int bx, int by, int bb) {
   const int j = t & 7;
-  float s[8], h[8];
+  uint32_t s[4], h[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    s[e] = sc[j * 8 + e];
-    h[e] = sh[j * 8 + e];
+  for (int e = 0; e < 4; ++e) {
+    s[e] = pack_bf16x2(sc[j * 8 + 2 * e], sc[j * 8 + 2 * e + 1]);
+    h[e] = pack_bf16x2(sh[j * 8 + 2 * e], sh[j * 8 + 2 * e + 1]);
   }
   const int tw = 1 << til.tw_log2, tb = 1 << til.tb_log2;
   const bool interior = bx >= 0 && bx + tw <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
   if (interior) {
+#pragma unroll 4
     for (int row = t >> 3; row < rows; row += kRowsPerIter)
       transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
   } else {
@@ -729,41 +735,94 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (tile_end > tile_begin) {
       ptx::mbar_wait(&aux->tmem_full, 0, 14);
       ptx::tcgen05_fence_after();
-      const int ib = row / p.bkc, ch_in = row - ib * p.bkc;
-      for (int cl = 0; cl < n_local; ++cl) {
-        int tp, ch;
-        bool ok;
+      const int et = threadIdx.x - 64;
+      if (p.bulk_out) {
+        // Every MMA of this CTA has completed, so the pipeline stages are dead: the fp32 result is transposed into
+        // them in the order torch's OIHW gradient has in memory and leaves as contiguous L2 reduce-adds issued by
+        // the TMA engine (cp.reduce.async.bulk), one per output channel n, instead of 4-byte atomics.
+        float* stg = reinterpret_cast<float*>(smem);
         if (p.shift_dout) {
-          tp = cl;
-          ch = row;
-          ok = ch < p.cin;
-        } else {
-          const int kk = (chunk0 + cl) * p.boxes_per_chunk + ib;
-          tp = kk / p.boxes_per_tap;
-          ch = (kk - tp * p.boxes_per_tap) * p.bkc + ch_in;
-          ok = kk < total_boxes && ch < p.cin;
-        }
-        long long base = 0, nstride = 0;
-        if (p.w_mode == 0) {
-          base = (long long)ch * taps + tp;
-          nstride = (long long)p.cin * taps;
-        } else {  // space-to-depth stem: tap (sy,sx) of 4x4, ch = (py*2+px)*8 + c  ->  W[n][c][dy][dx], 7x7, 6 ch
-          const int sy = tp / p.taps_x, sx = tp - sy * p.taps_x;
-          const int c = ch & 7, px = (ch >> 3) & 1, py = (ch >> 4) & 1;
-          const int dy = 2 * sy + py - 1, dx = 2 * sx + px - 1;
-          ok = ok && c < 6 && dy >= 0 && dy < 7 && dx >= 0 && dx < 7;
-          base = ((long long)c * 7 + dy) * 7 + dx;
-          nstride = 6 * 49;
-        }
-        for (int c = 0; c < p.n; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cl * p.n + c, r);
-          ptx::tmem_ld_wait();
-          if (ok) {
+          const int rowlen = p.cin * taps;   // floats of one n row: [cin][taps]
+          for (int tp = 0; tp < taps; ++tp) {
+            for (int c = 0; c < p.n; c += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + tp * p.n + c, r);
+              ptx::tmem_ld_wait();
+              if (row < p.cin) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float g = __uint_as_float(r[i]);
-              if (g != 0.f) atomicAdd(p.dW + (long long)(p.n_off + c + i) * nstride + base, g);
+                for (int i = 0; i < 32; ++i) stg[(size_t)(c + i) * rowlen + row * taps + tp] = __uint_as_float(r[i]);
+              }
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int n = et; n < p.n; n += 128)
+            ptx::bulk_reduce_add_f32(p.dW + (long long)(p.n_off + n) * rowlen, stg + (size_t)n * rowlen, rowlen * 4);
+          ptx::tma_store_commit();
+        } else {
+          // 1x1: chunk cl holds input channels [ (chunk0+cl)*128, +128 )
+          const int nbuf = p.bulk_bufs;
+          for (int cl = 0; cl < n_local; ++cl) {
+            const int ch0 = (chunk0 + cl) * 128;
+            const int valid = min(128, p.cin - ch0);
+            float* sb = stg + (size_t)(cl % nbuf) * p.n * 128;
+            if (cl >= nbuf) {  // the reduce that read this buffer nbuf chunks ago must be done with shared memory
+              if (nbuf == 2) ptx::tma_store_wait_read_pending<1>(); else ptx::tma_store_wait_read_pending<0>();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            for (int c = 0; c < p.n; c += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cl * p.n + c, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sb[(c + i) * 128 + row] = __uint_as_float(r[i]);
+            }
+            ptx::fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (valid > 0)
+              for (int n = et; n < p.n; n += 128)
+                ptx::bulk_reduce_add_f32(p.dW + (long long)(p.n_off + n) * p.cin + ch0, sb + n * 128, valid * 4);
+            ptx::tma_store_commit();
+          }
+        }
+        ptx::tma_store_wait_all();
+      } else {
+        const int ib = row / p.bkc, ch_in = row - ib * p.bkc;
+        for (int cl = 0; cl < n_local; ++cl) {
+          int tp, ch;
+          bool ok;
+          if (p.shift_dout) {
+            tp = cl;
+            ch = row;
+            ok = ch < p.cin;
+          } else {
+            const int kk = (chunk0 + cl) * p.boxes_per_chunk + ib;
+            tp = kk / p.boxes_per_tap;
+            ch = (kk - tp * p.boxes_per_tap) * p.bkc + ch_in;
+            ok = kk < total_boxes && ch < p.cin;
+          }
+          long long base = 0, nstride = 0;
+          if (p.w_mode == 0) {
+            base = (long long)ch * taps + tp;
+            nstride = (long long)p.cin * taps;
+          } else {  // space-to-depth stem: tap (sy,sx) of 4x4, ch = (py*2+px)*8 + c  ->  W[n][c][dy][dx], 7x7, 6 ch
+            const int sy = tp / p.taps_x, sx = tp - sy * p.taps_x;
+            const int c = ch & 7, px = (ch >> 3) & 1, py = (ch >> 4) & 1;
+            const int dy = 2 * sy + py - 1, dx = 2 * sx + px - 1;
+            ok = ok && c < 6 && dy >= 0 && dy < 7 && dx >= 0 && dx < 7;
+            base = ((long long)c * 7 + dy) * 7 + dx;
+            nstride = 6 * 49;
+          }
+          for (int c = 0; c < p.n; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cl * p.n + c, r);
+            ptx::tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float g = __uint_as_float(r[i]);
+                if (g != 0.f) atomicAdd(p.dW + (long long)(p.n_off + c + i) * nstride + base, g);
+              }
             }
           }
         }
@@ -945,6 +1004,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
   p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;
+  const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int chunk_groups;
   if (p.shift_dout) {
     p.n_chunks = 1;
@@ -952,13 +1012,25 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
     chunk_groups = 1;
   } else {
     p.n_chunks = ceil_div(taps * p.boxes_per_tap, p.boxes_per_chunk);
-    p.chunks_per_cta = 512 / p.n;
-    if (p.chunks_per_cta > p.n_chunks) p.chunks_per_cta = p.n_chunks;
+    const int max_cpc = 512 / p.n < p.n_chunks ? 512 / p.n : p.n_chunks;
+    // Every CTA adds its partial dW into global memory, so the reduce traffic is (pixel-split CTAs) x |dW|, while
+    // every channel group re-reads dOut.  Pick the chunks-per-CTA that minimises the modelled traffic.
+    const double dw_bytes = (double)taps * p.boxes_per_tap * p.bkc * p.n * 4.0;
+    const double dout_bytes = (double)m_tiles * 128.0 * p.n * 2.0;
+    double best = 0;
+    p.chunks_per_cta = max_cpc;
+    for (int cpc = 1; cpc <= max_cpc; ++cpc) {
+      const int cg = ceil_div(p.n_chunks, cpc);
+      int pc = num_sms() / cg;
+      if (pc < 1) pc = 1;
+      if (pc > m_tiles) pc = m_tiles;
+      const double cost = 2.0 * pc * dw_bytes + (double)cg * dout_bytes;
+      if (cpc == 1 || cost < best) { best = cost; p.chunks_per_cta = cpc; }
+    }
     chunk_groups = ceil_div(p.n_chunks, p.chunks_per_cta);
   }
   if (p.prologue && p.boxes_per_tap * p.bkc > kMaxPrologueC + 64)
     return set_error(RXB_ERR_INVALID, "conv_wgrad: cin too large");
-  const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int pix_ctas = num_sms() / chunk_groups;
   if (pix_ctas < 1) pix_ctas = 1;
   if (pix_ctas > m_tiles) pix_ctas = m_tiles;
@@ -978,6 +1050,18 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_wgrad: tile too large for shared memory");
   const size_t smem = (size_t)stages * (kWgA_BYTES + b_bytes) + sizeof(WgradAux) + 1024;
+  // result leaves through shared memory as bulk reduce-adds when its global layout is contiguous per output
+  // channel: 1x1 filters, or the shifted-dOut multi-tap mode; the staging area is the dead pipeline
+  const size_t pipe_bytes = (size_t)stages * (kWgA_BYTES + b_bytes);
+  p.bulk_out = 0;
+  p.bulk_bufs = 1;
+  if (p.w_mode == 0 && p.cin % 8 == 0) {
+    if (p.shift_dout && (size_t)p.n * p.cin * taps * 4 <= pipe_bytes) p.bulk_out = 1;
+    if (!p.shift_dout && taps == 1 && p.bkc == 64 && (size_t)p.n * 512 <= pipe_bytes) {
+      p.bulk_out = 1;
+      p.bulk_bufs = (size_t)p.n * 1024 <= pipe_bytes ? 2 : 1;
+    }
+  }
   RXB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RXB_PROF(stream, PROF_CONV_WGRAD);
   conv_wgrad_kernel<<<dim3(pix_ctas, chunk_groups), kGemmThreads, smem, stream>>>(tmA, tmD, p, stages);

@@ -76,6 +76,8 @@ struct WgradParams {
   float* dW;            // fp32, torch OIHW [Cout_total][cin_w][taps_y_w][taps_x_w], atomically accumulated
   int cout_total;
   int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch)
+  int bulk_out;         // 1: result staged in shared memory and added to dW by cp.reduce.async.bulk (else fp32 atomics)
+  int bulk_bufs;        // staging buffers for the 1x1 bulk path (1 or 2)
 };
 // A: bf16 [B,H,W,ldA]; dOut: bf16 [B,H,W,ldD].
 int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* dOut, long long ldD,

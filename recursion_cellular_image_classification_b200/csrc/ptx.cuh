@@ -107,6 +107,13 @@ __device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* 
       ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// dst[0..bytes) += src[0..bytes) as fp32, contiguous, executed by the TMA engine as L2 reductions (bytes % 16 == 0,
+// both 16-byte aligned).  Completion is tracked by the bulk async-group like a TMA store.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst_global, const float* src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(dst_global)), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all prior bulk stores of this thread have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

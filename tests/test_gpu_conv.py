@@ -17,8 +17,11 @@ def _rand_bf16(shape, gen, scale=1.0):
 def _ref_conv(A_nhwc, W_oihw, pad, scale=None, shift=None):
     x = A_nhwc.float().permute(0, 3, 1, 2)
     if scale is not None:
+        # the kernel applies the fold as ONE packed-bf16 fused multiply-add + ReLU in shared memory: scale and shift
+        # are bf16 operands, the exact fused result is rounded once to the bf16 the MMA reads
+        scale, shift = scale.bfloat16().float(), shift.bfloat16().float()
         x = torch.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
-        x = x.to(torch.bfloat16).float()     # the kernel feeds the MMA bf16
+        x = x.to(torch.bfloat16).float()
     return F.conv2d(x, W_oihw.float(), padding=pad).permute(0, 2, 3, 1)
 
 
@@ -99,7 +102,8 @@ def test_conv_wgrad_matches_torch(cuda, B, H, W, Cin, ldA, Cout, k, prologue):
     pad = {1: 0, 3: 1, 4: 2}[k]
     x = A[..., :Cin].float().permute(0, 3, 1, 2)
     if prologue:
-        x = torch.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+        sb, hb = scale.bfloat16().float(), shift.bfloat16().float()     # bf16 fold operands (see _ref_conv)
+        x = torch.relu(x * sb.view(1, -1, 1, 1) + hb.view(1, -1, 1, 1)).to(torch.bfloat16).float()
     x = x.double().requires_grad_(False)
     w = torch.zeros(Cout, Cin, k, k, dtype=torch.double, requires_grad=True)
     y = F.conv2d(x, w, padding=pad)[:, :, :H, :W]
