@@ -125,7 +125,7 @@ __device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4]
 }
 
 __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
-                                                    const PixelTiling& til, int box_h, int bx, int by, int bb) {
+                                                    const PixelTiling& til, int box_w, int box_h, int bx, int by, int bb) {
   const int j = t & 7;
   uint32_t s[4], h[4];
 #pragma unroll
@@ -133,8 +133,8 @@ __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, con
     s[e] = pack_bf16x2(sc[j * 8 + 2 * e], sc[j * 8 + 2 * e + 1]);
     h[e] = pack_bf16x2(sh[j * 8 + 2 * e], sh[j * 8 + 2 * e + 1]);
   }
-  const int tw = 1 << til.tw_log2, tb = 1 << til.tb_log2;
-  const bool interior = bx >= 0 && bx + tw <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
+  const int tb = 1 << til.tb_log2;
+  const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
   if (interior) {
 #pragma unroll 4
@@ -142,8 +142,8 @@ __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, con
       transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
   } else {
     for (int row = t >> 3; row < rows; row += kRowsPerIter) {
-      const int xi = row & (tw - 1);
-      const int r2 = row >> til.tw_log2;
+      const int r2 = row / box_w;
+      const int xi = row - r2 * box_w;
       const int yi = r2 % box_h, bi = r2 / box_h;
       const int x = bx + xi, y = by + yi, b = bb + bi;
       if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
@@ -193,7 +193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = p.stages;
   const int taps = p.taps_x * p.taps_y;
-  const int tps = p.halo ? p.taps_y : 1;                       // row taps served by one stage
+  const int tps = p.halo == 1 ? p.taps_y : 1;                  // row taps served by one stage of streamed weights
   const int a_tx = p.rows_a * ROW_BYTES;                       // bytes TMA delivers per A stage
   const int a_stage = (a_tx + 1023) & ~1023;
   const int b_tap = p.bn * ROW_BYTES;                          // one (tap, k-block) weight tile
@@ -214,9 +214,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int n0 = blockIdx.y * p.bn;
-  const int groups = p.halo ? p.taps_x : taps;
+  const int groups = p.halo == 2 ? 1 : p.halo == 1 ? p.taps_x : taps;  // A loads per k-block
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
+  const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;
   const int n_epi_threads = dgrad ? 256 : 128;                 // dgrad: warps 6-13 ; store: warps 2-5
 
   // ---- one-time setup
@@ -292,7 +293,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              n0 + bx * cw, x0, y0, b0);
         }
         for (int g = 0; g < groups; ++g) {
-          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo ? g : g - gy * p.taps_x;
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo == 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 1);
             ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + (p.b_resident ? 0 : b_stage));
@@ -300,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              y0 + gy - p.pad_y, b0);
             if (!p.b_resident) {
               for (int ty = 0; ty < tps; ++ty) {
-                const int tap = p.halo ? ty * p.taps_x + gx : g;
+                const int tap = p.halo == 1 ? ty * p.taps_x + gx : g;
                 ptx::tma_load_3d(smB + (size_t)stage * b_stage + ty * b_tap, &tmB, &aux->full[stage], kb * BK, n0, tap);
               }
             }
@@ -317,6 +318,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t row_tap16 = ((uint32_t)tw * ROW_BYTES) >> 4;  // one image row of the box, in descriptor units
       const uint64_t desc0 = ptx::make_smem_desc(0, 16, kSBO, kSwz);
       const uint32_t d_hi = ptx::desc_hi(desc0), d_lo0 = ptx::desc_lo(desc0);
+      // full-halo A box: the 8 pixels of a core-matrix group are one tile row, consecutive tile rows lie box_w box
+      // rows apart, and a tap (ty,tx) is a start offset of ty*box_w+tx rows (the 128B swizzle follows the absolute
+      // shared-memory address, so unaligned starts and strides are exact - probed on B200, profiles/r01_umma_probe.log)
+      const uint32_t a_hi = p.halo == 2 ? ptx::desc_hi(ptx::make_smem_desc(0, 16, (uint32_t)box_w * ROW_BYTES, kSwz)) : d_hi;
+      const uint32_t box_row16 = (uint32_t)ROW_BYTES >> 4;
       const uint32_t smA16 = ptx::smem_u32(smA) >> 4, smB16 = ptx::smem_u32(smB) >> 4;
       const uint32_t a_stage16 = (uint32_t)a_stage >> 4, b_stage16 = (uint32_t)b_stage >> 4, b_tap16 = (uint32_t)b_tap >> 4;
       // Column statistics of the stored tiles on the tensor pipe: with S = the staged bf16 tile [128 px][128 ch],
@@ -364,15 +370,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tcgen05_fence_after();
             if (ptx::elect_one()) {
               const uint32_t a_lo = d_lo0 + smA16 + (uint32_t)stage * a_stage16;
-              for (int ty = 0; ty < tps; ++ty) {
-                const int tap = p.halo ? ty * p.taps_x + g : g;
-                const uint32_t b_lo = d_lo0 + smB16 + (p.b_resident ? (uint32_t)(tap * p.kb_per_tap + kb) * b_tap16
-                                                                    : (uint32_t)stage * b_stage16 + (uint32_t)ty * b_tap16);
-                const uint32_t a_lo_t = a_lo + (uint32_t)ty * row_tap16;
+              if (p.halo == 2) {
+                for (int tap = 0; tap < taps; ++tap) {
+                  const int ty = tap / p.taps_x, tx = tap - ty * p.taps_x;
+                  const uint32_t b_lo = d_lo0 + smB16 + (uint32_t)(tap * p.kb_per_tap + kb) * b_tap16;
+                  const uint32_t a_lo_t = a_lo + (uint32_t)(ty * box_w + tx) * box_row16;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                  ptx::umma_bf16_ss_parts(d_tmem, a_lo_t + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, accumulate);
-                  accumulate = 1;
+                  for (int k = 0; k < BK / 16; ++k) {
+                    ptx::umma_bf16_ss_parts(d_tmem, a_lo_t + 2 * k, a_hi, b_lo + 2 * k, d_hi, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+              } else {
+                for (int ty = 0; ty < tps; ++ty) {
+                  const int tap = p.halo ? ty * p.taps_x + g : g;
+                  const uint32_t b_lo = d_lo0 + smB16 + (p.b_resident ? (uint32_t)(tap * p.kb_per_tap + kb) * b_tap16
+                                                                      : (uint32_t)stage * b_stage16 + (uint32_t)ty * b_tap16);
+                  const uint32_t a_lo_t = a_lo + (uint32_t)ty * row_tap16;
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+                    ptx::umma_bf16_ss_parts(d_tmem, a_lo_t + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, accumulate);
+                    accumulate = 1;
+                  }
                 }
               }
               ptx::umma_commit(&aux->empty[stage]);
@@ -556,11 +575,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
         for (int g = 0; g < groups; ++g) {
-          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo ? g : g - gy * p.taps_x;
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo == 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
             transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
-                                t, p.t, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
+                                t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&aux->xform[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -850,7 +869,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ay += ty - p.pad_y;
             }
             transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale + c0,
-                                aux->s_shift + c0, t, p.t, th, ax, ay, b0);
+                                aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0);
           }
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&aux->xform[stage]);
@@ -876,10 +895,10 @@ static CUtensorMapSwizzle swizzle_for(int box_c) {
 
 // activation map: dims (channels, W, H, B) with channel stride 1 and pixel stride ld; box (box_c, tw, box_h, tb)
 static int make_act_tmap(CUtensorMap* tm, const void* base, const PixelTiling& t, int channels, long long ld,
-                         int box_c, int box_h) {
+                         int box_c, int box_h, int box_w = 0) {
   uint64_t dims[4] = {(uint64_t)channels, (uint64_t)t.W, (uint64_t)t.H, (uint64_t)t.B};
   uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * t.W, (uint64_t)ld * 2 * t.W * t.H};
-  uint32_t box[4] = {(uint32_t)box_c, 1u << t.tw_log2, (uint32_t)box_h, 1u << t.tb_log2};
+  uint32_t box[4] = {(uint32_t)box_c, box_w ? (uint32_t)box_w : 1u << t.tw_log2, (uint32_t)box_h, 1u << t.tb_log2};
   return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
                    swizzle_for(box_c));
 }
@@ -914,17 +933,26 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     if (tall.tb_log2 == 0 && tall.tw_log2 == 3) {
       p.t = tall;
       p.halo = 1;
+      // 128-byte rows: the whole (tw+taps_x-1) x (th+taps_y-1) neighbourhood is ONE box and every tap is a descriptor
+      // offset into it (the weight panel must then be resident: one A stage serves all taps of a k-block)
+      static const int dbg_no_full_halo = getenv("RXB_DBG_NO_FULL_HALO") ? atoi(getenv("RXB_DBG_NO_FULL_HALO")) : 0;
+      if (bk == 64 && !dbg_no_full_halo) p.halo = 2;
     }
   }
+  const int taps = p.taps_x * p.taps_y;
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
+  if (p.halo == 2) {
+    const long long panel = (long long)taps * p.kb_per_tap * p.bn * bk * 2;
+    if (panel > 96 * 1024) p.halo = 1;
+  }
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
-  p.rows_a = p.halo ? box_h * tw : 128;
+  const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;
+  p.rows_a = p.halo ? box_h * box_w : 128;
   if (box_h > 256) return set_error(RXB_ERR_INVALID, "conv_gemm: halo box too tall");
 
   CUtensorMap tmA, tmB, tmOut, tmX;
-  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h);
+  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h, box_w);
   if (rc) return rc;
-  const int taps = p.taps_x * p.taps_y;
   {
     uint64_t dims[3] = {(uint64_t)p.cin, (uint64_t)p.n_total, (uint64_t)taps};
     uint64_t strides[2] = {(uint64_t)p.cin * 2, (uint64_t)p.cin * 2 * p.n_total};
@@ -947,7 +975,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   const int row_bytes = bk * 2;
   const long long a_stage = (p.rows_a * row_bytes + 1023) & ~1023;
   const long long b_tap = (long long)p.bn * row_bytes;
-  const long long b_stage = (p.halo ? p.taps_y : 1) * b_tap;
+  const long long b_stage = (p.halo == 1 ? p.taps_y : 1) * b_tap;
   const long long b_panel = (long long)taps * p.kb_per_tap * b_tap;
   const long long stage_tile = 128ll * ceil_div(p.bn, cw) * cw * 2;
   const long long fixed = (long long)sizeof(GemmAux) + 1024 /*alignment*/ + 1024 /*ones*/ + (dgrad ? 2 * stage_tile : 0);
@@ -963,7 +991,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   static const int dbg_no_resident = getenv("RXB_DBG_NO_RESIDENT") ? atoi(getenv("RXB_DBG_NO_RESIDENT")) : 0;
   static const int dbg_one_stg = getenv("RXB_DBG_ONE_STG") ? atoi(getenv("RXB_DBG_ONE_STG")) : 0;
   const bool allow_res = !(dbg_no_resident == 1 || (dbg_no_resident == 2 && p.bn < 128));
-  if (allow_res && b_panel <= 96 * 1024 && m_tiles > gx && (avail - b_panel) / a_stage >= 3) {
+  if ((allow_res || p.halo == 2) && b_panel <= 96 * 1024 && (m_tiles > gx || p.halo == 2) &&
+      (avail - b_panel) / a_stage >= (p.halo == 2 ? 2 : 3)) {
     p.b_resident = 1;
     per_stage = a_stage;
     avail -= b_panel;
@@ -975,6 +1004,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   long long stages = avail / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
+  if (p.halo == 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
   p.stages = (int)stages;
   const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) + p.n_stg * stage_tile + fixed);
   dim3 grid(gx, p.n_tiles);

@@ -433,6 +433,8 @@ int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long
 }
 
 // ------------------------------------------------------------------------------------------------ stem pool bwd
+// One thread = 8 channels of a 2x2 block of stem pixels {2q,2q+1} x {2r,2r+1}: the four pooling windows that can
+// contain them (oy in {q,q+1}, ox in {r,r+1}) are loaded once, all loads are independent and issued up front.
 __global__ void __launch_bounds__(kEwThreads)
 stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __restrict__ idx,
                      const __nv_bfloat16* __restrict__ S0, int B, int Hs, int Ws, BnFold f,
@@ -440,7 +442,7 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
   __shared__ float sh[2 * 64];
   const int cg = threadIdx.x & 7;
   const int Ho = Hs >> 1, Wo = Ws >> 1;
-  const long long total = (long long)B * Hs * Ws;
+  const long long total = (long long)B * Ho * Wo;
   float sc[8], sf[8], mu[8], rs[8], as[8], aq[8];
   load8f(f.scale + cg * 8, sc);
   load8f(f.shift + cg * 8, sf);
@@ -448,45 +450,62 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
   load8f(f.rstd + cg * 8, rs);
 #pragma unroll
   for (int e = 0; e < 8; ++e) as[e] = aq[e] = 0.f;
-  for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < total; pix += (long long)gridDim.x * 32) {
-    const int x_ = (int)(pix % Ws);
-    const long long r = pix / Ws;
-    const int y_ = (int)(r % Hs);
-    const int b = (int)(r / Hs);
-    float g[8];
+  for (long long quad = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); quad < total; quad += (long long)gridDim.x * 32) {
+    const int r = (int)(quad % Wo);
+    const long long t = quad / Wo;
+    const int q = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    uint2 wi[2][2];
+    uint4 wd[2][2];
+    uint4 xs[2][2];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = 0.f;
-    // output windows that contain (y_, x_): oy in {y_>>1, (y_>>1)+1 if y_ odd}, same for x
-    for (int wy = 0; wy <= (y_ & 1); ++wy) {
-      const int oy = (y_ >> 1) + wy;
-      if (oy >= Ho) continue;
-      const int ky = y_ - (2 * oy - 1);
-      for (int wx = 0; wx <= (x_ & 1); ++wx) {
-        const int ox = (x_ >> 1) + wx;
-        if (ox >= Wo) continue;
-        const int kx = x_ - (2 * ox - 1);
-        const uint32_t code = (uint32_t)(ky * 3 + kx);
-        const long long op = ((long long)b * Ho + oy) * Wo + ox;
-        const uint2 ib = __ldg(reinterpret_cast<const uint2*>(idx + op * 64 + cg * 8));
-        float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dPool + op * 64 + cg * 8)), d);
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int oy = q + wy, ox = r + wx;
+        const bool ok = oy < Ho && ox < Wo;
+        const long long op = ((long long)b * Ho + (ok ? oy : q)) * Wo + (ok ? ox : r);
+        wi[wy][wx] = __ldg(reinterpret_cast<const uint2*>(idx + op * 64 + cg * 8));
+        wd[wy][wx] = __ldg(reinterpret_cast<const uint4*>(dPool + op * 64 + cg * 8));
+        if (!ok) wi[wy][wx] = make_uint2(0xffffffffu, 0xffffffffu);   // matches no window position
+      }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+        xs[py][px] = ld_stream_v4(S0 + (((long long)b * Hs + 2 * q + py) * Ws + 2 * r + px) * 64 + cg * 8);
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+        // window (q+wy, r+wx) contains pixel (2q+py, 2r+px) at ky = py - 2wy + 1, kx = px - 2wx + 1 (when in 0..2)
+#pragma unroll
+        for (int wy = 0; wy <= py; ++wy)
+#pragma unroll
+          for (int wx = 0; wx <= px; ++wx) {
+            const uint32_t code = (uint32_t)((py - 2 * wy + 1) * 3 + (px - 2 * wx + 1));
+            float d[8];
+            unpack8(wd[wy][wx], d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t w = e < 4 ? wi[wy][wx].x : wi[wy][wx].y;
+              if (((w >> (8 * (e & 3))) & 0xffu) == code) g[e] += d[e];
+            }
+          }
+        float x[8];
+        unpack8(xs[py][px], x);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const uint32_t w = e < 4 ? ib.x : ib.y;
-          if (((w >> (8 * (e & 3))) & 0xffu) == code) g[e] += d[e];
+          const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? g[e] : 0.f;
+          g[e] = dy;
+          as[e] += dy;
+          aq[e] += dy * ((x[e] - mu[e]) * rs[e]);
         }
+        st_stream_v4(dy0 + (((long long)b * Hs + 2 * q + py) * Ws + 2 * r + px) * 64 + cg * 8, pack8(g));
       }
-    }
-    float x[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(S0 + pix * 64 + cg * 8)), x);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? g[e] : 0.f;
-      g[e] = dy;
-      as[e] += dy;
-      aq[e] += dy * ((x[e] - mu[e]) * rs[e]);
-    }
-    *reinterpret_cast<uint4*>(dy0 + pix * 64 + cg * 8) = pack8(g);
   }
   block_channel_reduce(as, aq, cg, 64, dsum, dsq, sh);
 }
@@ -494,8 +513,8 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
 int stem_pool_bwd(const __nv_bfloat16* dPool, const uint8_t* idx, const __nv_bfloat16* S0, int B, int Hs, int Ws,
                   BnFold f, __nv_bfloat16* dy0, float* dsum, float* dsq, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  stem_pool_bwd_kernel<<<ew_grid((long long)B * Hs * Ws, 32 * 4), kEwThreads, 0, st>>>(dPool, idx, S0, B, Hs, Ws, f,
-                                                                                      dy0, dsum, dsq);
+  stem_pool_bwd_kernel<<<ew_grid((long long)B * (Hs / 2) * (Ws / 2), 32 * 2), kEwThreads, 0, st>>>(dPool, idx, S0, B, Hs,
+                                                                                                  Ws, f, dy0, dsum, dsq);
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
