@@ -255,6 +255,12 @@ def run_ours(args):
         step(False)
     torch.cuda.synchronize()
     loss_first = loss_dev.item()
+    # host time to ENQUEUE one step into an empty stream (no synchronisation inside): shows whether the step is
+    # launch-bound on the CPU side
+    t_h = time.perf_counter()
+    step(False)
+    host_enqueue_ms = (time.perf_counter() - t_h) * 1e3
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -269,6 +275,7 @@ def run_ours(args):
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "warmup": n_warm, "ms_per_step": ms / args.steps, "quick": True,
+                              "host_enqueue_ms": host_enqueue_ms,
                               "gpu_launches": int(launches)}), flush=True)
         if world > 1:
             dist.destroy_process_group()
@@ -350,7 +357,7 @@ def run_ours(args):
                            "lr": lr},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(host_src.numel()) * world, "d2h_bytes_per_step": 4 * world},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
                 "clocks": clocks,
                 "roofline": roofline, "hbm_kernels": hbm_kernels, "kernel_breakdown": breakdown,
                 "cpu_baseline": cpu,
@@ -365,7 +372,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU (SURVEY 8d sweep: 32/64/128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=4)

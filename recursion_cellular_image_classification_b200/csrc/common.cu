@@ -1,4 +1,5 @@
 // common.cu — error state, device check, launch counter.
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -18,6 +19,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 bool g_prof_on = false;
+bool g_pdl = getenv("RXB_PDL") && atoi(getenv("RXB_PDL")) != 0;   // measured: no gain on the DenseNet step
 namespace {
 struct ProfRec { cudaEvent_t a, b; int cat; };
 std::vector<ProfRec> g_prof;

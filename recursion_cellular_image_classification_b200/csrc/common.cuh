@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
+#include <utility>
 #include "../../include/rxb.h"
 
 namespace rxb {
@@ -51,6 +53,33 @@ struct ProfScope {
 #define RXB_PROF(stream, cat) rxb::ProfScope prof_scope__((stream), (cat))
 
 inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch.  Kernels of the training/inference executor are enqueued with
+// cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may become resident and run their private
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream drains;
+// pdl_sync() is the point after which they may touch global memory (the predecessor has completed and flushed).
+// EVERY kernel launched through launch_k must call pdl_sync() before its first global read or write.
+extern bool g_pdl;   // RXB_PDL=1 enables the attribute (default off: kernels serialise as usual and pdl_sync() is a no-op)
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 int num_sms();
 
 template <typename T>

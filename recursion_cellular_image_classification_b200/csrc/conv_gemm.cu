@@ -30,8 +30,15 @@
 
 namespace rxb {
 
-constexpr int kXformThreads = 256;                     // warps 6-13: A-operand transform, or the dgrad epilogue
-constexpr int kGemmThreads = 192 + kXformThreads;      // + TMA, MMA, 4 store-epilogue warps
+constexpr int kXformThreads = 256;                     // 8 A-operand transform warps
+constexpr int kGemmThreads = 192 + kXformThreads;      // wgrad kernel: TMA, MMA, 4 epilogue warps, 8 transform warps
+// forward / dgrad kernel: warp 0 TMA loads, warp 1 MMA issue, warp 2 TMA stores, warps 3-18 sixteen workers:
+//   store epilogue with A prologue : workers 0-7 transform the A operand, workers 8-15 are the epilogue
+//   store epilogue, no prologue    : workers 8-15 are the epilogue
+//   dgrad epilogue                 : all sixteen workers are the epilogue
+// (a worker's TMEM lane quarter is warp % 4; four consecutive warps cover the four quarters)
+constexpr int kConvThreads = 96 + 16 * 32;
+constexpr int kWorker0 = 3;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 128;   // TMEM columns per accumulator stage (bn <= 128)
 constexpr int kGramCol = 256;     // TMEM columns [256,384): running Gram matrix of the stored tiles (diag = sum of squares)
@@ -44,16 +51,18 @@ struct __align__(16) GemmAux {
   float s_shift[kMaxPrologueC + 64];
   float e_scale[kMaxBN];
   float e_shift[kMaxBN];
+  uint32_t e_thr2[kMaxBN / 2];   // dgrad ReLU mask as a packed-bf16 threshold test: (x ^ sgn) > thr, two columns per word
+  uint32_t e_sgn2[kMaxBN / 2];
   float s_stat[2][kMaxBN];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t epi_in_full[2];
-  uint64_t epi_in_empty[2];
-  uint64_t stg_full[2];    // staged output tile complete in shared memory (epilogue -> MMA warp)
-  uint64_t stg_free[2];    // statistics MMAs over the staged tile complete (MMA warp -> epilogue)
+  uint64_t epi_in_full[4];
+  uint64_t epi_in_empty[4];
+  uint64_t stg_full[4];    // staged output tile complete in shared memory (epilogue -> MMA warp, store warp)
+  uint64_t stg_free[4];    // store warp has read the staged tile and the statistics MMAs over it are complete
   uint64_t b_full;         // resident weights landed
   uint64_t stats_done;
   uint32_t tmem_base;
@@ -178,8 +187,38 @@ __device__ __forceinline__ uint4* staging_chunk(uint8_t* base, int cw, int row, 
   return reinterpret_cast<uint4*>(base + row * 64 + ((j ^ ((row >> 1) & 3)) << 4));
 }
 
+// Two packed-bf16 comparisons a > b in one instruction.
+__device__ __forceinline__ void gt_bf16x2(uint32_t a, uint32_t b, bool& lo, bool& hi) {
+  uint32_t l, h;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.bf16x2 p|q, %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\tselp.u32 %1, 1, 0, q;\n\t}"
+      : "=r"(l), "=r"(h)
+      : "r"(a), "r"(b));
+  lo = l != 0;
+  hi = h != 0;
+}
+// fp32 -> bf16 bits rounded toward -infinity (so that for every bf16 x:  x > t  <=>  x > round_down(t))
+__device__ __forceinline__ uint32_t bf16_round_down_bits(float t) {
+  const uint32_t u = __float_as_uint(t);
+  uint32_t b = u >> 16;
+  if ((u & 0x80000000u) && (u & 0xffffu) && (u & 0x7f800000u) != 0x7f800000u) b += 1;   // negative: truncation went up
+  return b & 0xffffu;
+}
+// ReLU mask of relu(es*x + eh) as a threshold on x: returns thr bits, sets sgn (0x8000 flips x when es < 0)
+__device__ __forceinline__ uint32_t relu_threshold_bits(float es, float eh, uint32_t& sgn) {
+  sgn = 0;
+  if (es > 0.f) return bf16_round_down_bits(-eh / es);             // x > -eh/es
+  if (es < 0.f) { sgn = 0x8000u; return bf16_round_down_bits(eh / es); }   // x < -eh/es  <=>  -x > eh/es
+  return eh > 0.f ? 0xff80u : 0x7f80u;                              // constant mask: thr = -inf (always) / +inf (never)
+}
+
+// development timeline: role r (0 producer, 1 mma, 2 epilogue leader), tile it < 16, event ev < 8
+#define RXB_TL(r, it, ev)                                                                         \
+  do {                                                                                            \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 16) p.dbg[((r) * 16 + (it)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
 template <int BK, bool PROLOGUE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p) {
@@ -206,8 +245,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smA = smem;
   uint8_t* smB = smA + (size_t)stages * a_stage;
   uint8_t* st_out = smB + b_total;
-  uint8_t* st_x = st_out + p.n_stg * stage_tile;
-  uint8_t* ones = st_x + (dgrad ? 2 * stage_tile : 0);        // 1 KB of bf16 1.0: B operand of the column-sum MMA
+  // dgrad: the two activation-tile buffers double as the output staging (the epilogue overwrites x in place)
+  uint8_t* st_x = st_out;
+  uint8_t* ones = st_out + p.n_stg * stage_tile;   // 1 KB of bf16 1.0: B operand of the column-sum MMA
   GemmAux* aux = reinterpret_cast<GemmAux*>(ones + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,7 +258,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
   const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;
-  const int n_epi_threads = dgrad ? 256 : 128;                 // dgrad: warps 6-13 ; store: warps 2-5
+  const int n_epi_threads = dgrad ? 512 : 256;                 // dgrad: sixteen worker warps ; store: workers 8-15
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
@@ -233,35 +273,54 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
-      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads);
+      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 2);   // one epilogue group per accumulator stage
+    }
+    for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&aux->epi_in_full[a], 1);
-      ptx::mbar_init(&aux->epi_in_empty[a], 1);
+      ptx::mbar_init(&aux->epi_in_empty[a], p.mma_stats ? 2 : 1);   // dgrad: store warp has read it + stats MMAs done
       ptx::mbar_init(&aux->stg_full[a], 1);
-      ptx::mbar_init(&aux->stg_free[a], 1);
+      ptx::mbar_init(&aux->stg_free[a], p.mma_stats ? 2 : 1);   // store warp has read it (+ statistics MMAs done)
     }
     ptx::mbar_init(&aux->b_full, 1);
     ptx::mbar_init(&aux->stats_done, 1);
     ptx::fence_barrier_init();
   }
+  if (p.mma_stats) {
+    for (int i = threadIdx.x; i < 256; i += kConvThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
+  // everything above is private to the CTA and overlaps the previous kernel's drain; global memory from here on
+  pdl_sync();
   if (PROLOGUE) {
     const int padded = p.kb_per_tap * BK;
-    for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
+    for (int c = threadIdx.x; c < padded; c += kConvThreads) {
       aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
       aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
     }
   }
-  for (int c = threadIdx.x; c < kMaxBN; c += kGemmThreads) {
+  for (int c = threadIdx.x; c < kMaxBN; c += kConvThreads) {
     aux->s_stat[0][c] = 0.f;
     aux->s_stat[1][c] = 0.f;
     const bool in = dgrad && n0 + c < p.n_total;
     aux->e_scale[c] = in ? p.e_scale[n0 + c] : 0.f;
     aux->e_shift[c] = in ? p.e_shift[n0 + c] : 0.f;
   }
-  if (p.mma_stats) {
-    for (int i = threadIdx.x; i < 256; i += kGemmThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
-    ptx::fence_proxy_async_smem();
+  if (dgrad) {
+    for (int c2 = threadIdx.x; c2 < kMaxBN / 2; c2 += kConvThreads) {
+      uint32_t thr = 0, sg = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 2 * c2 + h;
+        uint32_t sg1 = 0, t1 = 0x7f80u;   // columns past n_total: never
+        if (n0 + c < p.n_total) t1 = relu_threshold_bits(p.e_scale[n0 + c], p.e_shift[n0 + c], sg1);
+        thr |= t1 << (16 * h);
+        sg |= sg1 << (16 * h);
+      }
+      aux->e_thr2[c2] = thr;
+      aux->e_sgn2[c2] = sg;
+    }
   }
-  if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -283,10 +342,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
+        RXB_TL(0, it, 0);
         if (dgrad) {
           // input of this tile's epilogue: the activation tile the consumer's BatchNorm saw (double-buffered)
-          const int xb = it & 1;
-          ptx::mbar_wait(&aux->epi_in_empty[xb], ((it >> 1) & 1) ^ 1, 6);
+          const int xb = it % p.n_stg;
+          ptx::mbar_wait(&aux->epi_in_empty[xb], ((it / p.n_stg) & 1) ^ 1, 6);
+          RXB_TL(0, it, 1);
           ptx::mbar_arrive_expect_tx(&aux->epi_in_full[xb], stage_tile);
           for (int bx = 0; bx < n_boxes; ++bx)
             ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, &aux->epi_in_full[xb],
@@ -308,6 +369,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
+        RXB_TL(0, it, 2);
       }
     }
   } else if (warp == 1) {
@@ -332,10 +394,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc_sum = ptx::make_idesc_bf16(128, 16, 1, 0);
       const uint64_t d_ones = ptx::make_smem_desc(ptx::smem_u32(ones), 128, 256, ptx::kSwizzleNone);
       auto issue_stats = [&](int j) {
-        const int sb = p.n_stg == 2 ? (j & 1) : 0;
-        const int use = p.n_stg == 2 ? (j >> 1) : j;
+        const int sb = j % p.n_stg;
+        const int use = j / p.n_stg;
         ptx::mbar_wait(&aux->stg_full[sb], use & 1, 8);
         ptx::tcgen05_fence_after();
+        if (lane == 0) RXB_TL(1, j, 3);
         if (ptx::elect_one()) {
           const uint64_t ds0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
                                                    ptx::kSwizzle128B);
@@ -346,7 +409,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (!dgrad) ptx::umma_bf16_ss(tmem_base + kGramCol, ds, ds, idesc_gram, accumulate);
             ptx::umma_bf16_ss(tmem_base + kSumCol, ds, d_ones, idesc_sum, accumulate);
           }
-          ptx::umma_commit(&aux->stg_free[sb]);
+          ptx::umma_commit(dgrad ? &aux->epi_in_empty[sb] : &aux->stg_free[sb]);
         }
         __syncwarp();
       };
@@ -362,6 +425,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
         ptx::mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1, 2);
         ptx::tcgen05_fence_after();
+        if (lane == 0) RXB_TL(1, it, 0);
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         uint32_t accumulate = 0;
         for (int g = 0; g < groups; ++g) {
@@ -403,6 +467,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (ptx::elect_one()) ptx::umma_commit(&aux->tmem_full[acc]);
         __syncwarp();
+        if (lane == 0) RXB_TL(1, it, 2);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         if (p.mma_stats && it > 0) issue_stats(it - 1);   // the previous tile's epilogue ran under this tile's main loop
@@ -413,33 +478,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (dgrad ? warp >= 6 : warp < 6) {
-    // =============================== epilogue: TMEM lanes (warp & 3) * 32 .. ; dgrad: two warps per lane quarter,
-    // each taking half of the columns
+  } else if (warp == 2) {
+    // =============================== TMA store warp: staged tile -> global, one TMA store (or L2 reduce-add into the
+    // running gradient) per 64-channel box, clipped at the tensor edges.  Keeps store issue and the wait for the
+    // TMA engine to drain the staging buffer off the epilogue warps' critical path.
+    if (lane == 0) {
+      int it = 0;
+      for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
+        int x0, y0, b0;
+        tile_origin(p.t, m_tile, x0, y0, b0);
+        const int sb = it % p.n_stg;
+        const int use = it / p.n_stg;
+        const uint8_t* so = st_out + (size_t)sb * stage_tile;
+        ptx::mbar_wait(&aux->stg_full[sb], use & 1, 16);
+        for (int bx = 0; bx < n_boxes; ++bx) {
+          if (n0 + bx * cw >= p.n_total) break;
+          if (dgrad && p.out_mode == OUT_G_ACCUM)
+            ptx::tma_reduce_add_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+          else
+            ptx::tma_store_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
+        }
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read();
+        ptx::mbar_arrive(dgrad ? &aux->epi_in_empty[sb] : &aux->stg_free[sb]);
+      }
+      ptx::tma_store_wait_all();
+    }
+  } else if (dgrad || warp >= kWorker0 + 8) {
+    // =============================== epilogue: two groups of warps take alternate tiles (group g owns TMEM accumulator
+    // stage g), so one group's TMEM reads overlap the other's arithmetic and shared-memory traffic.  Within a
+    // group a warp reads TMEM lanes (warp & 3) * 32 .. ; dgrad has two warps per lane quarter that split the
+    // 32-column chunks round-robin.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int half = dgrad ? (warp - 6) >> 2 : 0;
-    const int cols_per = dgrad ? p.bn >> 1 : p.bn;
-    const int c_begin = half * cols_per, c_end = c_begin + cols_per;
-    const bool leader = threadIdx.x == (dgrad ? 192 : 64);
-    const uint32_t bar_threads = (uint32_t)n_epi_threads;
-    int acc = 0;
+    const int first_epi_warp = dgrad ? kWorker0 : kWorker0 + 8;
+    const int warps_per_group = dgrad ? 8 : 4;
+    const int e = warp - first_epi_warp;
+    const int g2 = e / warps_per_group;                       // epilogue group = accumulator stage
+    const int grp = (e - g2 * warps_per_group) >> 2;          // column group inside the epilogue group
+    const int n_grp = dgrad ? 2 : 1;
+    const int group_threads = warps_per_group * 32;
+    const int et = threadIdx.x - (first_epi_warp + g2 * warps_per_group) * 32;   // 0..group_threads-1
+    const bool leader = et == 0;
+    const uint32_t bar_threads = (uint32_t)group_threads;
+    const uint32_t bar_id = 1 + g2;
+    const int acc = g2;
     uint32_t acc_phase = 0;
-    int it = 0;
-    for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
+    for (int it = g2; it < my_tiles; it += 2) {
+      const int m_tile = blockIdx.x + it * gridDim.x;
       int x0, y0, b0;
       tile_origin(p.t, m_tile, x0, y0, b0);
-      const int sb = p.n_stg == 2 ? (it & 1) : 0;
+      const int sb = it % p.n_stg;
+      const int use = it / p.n_stg;
       uint8_t* so = st_out + (size_t)sb * stage_tile;
+      if (leader) RXB_TL(2, it, 0);
       // the staging buffer is free once the TMA store issued n_stg tiles ago has read it and (statistics on the
-      // tensor pipe) the MMAs over it have completed
-      if (leader) {
-        if (p.n_stg == 2) ptx::tma_store_wait_read_pending<1>(); else ptx::tma_store_wait_read_pending<0>();
-      }
-      if (p.mma_stats && it >= p.n_stg) ptx::mbar_wait(&aux->stg_free[sb], ((p.n_stg == 2 ? it >> 1 : it) - 1) & 1, 10);
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
-      const uint8_t* sx = st_x + (size_t)(it & 1) * stage_tile;
-      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[it & 1], (it >> 1) & 1, 7);
+      // tensor pipe) the MMAs over it have completed; dgrad stages in place over the activation tile it owns
+      if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
+      if (leader) RXB_TL(2, it, 2);
+      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
+      if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
       const int r2 = row >> p.t.tw_log2;
@@ -447,7 +545,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              b0 + (r2 >> p.t.th_log2) < p.t.B;
       ptx::mbar_wait(&aux->tmem_full[acc], acc_phase, 4);
       ptx::tcgen05_fence_after();
-      for (int c = c_begin; c < c_end; c += 32) {
+      if (leader) RXB_TL(2, it, 4);
+      for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
         if (n0 + c >= p.n_total) break;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c, r);
@@ -478,62 +577,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             atomicAdd(&aux->s_stat[1][c + lane], cq);
           }
         } else {
-          // fused ReLU / BatchNorm backward: dy = acc * [x*es+eh > 0]; staged value = dy (OUT_DY) or es*dy (G modes)
+          // fused ReLU / BatchNorm backward: dy = acc * [es*x+eh > 0]; staged value = dy (OUT_DY) or es*dy (G modes),
+          // written over the activation chunk this thread just read.  The mask is a packed-bf16 threshold test.
           uint32_t xin[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 t4 = *staging_chunk(const_cast<uint8_t*>(sx), cw, row, c + 8 * i);
+            const uint4 t4 = *staging_chunk(so, cw, row, c + 8 * i);
             xin[4 * i] = t4.x; xin[4 * i + 1] = t4.y; xin[4 * i + 2] = t4.z; xin[4 * i + 3] = t4.w;
           }
+          const uint4* thr4 = reinterpret_cast<const uint4*>(aux->e_thr2 + (c >> 1));
+          const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (c >> 1));
           const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + c);
-          const float4* eh4 = reinterpret_cast<const float4*>(aux->e_shift + c);
           const bool scaled = p.out_mode != OUT_DY;
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 es = es4[i4], eh = eh4[i4];
-            const float esv[4] = {es.x, es.y, es.z, es.w}, ehv[4] = {eh.x, eh.y, eh.z, eh.w};
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 4 * i4 + e;
-              const float xv = (i & 1) ? bf16_hi(xin[i >> 1]) : bf16_lo(xin[i >> 1]);
-              const float a = scaled ? __uint_as_float(r[i]) * esv[e] : __uint_as_float(r[i]);
-              o[e] = (row_valid && fmaf(xv, esv[e], ehv[e]) > 0.f) ? a : 0.f;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const uint4 th4 = thr4[i4], sg4 = sgn4[i4];
+            const uint32_t thv[4] = {th4.x, th4.y, th4.z, th4.w}, sgv[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
+            float esv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+            if (scaled) {
+              const float4 e0 = es4[2 * i4], e1 = es4[2 * i4 + 1];
+              esv[0] = e0.x; esv[1] = e0.y; esv[2] = e0.z; esv[3] = e0.w;
+              esv[4] = e1.x; esv[5] = e1.y; esv[6] = e1.z; esv[7] = e1.w;
             }
-            packed[2 * i4] = pack_bf16x2(o[0], o[1]);
-            packed[2 * i4 + 1] = pack_bf16x2(o[2], o[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int pi = 4 * i4 + j;   // column pair (c + 2*pi, c + 2*pi + 1)
+              bool m0, m1;
+              gt_bf16x2(xin[pi] ^ sgv[j], thv[j], m0, m1);
+              const float a0 = __uint_as_float(r[2 * pi]) * esv[2 * j], a1 = __uint_as_float(r[2 * pi + 1]) * esv[2 * j + 1];
+              packed[pi] = pack_bf16x2(m0 ? a0 : 0.f, m1 ? a1 : 0.f);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *staging_chunk(so, cw, row, c + 8 * i) =
-                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                row_valid ? make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3])
+                          : make_uint4(0u, 0u, 0u, 0u);
         }
       }
+      if (leader) RXB_TL(2, it, 5);
       ptx::tcgen05_fence_before();
       ptx::mbar_arrive(&aux->tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-      // staged tile -> global: one TMA store (or L2 reduce-add into the running gradient) per 64-channel box,
-      // clipped at the tensor edges
+      acc_phase ^= 1;
+      // hand the staged tile to the store warp (and to the MMA warp for the column statistics)
       ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
       if (leader) {
-        for (int bx = 0; bx < n_boxes; ++bx) {
-          if (n0 + bx * cw >= p.n_total) break;
-          if (dgrad && p.out_mode == OUT_G_ACCUM)
-            ptx::tma_reduce_add_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
-          else
-            ptx::tma_store_4d(&tmOut, so + bx * (128 * cw * 2), n0 + bx * cw, x0, y0, b0);
-        }
-        ptx::tma_store_commit();
-        if (p.mma_stats) ptx::mbar_arrive(&aux->stg_full[sb]);
-        if (dgrad) ptx::mbar_arrive(&aux->epi_in_empty[it & 1]);
+        RXB_TL(2, it, 6);
+        ptx::mbar_arrive(&aux->stg_full[sb]);
       }
     }
-    if (leader) ptx::tma_store_wait_all();
     if (p.do_stats && p.mma_stats) {
       // per-channel totals of this CTA from TMEM: lane = channel; Gram diagonal and the sums column
-      if (half == 0 && my_tiles > 0) {
+      if (g2 == 0 && grp == 0 && my_tiles > 0) {
         ptx::mbar_wait(&aux->stats_done, 0, 12);
         ptx::tcgen05_fence_after();
         const int ch = n0 + row;
@@ -558,17 +654,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ch < p.n_total && total != 0.f) atomicAdd(p.ch_sum + ch, total);
       }
     } else if (p.do_stats) {
-      asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
-      for (int c = threadIdx.x - 64; c < p.bn && n0 + c < p.n_total; c += 128) {
+      asm volatile("bar.sync 3, %0;" ::"r"((uint32_t)n_epi_threads) : "memory");   // both groups
+      for (int c = threadIdx.x - first_epi_warp * 32; c < p.bn && n0 + c < p.n_total; c += n_epi_threads) {
         const float a = aux->s_stat[0][c], bq = aux->s_stat[1][c];
         if (a != 0.f) atomicAdd(p.ch_sum + n0 + c, a);
         if (bq != 0.f) atomicAdd(p.ch_sumsq + n0 + c, bq);
       }
     }
-  } else if (warp >= 6) {
-    // =============================== A-operand transform (pre-activation BatchNorm + ReLU)
+  } else {
+    // =============================== workers 0-7: A-operand transform (pre-activation BatchNorm + ReLU)
     if (PROLOGUE) {
-      const int t = threadIdx.x - 192;  // 0..kXformThreads-1
+      const int t = threadIdx.x - kWorker0 * 32;  // 0..kXformThreads-1
       int stage = 0;
       uint32_t phase = 0;
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
@@ -651,6 +747,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::mbar_init(&aux->tmem_full, 1);
     ptx::fence_barrier_init();
   }
+  if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
+  pdl_sync();   // CTA-private setup above overlaps the previous kernel; global memory from here on
   if (p.prologue) {
     const int padded = p.boxes_per_tap * p.bkc;
     for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
@@ -658,7 +756,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
     }
   }
-  if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -708,7 +805,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // whole warp walks the pipeline; one elected lane issues (keeps the descriptor arithmetic warp-uniform)
     {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.n, 1, 1);
+      // Shifted-dOut mode with Cout <= 64: one dOut tile is one swizzle atom along N and the taps' tiles lie d_tile
+      // bytes apart - exactly the descriptor's leading-dimension stride - so the taps_x tiles of a filter row are
+      // ONE MMA of N = taps_x*Cout whose accumulator columns are the per-tap accumulators side by side.
+      const int tiles_per_mma = (p.shift_dout && p.n <= 64 && p.taps_x * p.n <= 256) ? p.taps_x : 1;
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.n * tiles_per_mma, 1, 1);
       const uint32_t a_swz = p.bkc == 64 ? ptx::kSwizzle128B : ptx::kSwizzle64B;
       const uint32_t a_sbo = 8 * a_row_bytes;
       const uint32_t a_kstep16 = (16 * a_row_bytes) >> 4;
@@ -731,7 +832,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t a_lo = ptx::desc_lo(da0) + (uint32_t)stage * a_stage16;
             const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)stage * b_stage16;
             const uint32_t accumulate = tile > tile_begin ? 1u : 0u;
-            for (int t = 0; t < nd; ++t) {
+            for (int t = 0; t < nd; t += tiles_per_mma) {
               const uint32_t acc = tmem_base + (p.shift_dout ? t : cl) * p.n;
               const uint32_t b_lo_t = b_lo + (uint32_t)t * d_tile16;
 #pragma unroll
@@ -922,6 +1023,9 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   // tensor pipe (columns past n_total are zero weights / clipped stores)
   p.bn = (dgrad || p.n_total >= kMaxBN) ? kMaxBN : p.n_total;
   p.mma_stats = (dgrad || (p.do_stats && p.bn == kMaxBN)) ? 1 : 0;
+  static const int dbg_dgrad = getenv("RXB_DBG_DGRAD") ? atoi(getenv("RXB_DBG_DGRAD")) : 0;   // timing experiments only
+  if (dgrad && (dbg_dgrad & 1)) { p.mma_stats = 0; p.do_stats = 0; }
+  if (dgrad && (dbg_dgrad & 2) && p.out_mode == OUT_G_ACCUM) p.out_mode = OUT_G_WRITE;
   p.n_tiles = ceil_div(p.n_total, p.bn);
   p.kb_per_tap = ceil_div(p.cin, bk);
   if (prologue && p.kb_per_tap * bk > kMaxPrologueC + 64) return set_error(RXB_ERR_INVALID, "conv_gemm: cin too large");
@@ -978,7 +1082,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   const long long b_stage = (p.halo == 1 ? p.taps_y : 1) * b_tap;
   const long long b_panel = (long long)taps * p.kb_per_tap * b_tap;
   const long long stage_tile = 128ll * ceil_div(p.bn, cw) * cw * 2;
-  const long long fixed = (long long)sizeof(GemmAux) + 1024 /*alignment*/ + 1024 /*ones*/ + (dgrad ? 2 * stage_tile : 0);
+  // dgrad: 2-3 activation-tile buffers that double as the output staging
+  const long long fixed = (long long)sizeof(GemmAux) + 1024 /*alignment*/ + 1024 /*ones*/ + (dgrad ? stage_tile : 0);
   const long long budget = 227 * 1024;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int gx = num_sms() / p.n_tiles;
@@ -997,7 +1102,15 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     per_stage = a_stage;
     avail -= b_panel;
   }
-  if (!dbg_one_stg && (avail - stage_tile) / per_stage >= 4) {
+  static const int dbg_min_stages2 = getenv("RXB_DBG_MIN_STAGES2") ? atoi(getenv("RXB_DBG_MIN_STAGES2")) : 4;
+  if (dgrad) {
+    // the load of an activation tile is on the epilogue's dependency chain (buffer freed -> TMA load -> epilogue),
+    // so a third buffer hides one load latency
+    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 3;
+    p.n_stg = 2;
+    for (int extra = 1; extra <= dbg_nx - 2; ++extra)
+      if ((avail - stage_tile) / per_stage >= 3) { p.n_stg += 1; avail -= stage_tile; }
+  } else if (!dbg_one_stg && (avail - stage_tile) / per_stage >= dbg_min_stages2) {
     p.n_stg = 2;
     avail -= stage_tile;
   }
@@ -1006,21 +1119,52 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
   if (p.halo == 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
   p.stages = (int)stages;
-  const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) + p.n_stg * stage_tile + fixed);
+  const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) +
+                               (dgrad ? p.n_stg - 1 : p.n_stg) * stage_tile + fixed);
   dim3 grid(gx, p.n_tiles);
+  static const int dbg_tl = getenv("RXB_DBG_TIMELINE") ? atoi(getenv("RXB_DBG_TIMELINE")) : 0;
+  static unsigned long long* tl_dev = nullptr;
+  p.dbg = nullptr;
+  if (dbg_tl) {
+    if (!tl_dev) cudaMalloc(&tl_dev, 3 * 16 * 8 * 8);
+    cudaMemsetAsync(tl_dev, 0, 3 * 16 * 8 * 8, stream);
+    p.dbg = tl_dev;
+  }
 
   RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
 #define RXB_LAUNCH_GEMM(BK_, PRO_)                                                                             \
   do {                                                                                                         \
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)smem));                                                                 \
-    conv_gemm_kernel<BK_, PRO_><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmX, p);                \
+    RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, tmX, p)); \
   } while (0)
   if (bk == 64 && prologue) RXB_LAUNCH_GEMM(64, true);
   else if (bk == 64) RXB_LAUNCH_GEMM(64, false);
   else RXB_LAUNCH_GEMM(32, false);
 #undef RXB_LAUNCH_GEMM
   RXB_LAUNCH_OK();
+  if (dbg_tl) {   // development: print the timeline of CTA (0,0), cycles relative to its first event
+    unsigned long long h[3 * 16 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 3 * 16 * 8; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    static int printed = 0;
+    if (printed++ < dbg_tl) {
+      printf("timeline epi=%d n=%d cin=%d taps=%d stages=%d n_stg=%d res=%d halo=%d\n", p.epi_mode, p.n_total, p.cin, taps,
+             p.stages, p.n_stg, p.b_resident, p.halo);
+      const char* role[3] = {"prod", "mma ", "epi "};
+      for (int it = 0; it < 12; ++it)
+        for (int r = 0; r < 3; ++r) {
+          printf("  it%02d %s:", it, role[r]);
+          for (int ev = 0; ev < 8; ++ev) {
+            const unsigned long long v = h[(r * 16 + it) * 8 + ev];
+            if (v) printf(" %7llu", v - t0); else printf("       -");
+          }
+          printf("\n");
+        }
+    }
+  }
   return RXB_OK;
 }
 
@@ -1094,7 +1238,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   }
   RXB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RXB_PROF(stream, PROF_CONV_WGRAD);
-  conv_wgrad_kernel<<<dim3(pix_ctas, chunk_groups), kGemmThreads, smem, stream>>>(tmA, tmD, p, stages);
+  RXB_CUDA(launch_k(conv_wgrad_kernel, dim3(pix_ctas, chunk_groups), dim3(kGemmThreads), smem, stream, tmA, tmD, p, stages));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

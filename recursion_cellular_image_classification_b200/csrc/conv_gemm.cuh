@@ -45,9 +45,10 @@ struct GemmParams {
   int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
   int rows_a;       // pixel rows of one A stage (128, or (th+taps_y-1)*tw with halo)
   int stages;       // A (and streamed B) pipeline depth
-  int n_stg;        // output staging buffers (1 or 2)
+  int n_stg;        // output staging buffers (stores: 1 or 2; dgrad: 2..4 activation-tile buffers staged in place)
   int b_resident;   // 1: the whole [taps][k-blocks] weight panel of the N tile is loaded once per CTA
   int mma_stats;    // 1: per-channel sums of the stored tile are accumulated by tcgen05.mma over the staging buffer
+  unsigned long long* dbg;  // development: per-role clock64 timeline of CTA (0,0) (RXB_DBG_TIMELINE=1), else nullptr
 };
 
 // A: bf16 activation [B,H,W,ldA] (first `cin` channels used per tap); Wt: bf16 [taps][n_total][cin].

@@ -55,6 +55,7 @@ __global__ void bn_prep_kernel(const float* __restrict__ sum, const float* __res
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* __restrict__ rmean, float* __restrict__ rvar, float eps, float momentum,
                                int training, int C, BnFold f) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -82,8 +83,8 @@ int bn_prep(const float* sum, const float* sumsq, float count, const float* gamm
             float* running_mean, float* running_var, float eps, float momentum, int training, int C, BnFold f,
             cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  bn_prep_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sum, sumsq, count, gamma, beta, running_mean, running_var, eps,
-                                                  momentum, training, C, f);
+  RXB_CUDA(launch_k(bn_prep_kernel, dim3(ceil_div(C, 128)), dim3(128), (size_t)(0), st, sum, sumsq, count, gamma, beta, running_mean, running_var, eps,
+                                                  momentum, training, C, f));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -94,6 +95,7 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
                             const float* __restrict__ scale, const float* __restrict__ shift,
                             __nv_bfloat16* __restrict__ out, int ld_out, uint8_t* __restrict__ idx,
                             float* __restrict__ sum, float* __restrict__ sumsq) {
+  pdl_sync();
   __shared__ float sh[2 * 64];
   const int cg = threadIdx.x & 7;
   const int Ho = Hs >> 1, Wo = Ws >> 1;
@@ -148,8 +150,8 @@ int stem_bn_relu_maxpool(const __nv_bfloat16* S0, int B, int Hs, int Ws, const f
                          __nv_bfloat16* out, int ld_out, uint8_t* idx, float* sum, float* sumsq, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
   const long long total = (long long)B * (Hs / 2) * (Ws / 2);
-  stem_bn_relu_maxpool_kernel<<<ew_grid(total, 32), kEwThreads, 0, st>>>(S0, B, Hs, Ws, scale, shift, out, ld_out,
-                                                                        idx, sum, sumsq);
+  RXB_CUDA(launch_k(stem_bn_relu_maxpool_kernel, dim3(ew_grid(total, 32)), dim3(kEwThreads), (size_t)(0), st, S0, B, Hs, Ws, scale, shift, out, ld_out,
+                                                                        idx, sum, sumsq));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kEwThreads)
 transition_pool_fwd_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int B, int H, int W, int C,
                            const float* __restrict__ scale, const float* __restrict__ shift,
                            __nv_bfloat16* __restrict__ P) {
+  pdl_sync();
   const int groups = C >> 3;
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)B * Ho * Wo * groups;
@@ -195,7 +198,7 @@ int transition_pool_fwd(const __nv_bfloat16* X, int ldx, int B, int H, int W, in
                         const float* shift, __nv_bfloat16* P, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
   const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
-  transition_pool_fwd_kernel<<<ew_grid(total, kEwThreads), kEwThreads, 0, st>>>(X, ldx, B, H, W, C, scale, shift, P);
+  RXB_CUDA(launch_k(transition_pool_fwd_kernel, dim3(ew_grid(total, kEwThreads)), dim3(kEwThreads), (size_t)(0), st, X, ldx, B, H, W, C, scale, shift, P));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -204,6 +207,7 @@ int transition_pool_fwd(const __nv_bfloat16* X, int ldx, int B, int H, int W, in
 __global__ void __launch_bounds__(kEwThreads)
 final_bn_relu_gap_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int B, int HW, int C,
                          const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ feat) {
+  pdl_sync();
   const int groups = C >> 3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * groups) return;
@@ -228,7 +232,7 @@ int final_bn_relu_gap(const __nv_bfloat16* X, int ldx, int B, int HW, int C, con
                       const float* shift, float* feat, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
   const int total = B * (C / 8);
-  final_bn_relu_gap_kernel<<<ceil_div(total, 128), 128, 0, st>>>(X, ldx, B, HW, C, scale, shift, feat);
+  RXB_CUDA(launch_k(final_bn_relu_gap_kernel, dim3(ceil_div(total, 128)), dim3(128), (size_t)(0), st, X, ldx, B, HW, C, scale, shift, feat));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -239,6 +243,7 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* __restrict__ X, int ldx, int B,
                         int H, int W, int C, BnFold f, __nv_bfloat16* __restrict__ G, float* __restrict__ dsum,
                         float* __restrict__ dsq) {
+  pdl_sync();
   extern __shared__ float sh[];
   const int groups = C >> 3;
   const int cg = threadIdx.x % groups;
@@ -293,9 +298,9 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
   const int grid = ew_grid((long long)B * H * W, ppi * 4);
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (mode == 0)
-    bn_relu_bwd_to_G_kernel<0><<<grid, kEwThreads, smem, st>>>(upstream, X, ldx, B, H, W, C, f, G, dsum, dsq);
+    RXB_CUDA(launch_k((bn_relu_bwd_to_G_kernel<0>), dim3(grid), dim3(kEwThreads), (size_t)(smem), st, upstream, X, ldx, B, H, W, C, f, G, dsum, dsq));
   else
-    bn_relu_bwd_to_G_kernel<1><<<grid, kEwThreads, smem, st>>>(upstream, X, ldx, B, H, W, C, f, G, dsum, dsq);
+    RXB_CUDA(launch_k((bn_relu_bwd_to_G_kernel<1>), dim3(grid), dim3(kEwThreads), (size_t)(smem), st, upstream, X, ldx, B, H, W, C, f, G, dsum, dsq));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -321,6 +326,7 @@ __global__ void __launch_bounds__(256)
 sum_dyx_from_wdw_kernel(const float* __restrict__ W, const float* __restrict__ dW, int K, int C, int taps,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ sum_dy, float* __restrict__ out) {
+  pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane);
@@ -333,6 +339,7 @@ bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __res
                        float* __restrict__ dsum, float* __restrict__ dsq, BnFold f, float count, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ corrA,
                        float* __restrict__ corrB) {
+  pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   const float s = dsum[c];
@@ -359,8 +366,8 @@ bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __res
 int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, float* dsum, float* dsq, BnFold f,
                     float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  bn_bwd_finalize_kernel<<<ceil_div(C, 8), 256, 0, st>>>(mode, W, dW, K, taps, dsum, dsq, f, count, C, dgamma, dbeta,
-                                                        corrA, corrB);
+  RXB_CUDA(launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, mode, W, dW, K, taps, dsum, dsq, f, count, C, dgamma, dbeta,
+                                                        corrA, corrB));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -369,6 +376,7 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
                     BnFold f, const float* __restrict__ m1, const float* __restrict__ m2) {
+  pdl_sync();
   const int groups = C >> 3;
   const long long total = M * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -392,7 +400,7 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
                  const float* m2, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8), kEwThreads * 2), kEwThreads, 0, st>>>(dy, X, M, C, f, m1, m2);
+  RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M * (C / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -402,6 +410,7 @@ __global__ void __launch_bounds__(kEwThreads)
 grad_fixup_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ X, int ld, long long M,
                   int c0, int nch, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ corrA, const float* __restrict__ corrB, __nv_bfloat16* __restrict__ dst) {
+  pdl_sync();
   const int groups = nch >> 3;
   const long long total = M * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -426,8 +435,8 @@ int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long
                const float* mean, const float* rstd, const float* corrA, const float* corrB, __nv_bfloat16* dst,
                cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  grad_fixup_kernel<<<ew_grid(M * (nch / 8), kEwThreads * 2), kEwThreads, 0, st>>>(G, X, ld, M, c0, nch, mean, rstd,
-                                                                                 corrA, corrB, dst);
+  RXB_CUDA(launch_k(grad_fixup_kernel, dim3(ew_grid(M * (nch / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st, G, X, ld, M, c0, nch, mean, rstd,
+                                                                                 corrA, corrB, dst));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -439,6 +448,7 @@ __global__ void __launch_bounds__(kEwThreads)
 stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __restrict__ idx,
                      const __nv_bfloat16* __restrict__ S0, int B, int Hs, int Ws, BnFold f,
                      __nv_bfloat16* __restrict__ dy0, float* __restrict__ dsum, float* __restrict__ dsq) {
+  pdl_sync();
   __shared__ float sh[2 * 64];
   const int cg = threadIdx.x & 7;
   const int Ho = Hs >> 1, Wo = Ws >> 1;
@@ -513,8 +523,8 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
 int stem_pool_bwd(const __nv_bfloat16* dPool, const uint8_t* idx, const __nv_bfloat16* S0, int B, int Hs, int Ws,
                   BnFold f, __nv_bfloat16* dy0, float* dsum, float* dsq, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  stem_pool_bwd_kernel<<<ew_grid((long long)B * (Hs / 2) * (Ws / 2), 32 * 2), kEwThreads, 0, st>>>(dPool, idx, S0, B, Hs,
-                                                                                                  Ws, f, dy0, dsum, dsq);
+  RXB_CUDA(launch_k(stem_pool_bwd_kernel, dim3(ew_grid((long long)B * (Hs / 2) * (Ws / 2), 32 * 2)), dim3(kEwThreads), (size_t)(0), st, dPool, idx, S0, B, Hs,
+                                                                                                  Ws, f, dy0, dsum, dsq));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -524,6 +534,7 @@ __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(int M, int N, int K, const float* __restrict__ A, long long a_i, long long a_l,
                      const float* __restrict__ Bm, long long b_l, long long b_j, const float* __restrict__ bias,
                      float* __restrict__ C, long long c_i, long long c_j) {
+  pdl_sync();
   __shared__ float sA[32][33], sB[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
@@ -561,13 +572,14 @@ int sgemm_strided(int M, int N, int K, const float* A, long long a_i, long long 
                   long long b_j, const float* bias, float* C, long long c_i, long long c_j, cudaStream_t st) {
   RXB_PROF(st, PROF_HEAD);
   dim3 grid(ceil_div(N, 32), ceil_div(M, 32));
-  sgemm_strided_kernel<<<grid, 256, 0, st>>>(M, N, K, A, a_i, a_l, Bm, b_l, b_j, bias, C, c_i, c_j);
+  RXB_CUDA(launch_k(sgemm_strided_kernel, dim3(grid), dim3(256), (size_t)(0), st, M, N, K, A, a_i, a_l, Bm, b_l, b_j, bias, C, c_i, c_j));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
 
 __global__ void column_sum_kernel(const float* __restrict__ A, int rows, int cols, long long ld,
                                   float* __restrict__ out) {
+  pdl_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   float s = 0.f;
@@ -576,12 +588,13 @@ __global__ void column_sum_kernel(const float* __restrict__ A, int rows, int col
 }
 int column_sum(const float* A, int rows, int cols, long long ld, float* out, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  column_sum_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(A, rows, cols, ld, out);
+  RXB_CUDA(launch_k(column_sum_kernel, dim3(ceil_div(cols, 128)), dim3(128), (size_t)(0), st, A, rows, cols, ld, out));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
 
 __global__ void sum_scale_kernel(const float* __restrict__ v, int n, float scale, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -596,7 +609,7 @@ __global__ void sum_scale_kernel(const float* __restrict__ v, int n, float scale
 }
 int sum_scale(const float* v, int n, float scale, float* out, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  sum_scale_kernel<<<1, 256, 0, st>>>(v, n, scale, out);
+  RXB_CUDA(launch_k(sum_scale_kernel, dim3(1), dim3(256), (size_t)(0), st, v, n, scale, out));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -604,6 +617,7 @@ int sum_scale(const float* v, int n, float scale, float* out, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------ weight repack
 __global__ void __launch_bounds__(256)
 repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ arena, const RepackJob* __restrict__ jobs) {
+  pdl_sync();
   const RepackJob j = jobs[blockIdx.y];
   const float* src = params + j.src_off;
   __nv_bfloat16* dst = arena + j.dst_off;
@@ -656,7 +670,7 @@ int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* j
   int gx = (int)ceil_div<long long>(max_elems, 256 * 8);
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  repack_kernel<<<dim3(gx, n_jobs), 256, 0, st>>>(params, arena, jobs_dev);
+  RXB_CUDA(launch_k(repack_kernel, dim3(dim3(gx, n_jobs)), dim3(256), (size_t)(0), st, params, arena, jobs_dev));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -664,7 +678,7 @@ int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* j
 int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
                             const float* shift, const float* sum_dy, float* out, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  sum_dyx_from_wdw_kernel<<<ceil_div(C, 8), 256, 0, st>>>(W, dW, K, C, taps, scale, shift, sum_dy, out);
+  RXB_CUDA(launch_k(sum_dyx_from_wdw_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, W, dW, K, C, taps, scale, shift, sum_dy, out));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

@@ -14,6 +14,7 @@ constexpr int kCeThreads = 256;
 __global__ void __launch_bounds__(kCeThreads)
 softmax_ce_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ target, int C,
                   float* __restrict__ loss_rows, float* __restrict__ dlogits, float grad_scale) {
+  pdl_sync();
   __shared__ float red[kCeThreads / 32];
   __shared__ float bc;
   const int b = blockIdx.x;
@@ -60,6 +61,7 @@ softmax_ce_kernel(const float* __restrict__ logits, int ld, const long long* __r
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ mom, long long n, float lr,
            float mu, float wd, int nesterov, float grad_scale) {
+  pdl_sync();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float w = p[i];
@@ -84,8 +86,8 @@ int rxb_softmax_ce(const float* logits, int ld, const int64_t* target, int B, in
   int rc = rxb_check_device();
   if (rc) return rc;
   RXB_PROF(as_stream(stream), PROF_HEAD);
-  softmax_ce_kernel<<<B, kCeThreads, 0, as_stream(stream)>>>(logits, ld, reinterpret_cast<const long long*>(target),
-                                                             C, loss_rows, dlogits, grad_scale);
+  RXB_CUDA(launch_k(softmax_ce_kernel, dim3(B), dim3(kCeThreads), (size_t)(0), as_stream(stream), logits, ld, reinterpret_cast<const long long*>(target),
+                                                             C, loss_rows, dlogits, grad_scale));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -102,7 +104,7 @@ int rxb_sgd_step(float* p, const float* grad, float* mom, int64_t n, float lr, f
   long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   RXB_PROF(as_stream(stream), PROF_OPTIM);
-  sgd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(p, grad, mom, n, lr, mu, wd, nesterov, grad_scale);
+  RXB_CUDA(launch_k(sgd_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), as_stream(stream), p, grad, mom, n, lr, mu, wd, nesterov, grad_scale));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
