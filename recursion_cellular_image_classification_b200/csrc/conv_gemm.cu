@@ -534,7 +534,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (leader) RXB_TL(2, it, 0);
       // the staging buffer is free once the TMA store issued n_stg tiles ago has read it and (statistics on the
       // tensor pipe) the MMAs over it have completed; dgrad stages in place over the activation tile it owns
-      if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
+      if (!dgrad && use > 0) {
+        // with ONE staging buffer the two epilogue groups share it, so a group can be two phases behind the barrier:
+        // a parity wait only distinguishes adjacent phases, hence wait for phase use-2 before phase use-1
+        if (p.n_stg == 1 && use > 1) ptx::mbar_wait(&aux->stg_free[sb], use & 1, 11);
+        ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
+      }
       if (leader) RXB_TL(2, it, 2);
       if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
       if (leader) RXB_TL(2, it, 3);
@@ -702,6 +707,8 @@ struct __align__(16) WgradAux {
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t d_full[2];    // classic mode: the dOut tile of a pixel tile (loaded once, shared by all channel chunks)
+  uint64_t d_empty[2];
   uint64_t tmem_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -716,11 +723,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int taps = p.taps_x * p.taps_y;
   const int d_tile = 128 * p.n * 2;                     // one dOut tile
-  const int nd = p.shift_dout ? taps : 1;               // dOut tiles per stage
-  const int b_bytes = nd * d_tile;
+  const int nd = p.shift_dout ? taps : 1;               // dOut tiles (accumulator groups) per stage
+  // shift_dout == 2: ONE dOut box with the full (tw+taps_x-1) x (th+taps_y-1) halo serves every tap
+  const int halo_w = (1 << p.t.tw_log2) + p.taps_x - 1, halo_h = (1 << p.t.th_log2) + p.taps_y - 1;
+  const int halo_tx = halo_w * halo_h * p.n * 2;        // bytes TMA delivers for the halo box
+  const int b_bytes = p.shift_dout == 2 ? ((halo_tx + 1023) & ~1023) : nd * d_tile;
   uint8_t* smA = smem;
   uint8_t* smB = smem + (size_t)stages * kWgA_BYTES;
-  WgradAux* aux = reinterpret_cast<WgradAux*>(smB + (size_t)stages * b_bytes);
+  // classic mode: two dOut tile buffers (one load per pixel tile); shifted-dOut modes: one dOut group per stage
+  const int n_dbuf = p.shift_dout ? stages : 2;
+  WgradAux* aux = reinterpret_cast<WgradAux*>(smB + (size_t)n_dbuf * b_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
@@ -745,6 +757,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_init(&aux->empty[s], 1);
     }
     ptx::mbar_init(&aux->tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&aux->d_full[a], 1);
+      ptx::mbar_init(&aux->d_empty[a], 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(&aux->tmem_base);
@@ -768,9 +784,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int x0, y0, b0;
         tile_origin(p.t, tile, x0, y0, b0);
+        if (!p.shift_dout) {
+          const int tc = tile - tile_begin, db = tc & 1;
+          ptx::mbar_wait(&aux->d_empty[db], ((tc >> 1) & 1) ^ 1, 17);
+          ptx::mbar_arrive_expect_tx(&aux->d_full[db], d_tile);
+          for (int j = 0; j < d_boxes; ++j)
+            ptx::tma_load_4d(smB + (size_t)db * d_tile + (size_t)j * 16384, &tmD, &aux->d_full[db], j * 64, x0, y0, b0);
+        }
         for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 11);
-          ptx::mbar_arrive_expect_tx(&aux->full[stage], kWgA_BYTES + b_bytes);
+          ptx::mbar_arrive_expect_tx(&aux->full[stage],
+                                     kWgA_BYTES + (p.shift_dout == 2 ? halo_tx : p.shift_dout ? b_bytes : 0));
           uint8_t* a_dst = smA + (size_t)stage * kWgA_BYTES;
           for (int i = 0; i < p.boxes_per_chunk; ++i) {
             const int kk = (chunk0 + cl) * p.boxes_per_chunk + i;
@@ -788,15 +812,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tma_load_4d(a_dst + (size_t)i * a_box_bytes, &tmA, &aux->full[stage], c0, ax, ay, b0);
           }
           uint8_t* d_dst = smB + (size_t)stage * b_bytes;
-          for (int t = 0; t < nd; ++t) {
-            int dx = x0, dy = y0;
-            if (p.shift_dout) {  // dW[t] = sum_q A'[q] * dOut[q - (t - pad)]
+          if (p.shift_dout == 2) {
+            // dW[t] = sum_q A'[q] * dOut[q - (t - pad)]: the box starts (taps-1-pad) pixels before the tile
+            ptx::tma_load_4d(d_dst, &tmD, &aux->full[stage], 0, x0 - (p.taps_x - 1 - p.pad_x), y0 - (p.taps_y - 1 - p.pad_y), b0);
+          } else if (p.shift_dout) {
+            for (int t = 0; t < nd; ++t) {  // dW[t] = sum_q A'[q] * dOut[q - (t - pad)]
               const int ty = t / p.taps_x, tx = t - ty * p.taps_x;
-              dx -= tx - p.pad_x;
-              dy -= ty - p.pad_y;
+              const int dx = x0 - (tx - p.pad_x), dy = y0 - (ty - p.pad_y);
+              for (int j = 0; j < d_boxes; ++j)
+                ptx::tma_load_4d(d_dst + (size_t)t * d_tile + (size_t)j * 16384, &tmD, &aux->full[stage], j * 64, dx, dy, b0);
             }
-            for (int j = 0; j < d_boxes; ++j)
-              ptx::tma_load_4d(d_dst + (size_t)t * d_tile + (size_t)j * 16384, &tmD, &aux->full[stage], j * 64, dx, dy, b0);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -809,6 +834,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // bytes apart - exactly the descriptor's leading-dimension stride - so the taps_x tiles of a filter row are
       // ONE MMA of N = taps_x*Cout whose accumulator columns are the per-tap accumulators side by side.
       const int tiles_per_mma = (p.shift_dout && p.n <= 64 && p.taps_x * p.n <= 256) ? p.taps_x : 1;
+      // Full-halo mode: tap (ty,tx) reads the halo box from pixel row (taps_y-1-ty)*halo_w + (taps_x-1-tx); an 8-pixel
+      // K group is one tile row (tw = 8), consecutive groups lie halo_w rows apart, and the taps_x taps of a filter row
+      // are N atoms ONE pixel row apart (leading-dimension stride = one row), in DESCENDING tx order - so accumulator
+      // group (ty, j) holds tap (ty, taps_x-1-j).  (MN-major operands with unaligned starts: probed on B200,
+      // profiles/r01_umma_probe_unaligned_operands.log.)
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.n * tiles_per_mma, 1, 1);
       const uint32_t a_swz = p.bkc == 64 ? ptx::kSwizzle128B : ptx::kSwizzle64B;
       const uint32_t a_sbo = 8 * a_row_bytes;
@@ -819,19 +849,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t d_kstep16 = (16 * d_row_bytes) >> 4;
       const uint32_t d_lbo = 128 * d_row_bytes;
       const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smA), a_box_bytes, a_sbo, a_swz);
-      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smB), d_lbo, d_sbo, d_swz);
+      const uint64_t db0 = p.shift_dout == 2
+                               ? ptx::make_smem_desc(ptx::smem_u32(smB), d_row_bytes, (uint32_t)halo_w * d_row_bytes, d_swz)
+                               : ptx::make_smem_desc(ptx::smem_u32(smB), d_lbo, d_sbo, d_swz);
+      const uint32_t d_row16 = d_row_bytes >> 4;
+      const uint32_t d_kstep16_h = (2u * (uint32_t)halo_w * d_row_bytes) >> 4;   // 16 pixels = two tile rows
       const uint32_t a_hi = ptx::desc_hi(da0), b_hi = ptx::desc_hi(db0);
       const uint32_t a_stage16 = kWgA_BYTES >> 4, b_stage16 = (uint32_t)b_bytes >> 4, d_tile16 = (uint32_t)d_tile >> 4;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int tc = tile - tile_begin, db = tc & 1;
+        if (!p.shift_dout) ptx::mbar_wait(&aux->d_full[db], (tc >> 1) & 1, 18);
         for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(p.prologue ? &aux->xform[stage] : &aux->full[stage], phase, 13);
           ptx::tcgen05_fence_after();
           if (ptx::elect_one()) {
             const uint32_t a_lo = ptx::desc_lo(da0) + (uint32_t)stage * a_stage16;
-            const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)stage * b_stage16;
+            const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)(p.shift_dout ? stage : db) * b_stage16;
             const uint32_t accumulate = tile > tile_begin ? 1u : 0u;
+            if (p.shift_dout == 2) {
+              for (int ty = 0; ty < p.taps_y; ++ty) {
+                const uint32_t acc = tmem_base + (uint32_t)(ty * p.taps_x) * p.n;
+                const uint32_t b_lo_t = b_lo + (uint32_t)((p.taps_y - 1 - ty) * halo_w) * d_row16;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  ptx::umma_bf16_ss_parts(acc, a_lo + ks * a_kstep16, a_hi, b_lo_t + ks * d_kstep16_h, b_hi, idesc,
+                                          ks > 0 ? 1u : accumulate);
+              }
+            } else
             for (int t = 0; t < nd; t += tiles_per_mma) {
               const uint32_t acc = tmem_base + (p.shift_dout ? t : cl) * p.n;
               const uint32_t b_lo_t = b_lo + (uint32_t)t * d_tile16;
@@ -841,6 +887,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                         ks > 0 ? 1u : accumulate);
             }
             ptx::umma_commit(&aux->empty[stage]);
+            if (!p.shift_dout && cl == stages_per_tile - 1) ptx::umma_commit(&aux->d_empty[db]);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -864,9 +911,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.shift_dout) {
           const int rowlen = p.cin * taps;   // floats of one n row: [cin][taps]
           for (int tp = 0; tp < taps; ++tp) {
+            // accumulator group of tap tp (full-halo mode keeps a filter row's taps in descending tx order)
+            const int tyy = tp / p.taps_x, txx = tp - tyy * p.taps_x;
+            const int grp_col = (p.shift_dout == 2 ? tyy * p.taps_x + (p.taps_x - 1 - txx) : tp) * p.n;
             for (int c = 0; c < p.n; c += 32) {
               uint32_t r[32];
-              ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + tp * p.n + c, r);
+              ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + grp_col + c, r);
               ptx::tmem_ld_wait();
               if (row < p.cin) {
 #pragma unroll
@@ -913,6 +963,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           bool ok;
           if (p.shift_dout) {
             tp = cl;
+            if (p.shift_dout == 2) {  // accumulator group cl = (ty, j) holds tap (ty, taps_x-1-j)
+              const int tyy = cl / p.taps_x, jj = cl - tyy * p.taps_x;
+              tp = tyy * p.taps_x + (p.taps_x - 1 - jj);
+            }
             ch = row;
             ok = ch < p.cin;
           } else {
@@ -1178,6 +1232,15 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
   p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;
+  if (p.shift_dout && p.n <= 64 && p.taps_x * p.n <= 256 && p.taps_x > 1) {
+    // full-halo dOut box: needs 8-pixel tile rows (one K group per row); the tall tiling also keeps the halo small
+    static const int dbg_no_wg_halo = getenv("RXB_DBG_NO_WG_HALO") ? atoi(getenv("RXB_DBG_NO_WG_HALO")) : 0;
+    PixelTiling tall = make_tiling_tall(p.t.B, p.t.H, p.t.W);
+    if (!dbg_no_wg_halo && tall.tw_log2 == 3 && tall.tb_log2 == 0) {
+      p.t = tall;
+      p.shift_dout = 2;
+    }
+  }
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int chunk_groups;
   if (p.shift_dout) {
@@ -1215,18 +1278,27 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   const int th = 1 << p.t.th_log2;
   int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc, th);
   if (rc) return rc;
-  rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32, th);
+  const int tw = 1 << p.t.tw_log2;
+  if (p.shift_dout == 2)
+    rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32,
+                       th + p.taps_y - 1, tw + p.taps_x - 1);
+  else
+    rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32, th);
   if (rc) return rc;
 
-  const int b_bytes = (p.shift_dout ? taps : 1) * 128 * p.n * 2;
+  const int b_bytes = p.shift_dout == 2 ? (((tw + p.taps_x - 1) * (th + p.taps_y - 1) * p.n * 2 + 1023) & ~1023)
+                                        : (p.shift_dout ? taps : 1) * 128 * p.n * 2;
   const size_t budget = 226 * 1024;
-  int stages = (int)((budget - sizeof(WgradAux) - 1024) / (size_t)(kWgA_BYTES + b_bytes));
+  // classic mode: two dOut tile buffers shared by the channel chunks + A stages; shifted modes: dOut rides in the stage
+  const size_t d_fixed = p.shift_dout ? 0 : 2 * (size_t)b_bytes;
+  const size_t per_stage = kWgA_BYTES + (p.shift_dout ? b_bytes : 0);
+  int stages = (int)((budget - sizeof(WgradAux) - 1024 - d_fixed) / per_stage);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_wgrad: tile too large for shared memory");
-  const size_t smem = (size_t)stages * (kWgA_BYTES + b_bytes) + sizeof(WgradAux) + 1024;
+  const size_t smem = (size_t)stages * per_stage + d_fixed + sizeof(WgradAux) + 1024;
   // result leaves through shared memory as bulk reduce-adds when its global layout is contiguous per output
   // channel: 1x1 filters, or the shifted-dOut multi-tap mode; the staging area is the dead pipeline
-  const size_t pipe_bytes = (size_t)stages * (kWgA_BYTES + b_bytes);
+  const size_t pipe_bytes = (size_t)stages * per_stage + d_fixed;
   p.bulk_out = 0;
   p.bulk_bufs = 1;
   if (p.w_mode == 0 && p.cin % 8 == 0) {
