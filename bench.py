@@ -171,6 +171,75 @@ def cpu_baseline(seconds_budget=25.0):
                       "warm-up (model only, no loader)" % (B, n)}
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of each representative conv kernel at batch
+# 128, from the committed `ncu --set full` capture profiles/r01_conv_kernels_b128_ncu_raw.csv (tools/bench_conv.py prof).
+NCU_TRAFFIC_B128 = {"fwd_3x3": 659977840, "fwd_1x1": 1583840536, "dgrad_3x3_bn": 1169743680,
+                    "dgrad_1x1_bn_accum": 3522543520, "wgrad_3x3": 687589264, "wgrad_1x1": 1615371920}
+
+
+def conv_kernel_rooflines(B, dev, peaks):
+    """Six representative dense-block-1 launches (the geometry that dominates the step), each timed alone with
+    CUDA events on inputs far larger than L2.  Algorithmic bytes = every operand read once + result written once
+    (the running gradient of the accumulating dgrad is read AND written); FLOPs = 2*M*N*K."""
+    from recursion_cellular_image_classification_b200 import ops
+
+    def timeit(fn, reps=6):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps
+
+    H = W = IMG // 4
+    M = B * H * W
+    out = {}
+
+    def entry(name, ms, bytes_, flops, what):
+        gbs = bytes_ / (ms * 1e-3) / 1e9
+        tf = flops / (ms * 1e-3) / 1e12
+        tr = NCU_TRAFFIC_B128.get(name) if B == 128 else None
+        out[name] = {"what": what, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy", "ms": ms,
+                     "algorithmic_bytes": bytes_, "tflops": tf, "tensor_frac": tf / peaks["bf16_tflops_sustained"],
+                     "traffic": tr}
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    rnd = lambda *sh: torch.randn(*sh, device=dev, generator=g).to(torch.bfloat16)
+    X = rnd(B, H, W, 256)                       # concat buffer of dense block 1 (Ctot = 256)
+    Y = rnd(B, H, W, 128)                       # bottleneck activation
+    sc224, sh224 = torch.rand(224, device=dev) + 0.5, torch.randn(224, device=dev) * 0.1
+    sc128, sh128 = torch.rand(128, device=dev) + 0.5, torch.randn(128, device=dev) * 0.1
+    W1 = (torch.randn(1, 1, 128, 224, device=dev) * 0.05).to(torch.bfloat16)
+    W3 = (torch.randn(3, 3, 32, 128, device=dev) * 0.03).to(torch.bfloat16)
+    # forward 1x1 (Cin 224 -> 128, BN+ReLU prologue, statistics) and 3x3 (128 -> 32 written into the concat buffer)
+    ms = timeit(lambda: ops.conv_fwd(X, W1, Cin=224, scale=sc224, shift=sh224, out=Y, stats=True))
+    entry("fwd_1x1", ms, M * (224 + 128) * 2, 2.0 * M * 128 * 224, "dense layer 1x1, Cin 224")
+    ms = timeit(lambda: ops.conv_fwd(Y, W3, Cin=128, scale=sc128, shift=sh128, out=X, c_off=224, pad=(1, 1), stats=True))
+    entry("fwd_3x3", ms, M * (128 + 32) * 2, 2.0 * M * 32 * 128 * 9, "dense layer 3x3, 128 -> 32")
+    # backward: 3x3 dgrad (dZ 32 -> dy2 128), 1x1 dgrad accumulating into the concat gradient, both wgrads
+    dZ = rnd(B, H, W, 32)
+    W3d = (torch.randn(3, 3, 128, 32, device=dev) * 0.03).to(torch.bfloat16)
+    dy2 = torch.empty(B, H, W, 128, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: ops.conv_dgrad_bn(dZ, W3d, Y, sc128, sh128, 128, out_mode=ops.OUT_DY, out=dy2, pad=(1, 1)))
+    entry("dgrad_3x3_bn", ms, M * (32 + 128 + 128) * 2, 2.0 * M * 128 * 32 * 9, "3x3 data gradient + ReLU/BN2 backward")
+    W1d = (torch.randn(1, 1, 224, 128, device=dev) * 0.05).to(torch.bfloat16)
+    G = torch.zeros(B, H, W, 256, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: ops.conv_dgrad_bn(dy2, W1d, X, sc224, sh224, 224, out_mode=ops.OUT_G_ACCUM, out=G))
+    entry("dgrad_1x1_bn_accum", ms, M * (128 + 3 * 224) * 2, 2.0 * M * 224 * 128,
+          "1x1 data gradient + ReLU/BN1 backward, L2 reduce-add into the concat gradient (Cin 224)")
+    ms = timeit(lambda: ops.conv_wgrad(Y, dZ, 128, 32, taps=(3, 3), pad=(1, 1), scale=sc128, shift=sh128))
+    entry("wgrad_3x3", ms, M * (128 + 32) * 2, 2.0 * M * 32 * 128 * 9, "3x3 weight gradient")
+    ms = timeit(lambda: ops.conv_wgrad(X, dy2, 224, 128, scale=sc224, shift=sh224))
+    entry("wgrad_1x1", ms, M * (224 + 128) * 2, 2.0 * M * 128 * 224, "1x1 weight gradient, Cin 224")
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from recursion_cellular_image_classification_b200 import _lib, ops
@@ -288,7 +357,7 @@ def run_ours(args):
     loss_last = host_loss.item()
 
     # ---- kernel-family breakdown (event-bracketed launches, separate untimed pass) and HBM kernels
-    breakdown, roofline, hbm_kernels = None, None, None
+    breakdown, roofline, hbm_kernels, roofline_tensor, conv_kernels = None, None, None, None, None
     if rank == 0:
         ncat = 9
         msb = (ctypes.c_float * ncat)()
@@ -306,14 +375,21 @@ def run_ours(args):
         conv_ms = sum(breakdown[k]["ms_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
         conv_launches = sum(breakdown[k]["launches_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
         achieved_tf = FLOP_FWD_BWD_PER_IMG * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        roofline = {"kernel": "conv_gemm_kernel + conv_wgrad_kernel (tcgen05 implicit GEMM family)",
-                    "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
-                    "peak_source": peaks["source"] + " sustained cuBLAS bf16",
-                    "algorithmic_flops_per_step": FLOP_FWD_BWD_PER_IMG * B, "launches_per_step": conv_launches,
-                    "avg_launch_ms": conv_ms / max(conv_launches, 1), "traffic": None,
-                    "note": "the stride-1 DenseNet convs at bf16 have 64-230 FLOP/B arithmetic intensity, below the "
-                            "B200 ridge (~217 FLOP/B): they are HBM-bound; see DESIGN.md"}
+        roofline_tensor = {"kernel": "conv_gemm_kernel + conv_wgrad_kernel (tcgen05 implicit GEMM family), whole step",
+                           "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"],
+                           "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                           "peak_source": peaks["source"] + " sustained cuBLAS bf16",
+                           "algorithmic_flops_per_step": FLOP_FWD_BWD_PER_IMG * B, "launches_per_step": conv_launches,
+                           "avg_launch_ms": conv_ms / max(conv_launches, 1),
+                           "note": "the stride-1 DenseNet convs at bf16 have 43-230 FLOP/B arithmetic intensity, at or "
+                                   "below the B200 ridge (~217 FLOP/B): they are HBM-bound, see DESIGN.md section 5"}
+        conv_kernels = conv_kernel_rooflines(B, dev, peaks)
+        # the dominant kernel of the step (largest share of the launch list, profiles/): the 1x1 data-gradient
+        # with the fused ReLU/BatchNorm-backward epilogue, on its true bound
+        roofline = dict(conv_kernels["dgrad_1x1_bn_accum"])
+        roofline["kernel"] = "conv_gemm_kernel<64,false> EPI_DGRAD_BN (dense-layer 1x1 data gradient + ReLU/BN backward)"
+        roofline["share_of_step"] = breakdown["conv_dgrad"]["ms_per_step"] / max(sum(
+            v["ms_per_step"] for v in breakdown.values()), 1e-9)
         # HBM-bound families, timed alone on >L2 inputs
         def time_kernel(fn, reps=10):
             for _ in range(3):
@@ -359,7 +435,8 @@ def run_ours(args):
                         "h2d_bytes_per_step": int(host_src.numel()) * world, "d2h_bytes_per_step": 4 * world},
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
                 "clocks": clocks,
-                "roofline": roofline, "hbm_kernels": hbm_kernels, "kernel_breakdown": breakdown,
+                "roofline": roofline, "roofline_tensor_conv_family": roofline_tensor, "conv_kernels": conv_kernels,
+                "hbm_kernels": hbm_kernels, "kernel_breakdown": breakdown,
                 "cpu_baseline": cpu,
                 "loss": {"after_warmup": loss_first, "last": loss_last}}
         print(json.dumps(line), flush=True)

@@ -63,8 +63,8 @@ def run_dgrad(B, H, W, Cd, Cx, ldX, k, out_mode):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "prof":
-        # one launch of each representative block-1 shape (for ncu)
-        B = 64
+        # one launch of each representative block-1 shape (for ncu); optional batch as argv[2]
+        B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
         timeit_ = timeit
         globals()["timeit"] = lambda fn, reps=1: (fn(), torch.cuda.synchronize(), 0.001)[2]
         run(B, 128, 128, 128, 128, 32, 3, 1, 1)
