@@ -114,22 +114,23 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
     int bi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+    // all nine window loads are issued before any is used (clamped addresses; out-of-image taps are skipped below)
+    uint4 win[9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy - 1 + ky;
-      if (iy < 0 || iy >= Hs) continue;
+    for (int k = 0; k < 9; ++k) {
+      const int iy = min(max(2 * oy - 1 + k / 3, 0), Hs - 1), ix = min(max(2 * ox - 1 + k % 3, 0), Ws - 1);
+      win[k] = ld_stream_v4(S0 + (((long long)b * Hs + iy) * Ws + ix) * 64 + cg * 8);
+    }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox - 1 + kx;
-        if (ix < 0 || ix >= Ws) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(S0 + (((long long)b * Hs + iy) * Ws + ix) * 64 + cg * 8));
-        float x[8];
-        unpack8(v, x);
+    for (int k = 0; k < 9; ++k) {
+      const int iy = 2 * oy - 1 + k / 3, ix = 2 * ox - 1 + k % 3;
+      if (iy < 0 || iy >= Hs || ix < 0 || ix >= Ws) continue;
+      float x[8];
+      unpack8(win[k], x);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float a = fmaxf(fmaf(x[e], sc[e], sf[e]), 0.f);
-          if (a > best[e]) { best[e] = a; bi[e] = ky * 3 + kx; }
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float a = fmaxf(fmaf(x[e], sc[e], sf[e]), 0.f);
+        if (a > best[e]) { best[e] = a; bi[e] = k; }
       }
     }
     const uint4 o = pack8(best);
@@ -373,34 +374,64 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 }
 
 // ------------------------------------------------------------------------------------------------ BN bwd apply
+// dx = scale*(dy - m1 - xhat*m2) = scale*dy + cb*x + cc  with  cb = -scale*rstd*m2,  cc = scale*(rstd*m2*mean - m1).
+// A thread keeps ONE channel group (its folded constants live in registers) and walks pixels, four rows in flight.
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
                     BnFold f, const float* __restrict__ m1, const float* __restrict__ m2) {
   pdl_sync();
-  const int groups = C >> 3;
-  const long long total = M * groups;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % groups);
-    float sc[8], mu[8], rs[8], a1[8], a2[8], d[8], x[8];
+  const int groups = C >> 3;                         // divides the block size (C = 64 or 128)
+  const int cg = threadIdx.x % groups;
+  const int rows_per_block = kEwThreads / groups;
+  float sc[8], cb[8], cc[8];
+  {
+    float mu[8], rs[8], a1[8], a2[8];
     load8f(f.scale + cg * 8, sc);
     load8f(f.mean + cg * 8, mu);
     load8f(f.rstd + cg * 8, rs);
     load8f(m1 + cg * 8, a1);
     load8f(m2 + cg * 8, a2);
-    uint4* p = reinterpret_cast<uint4*>(dy) + i;
-    unpack8(*p, d);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(X) + i), x);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = sc[e] * (d[e] - a1[e] - (x[e] - mu[e]) * rs[e] * a2[e]);
-    *p = pack8(d);
+    for (int e = 0; e < 8; ++e) {
+      cb[e] = -sc[e] * rs[e] * a2[e];
+      cc[e] = sc[e] * (rs[e] * a2[e] * mu[e] - a1[e]);
+    }
+  }
+  const long long stride = (long long)gridDim.x * rows_per_block;
+  long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / groups;
+  for (; row + 3 * stride < M; row += 4 * stride) {
+    uint4 dv[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dv[u] = *reinterpret_cast<const uint4*>(dy + (row + u * stride) * C + cg * 8);   // in place: coherent load
+      xv[u] = ld_stream_v4(X + (row + u * stride) * C + cg * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d[8], x[8];
+      unpack8(dv[u], d);
+      unpack8(xv[u], x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
+      st_stream_v4(dy + (row + u * stride) * C + cg * 8, pack8(d));
+    }
+  }
+  for (; row < M; row += stride) {
+    float d[8], x[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + row * C + cg * 8), d);
+    unpack8(ld_stream_v4(X + row * C + cg * 8), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
+    st_stream_v4(dy + row * C + cg * 8, pack8(d));
   }
 }
 
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
                  const float* m2, cudaStream_t st) {
+  if (C % 8 || kEwThreads % (C / 8)) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must divide into the block", C);
   RXB_PROF(st, PROF_ELEMENTWISE);
-  RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M * (C / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2));
+  const int rows_per_block = kEwThreads / (C / 8);
+  RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

@@ -1,3 +1,2 @@
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench11.json 2> gpurun_out/bench11.err; tail -3 gpurun_out/bench11.err; cut -c1-200 gpurun_out/bench11.json
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench11_ref.json 2> gpurun_out/bench11_ref.err; tail -3 gpurun_out/bench11_ref.err; cut -c1-300 gpurun_out/bench11_ref.json
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench12.json 2> gpurun_out/bench12.err; cut -c1-200 gpurun_out/bench12.json; tail -3 gpurun_out/bench12.err
