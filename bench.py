@@ -252,7 +252,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short collective timeout: a rank mismatch aborts in two minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.require_gpu()
     lib = _lib.load()
     peaks = measured_peaks()
@@ -358,17 +360,20 @@ def run_ours(args):
 
     # ---- kernel-family breakdown (event-bracketed launches, separate untimed pass) and HBM kernels
     breakdown, roofline, hbm_kernels, roofline_tensor, conv_kernels = None, None, None, None, None
+    # every rank runs the profiled steps (they contain the gradient all-reduces); only rank 0 reports
+    ncat = 9
+    msb = (ctypes.c_float * ncat)()
+    cnt = (ctypes.c_int64 * ncat)()
+    prof_steps = 2
+    torch.cuda.synchronize()
+    lib.rxb_profile_enable(1)
+    for _ in range(prof_steps):
+        step(False)
+    _lib.check(lib.rxb_profile_collect(msb, cnt, ncat))
+    lib.rxb_profile_enable(0)
+    if world > 1:
+        dist.barrier()
     if rank == 0:
-        ncat = 9
-        msb = (ctypes.c_float * ncat)()
-        cnt = (ctypes.c_int64 * ncat)()
-        prof_steps = 2
-        torch.cuda.synchronize()
-        lib.rxb_profile_enable(1)
-        for _ in range(prof_steps):
-            step(False)
-        _lib.check(lib.rxb_profile_collect(msb, cnt, ncat))
-        lib.rxb_profile_enable(0)
         names = ["stats", "loader", "conv_fwd", "conv_dgrad", "conv_wgrad", "elementwise", "head", "optimizer", "tta"]
         breakdown = {nme: {"ms_per_step": msb[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps}
                      for i, nme in enumerate(names)}
