@@ -294,9 +294,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_sync();
   if (PROLOGUE) {
     const int padded = p.kb_per_tap * BK;
-    for (int c = threadIdx.x; c < padded; c += kConvThreads) {
-      aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
-      aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+    if (p.prep.sum != nullptr) {
+      // fused BatchNorm fold (the arithmetic of bn_prep_kernel); CTA (0,0) publishes it for the backward pass
+      const bool publish = blockIdx.x == 0 && blockIdx.y == 0;
+      for (int c = threadIdx.x; c < padded; c += kConvThreads) {
+        float sc = 0.f, sh = 0.f;
+        if (c < p.cin) {
+          float mean, var;
+          if (p.prep.training) {
+            mean = p.prep.sum[c] / p.prep.count;
+            var = fmaxf(p.prep.sumsq[c] / p.prep.count - mean * mean, 0.f);
+          } else {
+            mean = p.prep.rmean[c];
+            var = p.prep.rvar[c];
+          }
+          const float rstd = rsqrtf(var + p.prep.eps);
+          sc = p.prep.gamma[c] * rstd;
+          sh = p.prep.beta[c] - mean * sc;
+          if (publish) {
+            p.prep.f_scale[c] = sc;
+            p.prep.f_shift[c] = sh;
+            p.prep.f_mean[c] = mean;
+            p.prep.f_rstd[c] = rstd;
+            if (p.prep.training && p.prep.rmean != nullptr) {
+              const float unbiased = p.prep.count > 1.f ? var * (p.prep.count / (p.prep.count - 1.f)) : var;
+              p.prep.rmean[c] = (1.f - p.prep.momentum) * p.prep.rmean[c] + p.prep.momentum * mean;
+              p.prep.rvar[c] = (1.f - p.prep.momentum) * p.prep.rvar[c] + p.prep.momentum * unbiased;
+            }
+          }
+        }
+        aux->s_scale[c] = sc;
+        aux->s_shift[c] = sh;
+      }
+    } else {
+      for (int c = threadIdx.x; c < padded; c += kConvThreads) {
+        aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
+        aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+      }
     }
   }
   for (int c = threadIdx.x; c < kMaxBN; c += kConvThreads) {

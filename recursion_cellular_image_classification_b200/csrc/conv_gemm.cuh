@@ -22,6 +22,21 @@ enum EpiMode {
 };
 enum OutMode { OUT_DY = 0, OUT_G_WRITE = 1, OUT_G_ACCUM = 2 };
 
+// Fused BatchNorm fold for the A prologue: when sum != nullptr the kernel derives relu(x*scale+shift)'s scale/shift
+// itself from the per-channel batch sums (training) or running statistics (eval) - the arithmetic of bn_prep_kernel -
+// and CTA (0,0) stores the fold (scale, shift, mean, rstd) for the backward kernels and updates the running statistics.
+struct BnPrepArgs {
+  const float* sum;
+  const float* sumsq;
+  const float* gamma;
+  const float* beta;
+  float* rmean;
+  float* rvar;
+  float count, eps, momentum;
+  int training;
+  float *f_scale, *f_shift, *f_mean, *f_rstd;
+};
+
 struct GemmParams {
   int B, H, W;      // pixel space shared by A and the output (stride-1 convolutions)
   int n_total;      // valid N (multiple of 32)
@@ -36,6 +51,7 @@ struct GemmParams {
   // prologue (A := relu(A*scale + shift)), indexed by A channel
   const float* scale;
   const float* shift;
+  BnPrepArgs prep;  // alternative to scale/shift: fold computed in the kernel (prep.sum != nullptr)
   // EPI_DGRAD_BN: folded BatchNorm of the consumer, per N channel
   const float* e_scale;
   const float* e_shift;

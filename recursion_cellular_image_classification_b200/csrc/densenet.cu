@@ -265,7 +265,7 @@ static int check_cfg(const rxb_dn121_config* c) {
 // ---------------------------------------------------------------------------------------------- helpers
 static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* A, int ldA, int cin,
                       const ConvLayer& cv, int Cout, int taps, int pad, const BnFold* pro, __nv_bfloat16* out,
-                      int ldc, int c_off, float* ssum, float* ssq, cudaStream_t st) {
+                      int ldc, int c_off, float* ssum, float* ssq, cudaStream_t st, const BnPrepArgs* fused = nullptr) {
   GemmParams p = {};
   p.B = B; p.H = H; p.W = W;
   p.n_total = Cout;
@@ -277,6 +277,7 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
   p.ch_sum = ssum ? ssum + c_off : nullptr;
   p.ch_sumsq = ssq ? ssq + c_off : nullptr;
   if (pro) { p.scale = pro->scale; p.shift = pro->shift; }
+  if (fused) p.prep = *fused;
   return launch_conv_gemm(p, A, ldA, n.arena + cv.fwd_off, out, ldc, c_off, nullptr, 0, cin <= 32 ? 32 : 64,
                           pro != nullptr, st);
 }
@@ -323,6 +324,18 @@ static int conv_wgrad_any(int B, int H, int W, const __nv_bfloat16* A, int ldA, 
   return RXB_OK;
 }
 
+// the same fold, computed inside the consuming conv kernel's prologue (one launch less per BatchNorm)
+static BnPrepArgs fused_prep(const rxb_dn121& n, const BnLayer& bn, const float* sum, const float* sq, float count,
+                             int training) {
+  BnPrepArgs a = {};
+  a.sum = sum; a.sumsq = sq;
+  a.gamma = n.params + bn.gamma_off; a.beta = n.params + bn.beta_off;
+  a.rmean = n.buffers + bn.rm_off; a.rvar = n.buffers + bn.rv_off;
+  a.count = count; a.eps = n.cfg.bn_eps; a.momentum = n.cfg.bn_momentum; a.training = training;
+  a.f_scale = bn.fold.scale; a.f_shift = bn.fold.shift; a.f_mean = bn.fold.mean; a.f_rstd = bn.fold.rstd;
+  return a;
+}
+
 static int prep(const rxb_dn121& n, const BnLayer& bn, const float* sum, const float* sq, float count, int training,
                 cudaStream_t st) {
   return bn_prep(sum, sq, count, n.params + bn.gamma_off, n.params + bn.beta_off, n.buffers + bn.rm_off,
@@ -359,12 +372,13 @@ static int forward(rxb_dn121& n, const void* input, int training, cudaStream_t s
   for (int b = 0; b < 4; ++b) {
     Block& blk = n.blocks[b];
     for (auto& L : blk.layers) {
-      RXB_TRY(prep(n, L.bn1, blk.xsum, blk.xsq, (float)blk.M, training, st));
+      // both BatchNorm folds are derived inside the consuming conv kernels' prologues
+      const BnPrepArgs p1 = fused_prep(n, L.bn1, blk.xsum, blk.xsq, (float)blk.M, training);
       RXB_TRY(conv_store(n, c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, L.c1, kBott, 1, 0, &L.bn1.fold, L.Y, kBott, 0,
-                         stats ? L.ysum : nullptr, stats ? L.ysq : nullptr, st));
-      RXB_TRY(prep(n, L.bn2, L.ysum, L.ysq, (float)blk.M, training, st));
+                         stats ? L.ysum : nullptr, stats ? L.ysq : nullptr, st, &p1));
+      const BnPrepArgs p2 = fused_prep(n, L.bn2, L.ysum, L.ysq, (float)blk.M, training);
       RXB_TRY(conv_store(n, c.B, blk.H, blk.W, L.Y, kBott, kBott, L.c2, kGrowth, 3, 1, &L.bn2.fold, blk.X, blk.Ctot,
-                         L.Cin, stats ? blk.xsum : nullptr, stats ? blk.xsq : nullptr, st));
+                         L.Cin, stats ? blk.xsum : nullptr, stats ? blk.xsq : nullptr, st, &p2));
     }
     if (b < 3) {
       Transition& t = n.trans[b];

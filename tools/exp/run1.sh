@@ -1,2 +1,2 @@
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench12.json 2> gpurun_out/bench12.err; cut -c1-200 gpurun_out/bench12.json; tail -3 gpurun_out/bench12.err
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench13.json 2> gpurun_out/bench13.err; cut -c1-200 gpurun_out/bench13.json; tail -3 gpurun_out/bench13.err
