@@ -47,8 +47,8 @@ constexpr int kMaxPrologueC = 1024;
 constexpr int kMaxBN = 128;
 
 struct __align__(16) GemmAux {
-  float s_scale[kMaxPrologueC + 64];
-  float s_shift[kMaxPrologueC + 64];
+  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
+  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
   float e_scale[kMaxBN];
   float e_shift[kMaxBN];
   uint32_t e_thr2[kMaxBN / 2];   // dgrad ReLU mask as a packed-bf16 threshold test: (x ^ sgn) > thr, two columns per word
@@ -133,15 +133,13 @@ __device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4]
   *p = v;
 }
 
-__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
-                                                    const PixelTiling& til, int box_w, int box_h, int bx, int by, int bb) {
+__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const __nv_bfloat16* sc,
+                                                    const __nv_bfloat16* sh, int t, const PixelTiling& til, int box_w,
+                                                    int box_h, int bx, int by, int bb) {
   const int j = t & 7;
-  uint32_t s[4], h[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    s[e] = pack_bf16x2(sc[j * 8 + 2 * e], sc[j * 8 + 2 * e + 1]);
-    h[e] = pack_bf16x2(sh[j * 8 + 2 * e], sh[j * 8 + 2 * e + 1]);
-  }
+  // the 8 channels of this thread's chunk: one 16-byte load each for scale and shift (already bf16 pairs)
+  const uint4 s4 = *reinterpret_cast<const uint4*>(sc + j * 8), h4 = *reinterpret_cast<const uint4*>(sh + j * 8);
+  const uint32_t s[4] = {s4.x, s4.y, s4.z, s4.w}, h[4] = {h4.x, h4.y, h4.z, h4.w};
   const int tb = 1 << til.tb_log2;
   const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
@@ -323,13 +321,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        aux->s_scale[c] = sc;
-        aux->s_shift[c] = sh;
+        aux->s_scale[c] = __float2bfloat16_rn(sc);
+        aux->s_shift[c] = __float2bfloat16_rn(sh);
       }
     } else {
       for (int c = threadIdx.x; c < padded; c += kConvThreads) {
-        aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
-        aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+        aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
+        aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
       }
     }
   }
@@ -736,8 +734,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 // Weight gradient
 struct __align__(16) WgradAux {
-  float s_scale[kMaxPrologueC + 64];
-  float s_shift[kMaxPrologueC + 64];
+  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
+  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -774,7 +772,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int chunk0 = blockIdx.y * p.chunks_per_cta;
   // accumulators held by this CTA: channel chunks (classic) or filter taps (shift_dout)
   const int n_local = p.shift_dout ? taps : min(p.chunks_per_cta, p.n_chunks - chunk0);
-  const int stages_per_tile = p.shift_dout ? 1 : n_local;
+  const int stages_per_tile = (p.shift_dout || p.a_halo) ? 1 : n_local;
+  const int a_halo_tx = halo_w * halo_h * p.bkc * 2;     // a_halo: bytes of the full-halo A box
   const int tile_begin = blockIdx.x * p.pix_tiles_per_cta;
   const int tile_end = min(m_tiles, tile_begin + p.pix_tiles_per_cta);
   const int a_row_bytes = p.bkc * 2;
@@ -802,8 +801,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.prologue) {
     const int padded = p.boxes_per_tap * p.bkc;
     for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
-      aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
-      aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+      aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
+      aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
     }
   }
   ptx::tcgen05_fence_before();
@@ -827,9 +826,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 11);
-          ptx::mbar_arrive_expect_tx(&aux->full[stage],
-                                     kWgA_BYTES + (p.shift_dout == 2 ? halo_tx : p.shift_dout ? b_bytes : 0));
+          ptx::mbar_arrive_expect_tx(&aux->full[stage], (p.a_halo ? a_halo_tx : kWgA_BYTES) +
+                                                            (p.shift_dout == 2 ? halo_tx : p.shift_dout ? b_bytes : 0));
           uint8_t* a_dst = smA + (size_t)stage * kWgA_BYTES;
+          if (p.a_halo) {   // dW[t] = sum_q dOut[q] * A[q + t - pad]: the box starts pad pixels before the tile
+            ptx::tma_load_4d(a_dst, &tmA, &aux->full[stage], 0, x0 - p.pad_x, y0 - p.pad_y, b0);
+          } else
           for (int i = 0; i < p.boxes_per_chunk; ++i) {
             const int kk = (chunk0 + cl) * p.boxes_per_chunk + i;
             int tp = 0, c0 = p.boxes_per_tap * p.bkc;  // fully out of bounds -> zero box
@@ -902,7 +904,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t a_lo = ptx::desc_lo(da0) + (uint32_t)stage * a_stage16;
             const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)(p.shift_dout ? stage : db) * b_stage16;
             const uint32_t accumulate = tile > tile_begin ? 1u : 0u;
-            if (p.shift_dout == 2) {
+            if (p.a_halo) {
+              // chunk ty = filter row: its taps_x taps are M atoms one pixel row apart (leading stride = one row),
+              // an 8-pixel K group is one tile row, consecutive groups lie halo_w rows apart
+              const uint64_t dah = ptx::make_smem_desc(0, (uint32_t)a_row_bytes, (uint32_t)halo_w * a_row_bytes, a_swz);
+              const uint32_t ah_hi = ptx::desc_hi(dah);
+              const uint32_t ah_lo = ptx::desc_lo(dah) + (ptx::smem_u32(smA) >> 4) + (uint32_t)stage * a_stage16;
+              const uint32_t ah_kstep16 = (2u * (uint32_t)halo_w * a_row_bytes) >> 4;
+              for (int ty = 0; ty < n_local; ++ty) {
+                const uint32_t acc = tmem_base + (uint32_t)ty * p.n;
+                const uint32_t a_lo_t = ah_lo + (((uint32_t)((chunk0 + ty) * halo_w) * a_row_bytes) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  ptx::umma_bf16_ss_parts(acc, a_lo_t + ks * ah_kstep16, ah_hi, b_lo + ks * d_kstep16, b_hi, idesc,
+                                          ks > 0 ? 1u : accumulate);
+              }
+            } else if (p.shift_dout == 2) {
               for (int ty = 0; ty < p.taps_y; ++ty) {
                 const uint32_t acc = tmem_base + (uint32_t)(ty * p.taps_x) * p.n;
                 const uint32_t b_lo_t = b_lo + (uint32_t)((p.taps_y - 1 - ty) * halo_w) * d_row16;
@@ -1275,7 +1292,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
       p.shift_dout = 2;
     }
   }
-  const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
+  int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int chunk_groups;
   if (p.shift_dout) {
     p.n_chunks = 1;
@@ -1300,8 +1317,24 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
     }
     chunk_groups = ceil_div(p.n_chunks, p.chunks_per_cta);
   }
+  // full-halo A box (the stem's 4x4 taps over 32 channels): needs a filter row per 128-row chunk, no A prologue,
+  // 8-pixel tile rows and every chunk in one CTA
+  p.a_halo = 0;
+  {
+    static const int dbg_no_a_halo = getenv("RXB_DBG_NO_A_HALO") ? atoi(getenv("RXB_DBG_NO_A_HALO")) : 0;
+    PixelTiling tall = make_tiling_tall(p.t.B, p.t.H, p.t.W);
+    if (!dbg_no_a_halo && !p.shift_dout && taps > 1 && !p.prologue && p.bkc * p.taps_x == 128 && p.boxes_per_tap == 1 &&
+        p.n_chunks == p.taps_y && p.taps_y * p.n <= 512 && tall.tw_log2 == 3 && tall.tb_log2 == 0 &&
+        (8 + p.taps_x - 1) * ((1 << tall.th_log2) + p.taps_y - 1) * p.bkc * 2 <= kWgA_BYTES) {
+      p.a_halo = 1;
+      p.t = tall;
+      p.chunks_per_cta = p.n_chunks;
+      chunk_groups = 1;
+    }
+  }
   if (p.prologue && p.boxes_per_tap * p.bkc > kMaxPrologueC + 64)
     return set_error(RXB_ERR_INVALID, "conv_wgrad: cin too large");
+  m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int pix_ctas = num_sms() / chunk_groups;
   if (pix_ctas < 1) pix_ctas = 1;
   if (pix_ctas > m_tiles) pix_ctas = m_tiles;
@@ -1310,9 +1343,10 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
 
   CUtensorMap tmA, tmD;
   const int th = 1 << p.t.th_log2;
-  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc, th);
-  if (rc) return rc;
   const int tw = 1 << p.t.tw_log2;
+  int rc = p.a_halo ? make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc, th + p.taps_y - 1, tw + p.taps_x - 1)
+                    : make_act_tmap(&tmA, A, p.t, p.cin, ldA, p.bkc, th);
+  if (rc) return rc;
   if (p.shift_dout == 2)
     rc = make_act_tmap(&tmD, static_cast<const __nv_bfloat16*>(dOut) + p.n_off, p.t, p.n, ldD, p.n >= 64 ? 64 : 32,
                        th + p.taps_y - 1, tw + p.taps_x - 1);

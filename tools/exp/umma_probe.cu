@@ -10,7 +10,7 @@
 #include "ptx.cuh"
 using namespace rxb;
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_rows_step, long long* out_cycles) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_rows_step, long long* out_cycles, int Mrows = 128) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int a_ro
   ptx::tcgen05_fence_after();
   const uint32_t tmem = tmem_base_s;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = ptx::make_idesc_bf16(128, N, 0, 0);
+    const uint32_t idesc = ptx::make_idesc_bf16(Mrows, N, 0, 0);
     const uint32_t a_addr = ptx::smem_u32(smem), b_addr = ptx::smem_u32(smem + 64 * 1024);
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -205,6 +205,15 @@ int main() {
       long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
       printf("rate: M=128 N=%3d K=16 a_row_step=%d : %.1f cycles/MMA (floor %d)\n", N, step, (double)c / iters, N / 2);
     }
+  for (int N : {64, 128, 256}) {
+    const int iters = 2048;
+    rate_kernel<<<148, 128, 100 * 1024>>>(N, iters, 0, dc, 64);
+    CK(cudaDeviceSynchronize());
+    rate_kernel<<<148, 128, 100 * 1024>>>(N, iters, 0, dc, 64);
+    CK(cudaDeviceSynchronize());
+    long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+    printf("rate: M= 64 N=%3d K=16 : %.1f cycles/MMA\n", N, (double)c / iters);
+  }
   // ---- shift correctness
   const int a_rows = 400;
   std::vector<__nv_bfloat16> hA(a_rows * 64), hB(32 * 64);
