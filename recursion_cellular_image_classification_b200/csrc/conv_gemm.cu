@@ -1145,7 +1145,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
       // 128-byte rows: the whole (tw+taps_x-1) x (th+taps_y-1) neighbourhood is ONE box and every tap is a descriptor
       // offset into it (the weight panel must then be resident: one A stage serves all taps of a k-block)
       static const int dbg_no_full_halo = getenv("RXB_DBG_NO_FULL_HALO") ? atoi(getenv("RXB_DBG_NO_FULL_HALO")) : 0;
-      if (bk == 64 && !dbg_no_full_halo) p.halo = 2;
+      // (64-byte rows, BK = 32: the same holds for the 64 B swizzle - probed too; dbg value 2 keeps them on row halo)
+      if ((bk == 64 || dbg_no_full_halo != 2) && dbg_no_full_halo != 1) p.halo = 2;
     }
   }
   const int taps = p.taps_x * p.taps_y;

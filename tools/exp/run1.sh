@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
-timeout 200 python tools/bench_conv.py 2>&1 | grep -E "k4|Cin224|k3 pro1 stats1" > gpurun_out/bc19.log 2>&1; cat gpurun_out/bc19.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench14.json 2> gpurun_out/bench14.err; cut -c1-200 gpurun_out/bench14.json; tail -3 gpurun_out/bench14.err
+timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_densenet.py -x -q -m gpu > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
+timeout 200 python tools/bench_conv.py 2>&1 | grep -E "k4|dgrd|Cin32" > gpurun_out/bc20.log 2>&1; cat gpurun_out/bc20.log
