@@ -85,6 +85,7 @@ PixelTiling make_tiling(int B, int H, int W) {
   t.tiles_x = ceil_div(W, 1 << twl);
   t.tiles_y = ceil_div(H, 1 << thl);
   t.tiles_b = ceil_div(B, 1 << tbl);
+  t.x_step = 1 << twl;
   return t;
 }
 
@@ -98,6 +99,7 @@ PixelTiling make_tiling_tall(int B, int H, int W) {
   t.tiles_x = ceil_div(W, 1 << twl);
   t.tiles_y = ceil_div(H, 1 << thl);
   t.tiles_b = ceil_div(B, 1 << tbl);
+  t.x_step = 1 << twl;
   return t;
 }
 
@@ -106,7 +108,7 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
   const int rest = m_tile / t.tiles_x;
   const int ty = rest % t.tiles_y;
   const int tb = rest / t.tiles_y;
-  x0 = tx << t.tw_log2;
+  x0 = tx * t.x_step;
   y0 = ty << t.th_log2;
   b0 = tb << t.tb_log2;
 }
@@ -252,10 +254,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   const int my_tiles = blockIdx.x < m_tiles ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int n0 = blockIdx.y * p.bn;
-  const int groups = p.halo == 2 ? 1 : p.halo == 1 ? p.taps_x : taps;  // A loads per k-block
+  const int groups = p.halo >= 2 ? 1 : p.halo == 1 ? p.taps_x : taps;  // A loads per k-block
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
-  const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;
+  const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;   // halo 3: the 16-wide M tile already contains its x halo
+  const bool xmerge = p.halo == 3;
+  const int out_w = xmerge ? tw - (p.taps_x - 1) : tw;       // valid output columns of a tile
   const int n_epi_threads = dgrad ? 512 : 256;                 // dgrad: sixteen worker warps ; store: workers 8-15
 
   // ---- one-time setup
@@ -365,8 +369,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // the whole weight panel of this N tile stays in shared memory for the life of the CTA
         ptx::mbar_arrive_expect_tx(&aux->b_full, taps * p.kb_per_tap * b_tap);
         for (int tap = 0; tap < taps; ++tap)
-          for (int kb = 0; kb < p.kb_per_tap; ++kb)
-            ptx::tma_load_3d(smB + (size_t)(tap * p.kb_per_tap + kb) * b_tap, &tmB, &aux->b_full, kb * BK, n0, tap);
+          for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+            // x-merged: slots ordered [ty][kb][tx] so the taps of a filter row are contiguous rows of ONE B operand
+            const int ty = tap / p.taps_x, tx = tap - ty * p.taps_x;
+            const int slot = p.halo == 3 ? (ty * p.kb_per_tap + kb) * p.taps_x + tx : tap * p.kb_per_tap + kb;
+            ptx::tma_load_3d(smB + (size_t)slot * b_tap, &tmB, &aux->b_full, kb * BK, n0, tap);
+          }
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -386,7 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              n0 + bx * cw, x0, y0, b0);
         }
         for (int g = 0; g < groups; ++g) {
-          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo == 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 1);
             ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + (p.b_resident ? 0 : b_stage));
@@ -408,7 +416,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // =============================== MMA issuer: the whole warp walks the pipeline (so every address is warp-uniform);
     // one elected lane issues the tcgen05 instructions
     {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.bn, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.halo == 3 ? p.bn * p.taps_x : p.bn, 0, 0);
       const uint32_t row_tap16 = ((uint32_t)tw * ROW_BYTES) >> 4;  // one image row of the box, in descriptor units
       const uint64_t desc0 = ptx::make_smem_desc(0, 16, kSBO, kSwz);
       const uint32_t d_hi = ptx::desc_hi(desc0), d_lo0 = ptx::desc_lo(desc0);
@@ -466,7 +474,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tcgen05_fence_after();
             if (ptx::elect_one()) {
               const uint32_t a_lo = d_lo0 + smA16 + (uint32_t)stage * a_stage16;
-              if (p.halo == 2) {
+              if (p.halo == 3) {
+                // x-merged: per filter row ONE MMA chain with N = taps_x*bn; accumulator columns [tx][n]
+                for (int ty = 0; ty < p.taps_y; ++ty) {
+                  const uint32_t b_lo = d_lo0 + smB16 + (uint32_t)((ty * p.kb_per_tap + kb) * p.taps_x) * b_tap16;
+                  const uint32_t a_lo_t = a_lo + (uint32_t)ty * row_tap16;
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) {
+                    ptx::umma_bf16_ss_parts(d_tmem, a_lo_t + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                }
+              } else if (p.halo == 2) {
                 for (int tap = 0; tap < taps; ++tap) {
                   const int ty = tap / p.taps_x, tx = tap - ty * p.taps_x;
                   const uint32_t b_lo = d_lo0 + smB16 + (uint32_t)(tap * p.kb_per_tap + kb) * b_tap16;
@@ -578,8 +597,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
       const int r2 = row >> p.t.tw_log2;
-      const bool row_valid = x0 + (row & (tw - 1)) < p.t.W && y0 + (r2 & (th - 1)) < p.t.H &&
+      const int xx = row & (tw - 1);                       // column inside the M tile
+      const int xo = xmerge ? xx - p.pad_x : xx;           // output column inside the tile (x-merged: minus the halo)
+      const bool row_valid = xo >= 0 && xo < out_w && x0 + xo < p.t.W && y0 + (r2 & (th - 1)) < p.t.H &&
                              b0 + (r2 >> p.t.th_log2) < p.t.B;
+      const int srow = xmerge ? (r2 * out_w + min(max(xo, 0), out_w - 1)) : row;   // staging row of this thread
       ptx::mbar_wait(&aux->tmem_full[acc], acc_phase, 4);
       ptx::tcgen05_fence_after();
       if (leader) RXB_TL(2, it, 4);
@@ -588,6 +610,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c, r);
         ptx::tmem_ld_wait();
+        if (xmerge) {
+          // out[x] = Z_0[x-1] + Z_1[x] + Z_2[x+1] (pad 1): partial sums of the neighbouring input columns sit in the
+          // neighbouring lanes (16-lane segments = tile rows; the segment ends are halo columns, not stored)
+          uint32_t r1[32], r2v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + p.bn + c, r1);
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + 2 * p.bn + c, r2v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r[i]), 1);
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2v[i]), 1);
+            r[i] = __float_as_uint(left + __uint_as_float(r1[i]) + right);
+          }
+        }
         uint32_t packed[16];
         if (!dgrad) {
 #pragma unroll
@@ -595,10 +631,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             packed[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
             if (p.do_stats && !row_valid) packed[i] = 0u;
           }
+          if (!xmerge || (xo >= 0 && xo < out_w)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *staging_chunk(so, cw, row, c + 8 * i) =
-                make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              *staging_chunk(so, cw, srow, c + 8 * i) =
+                  make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          }
           if (p.do_stats && !p.mma_stats) {
             float v[32], sq[32];
 #pragma unroll
@@ -708,7 +746,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
         for (int g = 0; g < groups; ++g) {
-          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo == 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
+          const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
             transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
@@ -1150,11 +1188,24 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     }
   }
   const int taps = p.taps_x * p.taps_y;
-  const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   if (p.halo == 2) {
     const long long panel = (long long)taps * p.kb_per_tap * p.bn * bk * 2;
     if (panel > 96 * 1024) p.halo = 1;
   }
+  // x-merged tiles for narrow outputs: a tcgen05.mma costs the same ~70 cycles for every N <= 128, so the taps_x taps
+  // of a filter row become ONE N = taps_x*Cout MMA over a 16-wide M tile that carries its own x halo (14 valid
+  // columns); the epilogue adds the neighbouring columns' partial sums with warp shuffles.  3x fewer MMAs for 3x3/32.
+  static const int dbg_no_xmerge = getenv("RXB_DBG_NO_XMERGE") ? atoi(getenv("RXB_DBG_NO_XMERGE")) : 0;
+  if (!dbg_no_xmerge && p.halo == 2 && !dgrad && bk == 64 && p.taps_x == 3 && p.pad_x == 1 && p.n_tiles == 1 &&
+      p.bn == 32 && p.H >= 8 && p.W >= 14) {
+    p.halo = 3;
+    p.t.tw_log2 = 4; p.t.th_log2 = 3; p.t.tb_log2 = 0;
+    p.t.x_step = 16 - (p.taps_x - 1);
+    p.t.tiles_x = ceil_div(p.W, p.t.x_step);
+    p.t.tiles_y = ceil_div(p.H, 8);
+    p.t.tiles_b = p.B;
+  }
+  const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
   const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;
   p.rows_a = p.halo ? box_h * box_w : 128;
@@ -1172,7 +1223,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     if (rc) return rc;
   }
   const int cw = p.bn >= 64 ? 64 : 32;
-  rc = make_act_tmap(&tmOut, static_cast<__nv_bfloat16*>(out) + c_off, p.t, p.n_total, ldc, cw, th);
+  rc = make_act_tmap(&tmOut, static_cast<__nv_bfloat16*>(out) + c_off, p.t, p.n_total, ldc, cw, th,
+                     p.halo == 3 ? p.t.x_step : 0);
   if (rc) return rc;
   if (dgrad) {
     rc = make_act_tmap(&tmX, X, p.t, p.n_total, ldx, cw, th);
@@ -1202,8 +1254,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   static const int dbg_no_resident = getenv("RXB_DBG_NO_RESIDENT") ? atoi(getenv("RXB_DBG_NO_RESIDENT")) : 0;
   static const int dbg_one_stg = getenv("RXB_DBG_ONE_STG") ? atoi(getenv("RXB_DBG_ONE_STG")) : 0;
   const bool allow_res = !(dbg_no_resident == 1 || (dbg_no_resident == 2 && p.bn < 128));
-  if ((allow_res || p.halo == 2) && b_panel <= 96 * 1024 && (m_tiles > gx || p.halo == 2) &&
-      (avail - b_panel) / a_stage >= (p.halo == 2 ? 2 : 3)) {
+  if ((allow_res || p.halo >= 2) && b_panel <= 96 * 1024 && (m_tiles > gx || p.halo >= 2) &&
+      (avail - b_panel) / a_stage >= (p.halo >= 2 ? 2 : 3)) {
     p.b_resident = 1;
     per_stage = a_stage;
     avail -= b_panel;
@@ -1223,7 +1275,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   long long stages = avail / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
-  if (p.halo == 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
+  if (p.halo >= 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
   p.stages = (int)stages;
   const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) +
                                (dgrad ? p.n_stg - 1 : p.n_stg) * stage_tile + fixed);

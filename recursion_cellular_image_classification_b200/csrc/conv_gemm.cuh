@@ -12,6 +12,7 @@ struct PixelTiling {
   int W, H, B;
   int tw_log2, th_log2, tb_log2;
   int tiles_x, tiles_y, tiles_b;
+  int x_step;   // distance between tile origins in x: 1 << tw_log2, or tw - (taps_x - 1) when the M tile carries its x halo
 };
 PixelTiling make_tiling(int B, int H, int W);       // wide tiles (tw as large as possible)
 PixelTiling make_tiling_tall(int B, int H, int W);  // tw <= 8: tall tiles for the row-halo tap reuse
@@ -59,6 +60,9 @@ struct GemmParams {
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;
   int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
+                    // 2: one box with the full x and y halo, every tap a descriptor offset
+                    // 3: x-merged: the M tile is 16 wide INCLUDING its x halo, the taps_x taps of a filter row are one
+                    //    N = taps_x*Cout MMA and the epilogue adds the neighbours' partial sums with warp shuffles
   int rows_a;       // pixel rows of one A stage (128, or (th+taps_y-1)*tw with halo)
   int stages;       // A (and streamed B) pipeline depth
   int n_stg;        // output staging buffers (stores: 1 or 2; dgrad: 2..4 activation-tile buffers staged in place)
