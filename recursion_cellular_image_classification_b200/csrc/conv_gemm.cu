@@ -153,7 +153,8 @@ __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, con
     for (int row = t >> 3; row < rows; row += kRowsPerIter) {
       const int r2 = row / box_w;
       const int xi = row - r2 * box_w;
-      const int yi = r2 % box_h, bi = r2 / box_h;
+      const int bi = tb == 1 ? 0 : r2 / box_h;     // halo boxes hold one image: no second division
+      const int yi = r2 - bi * box_h;
       const int x = bx + xi, y = by + yi, b = bb + bi;
       if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
       transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
@@ -1197,7 +1198,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   // columns); the epilogue adds the neighbouring columns' partial sums with warp shuffles.  3x fewer MMAs for 3x3/32.
   static const int dbg_no_xmerge = getenv("RXB_DBG_NO_XMERGE") ? atoi(getenv("RXB_DBG_NO_XMERGE")) : 0;
   if (!dbg_no_xmerge && p.halo == 2 && !dgrad && bk == 64 && p.taps_x == 3 && p.pad_x == 1 && p.n_tiles == 1 &&
-      p.bn == 32 && p.H >= 8 && p.W >= 14) {
+      p.bn == 32 && p.H >= 8 && p.W >= 56) {   // narrower images waste too many of the 14-wide tiles' columns
     p.halo = 3;
     p.t.tw_log2 = 4; p.t.th_log2 = 3; p.t.tb_log2 = 0;
     p.t.x_step = 16 - (p.taps_x - 1);
