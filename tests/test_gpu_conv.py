@@ -41,7 +41,10 @@ CASES = [
     (2, 12, 20, 128, 128, 32, 3, True),
     (1, 16, 16, 512, 512, 256, 1, False),    # transition-like, N = 256
     (1, 16, 16, 32, 32, 64, 4, False),       # space-to-depth stem: 4x4 taps, 32 channels per tap
-    (2, 128, 128, 128, 128, 32, 3, True),    # block-1 geometry (tile = one 128-pixel row)
+    (2, 128, 128, 128, 128, 32, 3, True),    # block-1 geometry: x-merged 14-wide tiles (128 = 9*14 + 2)
+    (1, 24, 72, 128, 128, 32, 3, True),      # x-merged tiles clipped in x (72 = 5*14 + 2) with three tile rows
+    (2, 20, 60, 128, 128, 32, 3, False),     # x-merged, H not a multiple of the 8-row tile
+    (1, 40, 72, 32, 32, 64, 4, False),       # stem geometry with a full-halo box clipped on every side
 ]
 
 
@@ -85,8 +88,11 @@ WG_CASES = [
     (4, 8, 8, 640, 1024, 128, 1, True),      # 5 accumulator groups -> two chunk groups
     (2, 12, 20, 128, 128, 32, 3, False),
     (1, 16, 16, 256, 256, 256, 1, False),    # transition-like
-    (1, 16, 16, 32, 32, 64, 4, False),       # stem-like: 32-channel boxes, 4 taps per accumulator group
-    (2, 64, 64, 128, 128, 32, 3, True),
+    (1, 16, 16, 32, 32, 64, 4, False),       # stem-like: ONE full-halo input box, a filter row per accumulator group
+    (1, 40, 24, 32, 32, 64, 4, False),       # ... with tiles hanging over the image edge
+    (2, 64, 64, 128, 128, 32, 3, True),      # full-halo dOut box, a filter row's taps as one N = 96 MMA
+    (1, 20, 28, 128, 128, 32, 3, True),      # ... image not a multiple of the 8x16 tile
+    (2, 32, 32, 1024, 1024, 128, 1, True),   # 8 channel chunks: dOut tile shared by the chunks of a CTA
 ]
 
 
