@@ -287,11 +287,40 @@ def run_ours(args):
     n_phases = lib.rxb_dn121_num_phases()
     ranges = [net.phase_grad_range(B, IMG, IMG, ph) for ph in range(n_phases)]
 
-    def step(from_host):
+    # end-to-end arm: every step's u8 batch comes from pinned host memory.  Like a prefetching data loader, the copy of
+    # step i+1 runs on a copy stream into the second device buffer while step i computes; each timed step still
+    # performs exactly one H2D copy inside the timed region (the first one is not hidden).
+    copy_stream = torch.cuda.Stream(device=dev)
+    src2 = [src, torch.empty_like(src)]
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    loader_done = [torch.cuda.Event(), torch.cuda.Event()]
+    pf = {"i": 0, "primed": False}
+
+    def issue_copy(buf):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(loader_done[buf])                     # the loader that last read this buffer is done
+            src2[buf].copy_(host_src, non_blocking=True)                 # H2D of one step's u8 batch
+            copy_done[buf].record(copy_stream)
+
+    def step(from_host, last=True):
+        cur = torch.cuda.current_stream()
+        s_in = src
         if from_host:
-            src.copy_(host_src, non_blocking=True)                       # H2D of this step's u8 batch
+            buf = pf["i"] % 2
+            if not pf["primed"]:
+                issue_copy(buf)
+                pf["primed"] = True
+            cur.wait_event(copy_done[buf])
+            s_in = src2[buf]
         aug = torch.randint(0, 16, (B,), device=dev, generator=gen, dtype=torch.uint8)   # D4 code per image
-        ops.load_norm_aug(src, src_idx, exp_id, aug, crop, norm_m, norm_d, (IMG, IMG), ops.OUT_BF16_S2D32, out=xs)
+        ops.load_norm_aug(s_in, src_idx, exp_id, aug, crop, norm_m, norm_d, (IMG, IMG), ops.OUT_BF16_S2D32, out=xs)
+        if from_host:
+            loader_done[buf].record(cur)
+            if last:
+                pf["primed"] = False                                     # the next host step starts with its own copy
+            else:
+                issue_copy(1 - buf)                                      # prefetch the next step's batch
+            pf["i"] += 1
         works = []
         for ph in range(n_phases):
             net.train_step(xs, labels, global_batch=gB, phase=ph, loss_out=loss_dev)
@@ -310,8 +339,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step(from_host)
+        for k in range(steps):
+            step(from_host, last=(k == steps - 1))
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
