@@ -218,7 +218,10 @@ __device__ __forceinline__ uint32_t relu_threshold_bits(float es, float eh, uint
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 16) p.dbg[((r) * 16 + (it)) * 8 + (ev)] = clock64(); \
   } while (0)
 
-template <int BK, bool PROLOGUE>
+// EPI: 0 = store epilogue for 128-wide tiles (statistics, if any, on the tensor pipe); 1 = store epilogue for
+// narrow tiles (bn < 128: shuffle statistics, x-merged 3x3 tiles); 2 = fused ReLU/BatchNorm-backward dgrad epilogue.
+// Compile-time so each variant keeps only its own epilogue (register pressure under the 96-register cap).
+template <int BK, bool PROLOGUE, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
@@ -242,7 +245,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int cw = p.bn >= 64 ? 64 : 32;                         // channels per staging / store box
   const int n_boxes = (p.bn + cw - 1) / cw;
   const int stage_tile = 128 * n_boxes * cw * 2;
-  const bool dgrad = p.epi_mode == EPI_DGRAD_BN;
+  constexpr bool dgrad = EPI == 2;
+  constexpr bool narrow = EPI == 1;
   uint8_t* smA = smem;
   uint8_t* smB = smA + (size_t)stages * a_stage;
   uint8_t* st_out = smB + b_total;
@@ -259,7 +263,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tw = 1 << p.t.tw_log2, th = 1 << p.t.th_log2;
   const int box_h = p.halo ? th + p.taps_y - 1 : th;
   const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;   // halo 3: the 16-wide M tile already contains its x halo
-  const bool xmerge = p.halo == 3;
+  const bool xmerge = narrow && p.halo == 3;
   const int out_w = xmerge ? tw - (p.taps_x - 1) : tw;       // valid output columns of a tile
   const int n_epi_threads = dgrad ? 512 : 256;                 // dgrad: sixteen worker warps ; store: workers 8-15
 
@@ -608,21 +612,68 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (leader) RXB_TL(2, it, 4);
       for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
         if (n0 + c >= p.n_total) break;
+        if constexpr (dgrad) {
+          // fused ReLU / BatchNorm backward: dy = acc * [es*x+eh > 0]; staged value = dy (OUT_DY) or es*dy (G modes),
+          // written over the activation chunk this thread just read.  The mask is a packed-bf16 threshold test.
+          // Sixteen columns at a time (register pressure).
+          const bool scaled = p.out_mode != OUT_DY;
+#pragma unroll
+          for (int hc = 0; hc < 32; hc += 16) {
+            const int cc = c + hc;
+            uint32_t r16[16];
+            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + cc, r16);
+            uint4* xc0 = staging_chunk(so, cw, row, cc);
+            uint4* xc1 = staging_chunk(so, cw, row, cc + 8);
+            const uint4 xa = *xc0, xb = *xc1;
+            const uint32_t xin[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const uint4* thr4 = reinterpret_cast<const uint4*>(aux->e_thr2 + (cc >> 1));
+            const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (cc >> 1));
+            const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + cc);
+            ptx::tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i4 = 0; i4 < 2; ++i4) {
+              const uint4 th4 = thr4[i4], sg4 = sgn4[i4];
+              const uint32_t thv[4] = {th4.x, th4.y, th4.z, th4.w}, sgv[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
+              float esv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+              if (scaled) {
+                const float4 e0 = es4[2 * i4], e1 = es4[2 * i4 + 1];
+                esv[0] = e0.x; esv[1] = e0.y; esv[2] = e0.z; esv[3] = e0.w;
+                esv[4] = e1.x; esv[5] = e1.y; esv[6] = e1.z; esv[7] = e1.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int pi = 4 * i4 + j;   // column pair (cc + 2*pi, cc + 2*pi + 1)
+                bool m0, m1;
+                gt_bf16x2(xin[pi] ^ sgv[j], thv[j], m0, m1);
+                const float a0 = __uint_as_float(r16[2 * pi]) * esv[2 * j], a1 = __uint_as_float(r16[2 * pi + 1]) * esv[2 * j + 1];
+                pk[pi] = pack_bf16x2(m0 ? a0 : 0.f, m1 ? a1 : 0.f);
+              }
+            }
+            *xc0 = row_valid ? make_uint4(pk[0], pk[1], pk[2], pk[3]) : make_uint4(0u, 0u, 0u, 0u);
+            *xc1 = row_valid ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + c, r);
         ptx::tmem_ld_wait();
         if (xmerge) {
           // out[x] = Z_0[x-1] + Z_1[x] + Z_2[x+1] (pad 1): partial sums of the neighbouring input columns sit in the
-          // neighbouring lanes (16-lane segments = tile rows; the segment ends are halo columns, not stored)
-          uint32_t r1[32], r2v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + p.bn + c, r1);
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + 2 * p.bn + c, r2v);
-          ptx::tmem_ld_wait();
+          // neighbouring lanes (16-lane segments = tile rows; the segment ends are halo columns, not stored).
+          // Sixteen columns at a time keeps the live registers at 64.
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r[i]), 1);
-            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2v[i]), 1);
-            r[i] = __float_as_uint(left + __uint_as_float(r1[i]) + right);
+          for (int hc = 0; hc < 32; hc += 16) {
+            uint32_t h1[16], h2[16];
+            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + p.bn + c + hc, h1);
+            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + 2 * p.bn + c + hc, h2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r[hc + i]), 1);
+              const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(h2[i]), 1);
+              r[hc + i] = __float_as_uint(left + __uint_as_float(h1[i]) + right);
+            }
           }
         }
         uint32_t packed[16];
@@ -638,57 +689,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *staging_chunk(so, cw, srow, c + 8 * i) =
                   make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           }
-          if (p.do_stats && !p.mma_stats) {
-            float v[32], sq[32];
+          if (narrow && p.do_stats && !p.mma_stats) {
+            // sums, then squares re-derived from the packed values: the two 32-value arrays are never live together
+            float v[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               v[2 * i] = bf16_lo(packed[i]);
               v[2 * i + 1] = bf16_hi(packed[i]);
             }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
             const float cs = warp_column_sums(v, lane);
-            const float cq = warp_column_sums(sq, lane);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float lo = bf16_lo(packed[i]), hi = bf16_hi(packed[i]);
+              v[2 * i] = lo * lo;
+              v[2 * i + 1] = hi * hi;
+            }
+            const float cq = warp_column_sums(v, lane);
             atomicAdd(&aux->s_stat[0][c + lane], cs);
             atomicAdd(&aux->s_stat[1][c + lane], cq);
           }
-        } else {
-          // fused ReLU / BatchNorm backward: dy = acc * [es*x+eh > 0]; staged value = dy (OUT_DY) or es*dy (G modes),
-          // written over the activation chunk this thread just read.  The mask is a packed-bf16 threshold test.
-          uint32_t xin[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 t4 = *staging_chunk(so, cw, row, c + 8 * i);
-            xin[4 * i] = t4.x; xin[4 * i + 1] = t4.y; xin[4 * i + 2] = t4.z; xin[4 * i + 3] = t4.w;
-          }
-          const uint4* thr4 = reinterpret_cast<const uint4*>(aux->e_thr2 + (c >> 1));
-          const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (c >> 1));
-          const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + c);
-          const bool scaled = p.out_mode != OUT_DY;
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const uint4 th4 = thr4[i4], sg4 = sgn4[i4];
-            const uint32_t thv[4] = {th4.x, th4.y, th4.z, th4.w}, sgv[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
-            float esv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-            if (scaled) {
-              const float4 e0 = es4[2 * i4], e1 = es4[2 * i4 + 1];
-              esv[0] = e0.x; esv[1] = e0.y; esv[2] = e0.z; esv[3] = e0.w;
-              esv[4] = e1.x; esv[5] = e1.y; esv[6] = e1.z; esv[7] = e1.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int pi = 4 * i4 + j;   // column pair (c + 2*pi, c + 2*pi + 1)
-              bool m0, m1;
-              gt_bf16x2(xin[pi] ^ sgv[j], thv[j], m0, m1);
-              const float a0 = __uint_as_float(r[2 * pi]) * esv[2 * j], a1 = __uint_as_float(r[2 * pi + 1]) * esv[2 * j + 1];
-              packed[pi] = pack_bf16x2(m0 ? a0 : 0.f, m1 ? a1 : 0.f);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *staging_chunk(so, cw, row, c + 8 * i) =
-                row_valid ? make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3])
-                          : make_uint4(0u, 0u, 0u, 0u);
         }
       }
       if (leader) RXB_TL(2, it, 5);
@@ -703,7 +722,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_arrive(&aux->stg_full[sb]);
       }
     }
-    if (p.do_stats && p.mma_stats) {
+    if (!narrow && p.do_stats && p.mma_stats) {
       // per-channel totals of this CTA from TMEM: lane = channel; Gram diagonal and the sums column
       if (g2 == 0 && grp == 0 && my_tiles > 0) {
         ptx::mbar_wait(&aux->stats_done, 0, 12);
@@ -1291,15 +1310,17 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   }
 
   RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
-#define RXB_LAUNCH_GEMM(BK_, PRO_)                                                                             \
-  do {                                                                                                         \
-    RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                  (int)smem));                                                                 \
-    RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, tmX, p)); \
+#define RXB_LAUNCH_GEMM(BK_, PRO_, EPI_)                                                                        \
+  do {                                                                                                          \
+    RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                  \
+    RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_, EPI_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, \
+                      tmX, p));                                                                                 \
   } while (0)
-  if (bk == 64 && prologue) RXB_LAUNCH_GEMM(64, true);
-  else if (bk == 64) RXB_LAUNCH_GEMM(64, false);
-  else RXB_LAUNCH_GEMM(32, false);
+  const int epi = dgrad ? 2 : (p.bn < kMaxBN ? 1 : 0);
+  if (bk == 64 && prologue) { if (epi == 1) RXB_LAUNCH_GEMM(64, true, 1); else RXB_LAUNCH_GEMM(64, true, 0); }
+  else if (bk == 64) { if (epi == 2) RXB_LAUNCH_GEMM(64, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(64, false, 1); else RXB_LAUNCH_GEMM(64, false, 0); }
+  else { if (epi == 2) RXB_LAUNCH_GEMM(32, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(32, false, 1); else RXB_LAUNCH_GEMM(32, false, 0); }
 #undef RXB_LAUNCH_GEMM
   RXB_LAUNCH_OK();
   if (dbg_tl) {   // development: print the timeline of CTA (0,0), cycles relative to its first event
