@@ -275,12 +275,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (dgrad) ptx::prefetch_tmap(&tmX);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&aux->full[s], 1);
-      ptx::mbar_init(&aux->xform[s], kXformThreads);
+      ptx::mbar_init(&aux->xform[s], kXformThreads / 32);   // one arrival per transform warp
       ptx::mbar_init(&aux->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
-      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 2);   // one epilogue group per accumulator stage
+      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 64);  // one arrival per warp of the stage's epilogue group
     }
     for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&aux->epi_in_full[a], 1);
@@ -712,7 +712,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (leader) RXB_TL(2, it, 5);
       ptx::tcgen05_fence_before();
-      ptx::mbar_arrive(&aux->tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
       acc_phase ^= 1;
       // hand the staged tile to the store warp (and to the MMA warp for the column statistics)
       ptx::fence_proxy_async_smem();
@@ -771,8 +772,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_wait(&aux->full[stage], phase, 5);
             transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
                                 t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(&aux->xform[stage]);
+            ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&aux->xform[stage]);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -844,7 +846,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::prefetch_tmap(&tmD);
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&aux->full[s], 1);
-      ptx::mbar_init(&aux->xform[s], kXformThreads);
+      ptx::mbar_init(&aux->xform[s], kXformThreads / 32);   // one arrival per transform warp
       ptx::mbar_init(&aux->empty[s], 1);
     }
     ptx::mbar_init(&aux->tmem_full, 1);
@@ -1136,7 +1138,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0);
           }
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&aux->xform[stage]);
+          __syncwarp();
+          if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&aux->xform[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
