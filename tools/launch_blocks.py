@@ -6,7 +6,10 @@ rows = list(csv.DictReader(lines[i:]))
 idx = [n for n, r in enumerate(rows) if 'loader_kernel' in r['Kernel Name']]
 rows = rows[idx[-2]:idx[-1]] if len(idx) >= 2 else rows
 L = [6, 12, 24, 16]
-def name(r): return re.sub(r'\(.*', '', r['Kernel Name']).replace('void ', '').replace('rxb::', '')
+def name(r):
+    n = re.sub(r'\(.*', '', r['Kernel Name']).replace('void ', '').replace('rxb::', '')
+    m = re.match(r'conv_gemm_kernel<(\d+), (\d), (\d)>', n)          # <BK, PROLOGUE, EPI> -> the older two-argument names
+    return 'conv_gemm_kernel<%s, %s>' % (m.group(1), m.group(2)) if m else n
 def us(r): return float(r['Metric Value']) / 1e3
 tab = collections.defaultdict(float)
 # forward: conv<64,1> launches in order
