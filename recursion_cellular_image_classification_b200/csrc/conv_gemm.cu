@@ -877,9 +877,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         int x0, y0, b0;
         tile_origin(p.t, tile, x0, y0, b0);
+        RXB_TL(0, tile - tile_begin, 0);
         if (!p.shift_dout) {
           const int tc = tile - tile_begin, db = tc & 1;
           ptx::mbar_wait(&aux->d_empty[db], ((tc >> 1) & 1) ^ 1, 17);
+          RXB_TL(0, tc, 1);
           ptx::mbar_arrive_expect_tx(&aux->d_full[db], d_tile);
           for (int j = 0; j < d_boxes; ++j)
             ptx::tma_load_4d(smB + (size_t)db * d_tile + (size_t)j * 16384, &tmD, &aux->d_full[db], j * 64, x0, y0, b0);
@@ -921,6 +923,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        RXB_TL(0, tile - tile_begin, 2);
       }
     }
   } else if (warp == 1) {
@@ -956,10 +959,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int tc = tile - tile_begin, db = tc & 1;
+        if (lane == 0) RXB_TL(1, tc, 0);
         if (!p.shift_dout) ptx::mbar_wait(&aux->d_full[db], (tc >> 1) & 1, 18);
+        if (lane == 0) RXB_TL(1, tc, 1);
         for (int cl = 0; cl < stages_per_tile; ++cl) {
           ptx::mbar_wait(p.prologue ? &aux->xform[stage] : &aux->full[stage], phase, 13);
           ptx::tcgen05_fence_after();
+          if (lane == 0 && cl < 4) RXB_TL(1, tc, 2 + cl);
           if (ptx::elect_one()) {
             const uint32_t a_lo = ptx::desc_lo(da0) + (uint32_t)stage * a_stage16;
             const uint32_t b_lo = ptx::desc_lo(db0) + (uint32_t)(p.shift_dout ? stage : db) * b_stage16;
@@ -1011,9 +1017,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;
     const int row = q * 32 + lane;
     if (tile_end > tile_begin) {
+      if (threadIdx.x == 64) RXB_TL(2, 0, 0);
       ptx::mbar_wait(&aux->tmem_full, 0, 14);
       ptx::tcgen05_fence_after();
       const int et = threadIdx.x - 64;
+      if (et == 0) RXB_TL(2, 0, 1);
       if (p.bulk_out) {
         // Every MMA of this CTA has completed, so the pipeline stages are dead: the fp32 result is transposed into
         // them in the order torch's OIHW gradient has in memory and leaves as contiguous L2 reduce-adds issued by
@@ -1067,6 +1075,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         ptx::tma_store_wait_all();
+        if (et == 0) RXB_TL(2, 0, 2);
       } else {
         const int ib = row / p.bkc, ch_in = row - ib * p.bkc;
         for (int cl = 0; cl < n_local; ++cl) {
@@ -1456,8 +1465,39 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   }
   RXB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RXB_PROF(stream, PROF_CONV_WGRAD);
+  static const int dbg_tl = getenv("RXB_DBG_TIMELINE") ? atoi(getenv("RXB_DBG_TIMELINE")) : 0;
+  static unsigned long long* tl_dev = nullptr;
+  p.dbg = nullptr;
+  if (dbg_tl) {
+    if (!tl_dev) cudaMalloc(&tl_dev, 3 * 16 * 8 * 8);
+    cudaMemsetAsync(tl_dev, 0, 3 * 16 * 8 * 8, stream);
+    p.dbg = tl_dev;
+  }
   RXB_CUDA(launch_k(conv_wgrad_kernel, dim3(pix_ctas, chunk_groups), dim3(kGemmThreads), smem, stream, tmA, tmD, p, stages));
   RXB_LAUNCH_OK();
+  if (dbg_tl) {   // development: timeline of CTA (0,0); rows: producer / MMA per pixel tile, epilogue in row it00
+    unsigned long long h[3 * 16 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, tl_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 3 * 16 * 8; ++i) if (h[i] && h[i] < t0) t0 = h[i];
+    static int printed = 0;
+    if (printed++ < dbg_tl) {
+      printf("wgrad timeline cin=%d n=%d taps=%d stages=%d shift=%d a_halo=%d chunks/cta=%d tiles/cta=%d grid=(%d,%d)\n", p.cin,
+             p.n, taps, stages, p.shift_dout, p.a_halo, p.chunks_per_cta, p.pix_tiles_per_cta, pix_ctas, chunk_groups);
+      const char* role[3] = {"prod", "mma ", "epi "};
+      for (int it = 0; it < 14; ++it)
+        for (int r = 0; r < 3; ++r) {
+          if (r == 2 && it > 0) continue;
+          printf("  it%02d %s:", it, role[r]);
+          for (int ev = 0; ev < 8; ++ev) {
+            const unsigned long long v = h[(r * 16 + it) * 8 + ev];
+            if (v) printf(" %7llu", v - t0); else printf("       -");
+          }
+          printf("\n");
+        }
+    }
+  }
   return RXB_OK;
 }
 

@@ -99,6 +99,7 @@ struct WgradParams {
   int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch)
   int a_halo;           // 1: multi-tap, bkc*taps_x == 128, no prologue: ONE full-halo A box per pixel tile; chunk = filter
                         //    row ty whose taps_x taps are M atoms one pixel row apart (the stem's 4x4 taps)
+  unsigned long long* dbg;  // development timeline of CTA (0,0) (RXB_DBG_TIMELINE), else nullptr
   int bulk_out;         // 1: result staged in shared memory and added to dW by cp.reduce.async.bulk (else fp32 atomics)
   int bulk_bufs;        // staging buffers for the 1x1 bulk path (1 or 2)
 };

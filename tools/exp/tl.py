@@ -13,3 +13,5 @@ if which == "f1": bc.run(B, 128, 128, 224, 256, 128, 1, 1, 1)
 if which == "f1p": bc.run(B, 128, 128, 128, 256, 128, 1, 0, 0)
 if which == "f3": bc.run(B, 128, 128, 128, 128, 32, 3, 1, 1)
 if which == "d3": bc.run_dgrad(B, 128, 128, 32, 128, 128, 3, 0)
+if which == "w1": bc.run_wgrad(128, 32, 32, 768, 1024, 128, 1, 1)
+if which == "w1b": bc.run_wgrad(128, 128, 128, 224, 256, 128, 1, 1)
