@@ -597,7 +597,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       }
       if (leader) RXB_TL(2, it, 2);
-      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
+      if (dgrad) {
+        // three buffers are shared by two epilogue groups, so this group may not have waited on the buffer's previous
+        // use: a parity wait only tells adjacent phases apart, hence wait for phase use-1 before phase use
+        if (use > 0) ptx::mbar_wait(&aux->epi_in_full[sb], (use - 1) & 1, 19);
+        ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
+      }
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
