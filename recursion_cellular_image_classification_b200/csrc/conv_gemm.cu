@@ -590,19 +590,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (leader) RXB_TL(2, it, 0);
       // the staging buffer is free once the TMA store issued n_stg tiles ago has read it and (statistics on the
       // tensor pipe) the MMAs over it have completed; dgrad stages in place over the activation tile it owns
-      if (!dgrad && use > 0) {
-        // with ONE staging buffer the two epilogue groups share it, so a group can be two phases behind the barrier:
-        // a parity wait only distinguishes adjacent phases, hence wait for phase use-2 before phase use-1
-        if (p.n_stg == 1 && use > 1) ptx::mbar_wait(&aux->stg_free[sb], use & 1, 11);
-        ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
-      }
+      // (stores always have TWO staging buffers, one per epilogue group, so a group waits on every phase of its buffer)
+      if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       if (leader) RXB_TL(2, it, 2);
-      if (dgrad) {
-        // three buffers are shared by two epilogue groups, so this group may not have waited on the buffer's previous
-        // use: a parity wait only tells adjacent phases apart, hence wait for phase use-1 before phase use
-        if (use > 0) ptx::mbar_wait(&aux->epi_in_full[sb], (use - 1) & 1, 19);
-        ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
-      }
+      // (Three buffers are shared by the two epilogue groups, so a group waits on every SECOND phase of a buffer.  A
+      // parity wait tells only adjacent phases apart; it is exact here because the barrier cannot lag: the load of this
+      // tile is issued only after the tile three back released the buffer, and that tile's load was issued before every
+      // load and MMA this group has already consumed.)
+      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
@@ -1287,9 +1282,9 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (gx <= 0) return RXB_OK;
   p.b_resident = 0;
   p.n_stg = 1;
-  long long per_stage = a_stage + b_stage, avail = budget - fixed - stage_tile;
+  // stores: two staging buffers (one per epilogue group); dgrad: two activation/staging buffers, a third if it fits
+  long long per_stage = a_stage + b_stage, avail = budget - fixed - stage_tile - (dgrad ? 0 : stage_tile);
   static const int dbg_no_resident = getenv("RXB_DBG_NO_RESIDENT") ? atoi(getenv("RXB_DBG_NO_RESIDENT")) : 0;
-  static const int dbg_one_stg = getenv("RXB_DBG_ONE_STG") ? atoi(getenv("RXB_DBG_ONE_STG")) : 0;
   const bool allow_res = !(dbg_no_resident == 1 || (dbg_no_resident == 2 && p.bn < 128));
   if ((allow_res || p.halo >= 2) && b_panel <= 96 * 1024 && (m_tiles > gx || p.halo >= 2) &&
       (avail - b_panel) / a_stage >= (p.halo >= 2 ? 2 : 3)) {
@@ -1297,7 +1292,6 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     per_stage = a_stage;
     avail -= b_panel;
   }
-  static const int dbg_min_stages2 = getenv("RXB_DBG_MIN_STAGES2") ? atoi(getenv("RXB_DBG_MIN_STAGES2")) : 4;
   if (dgrad) {
     // the load of an activation tile is on the epilogue's dependency chain (buffer freed -> TMA load -> epilogue),
     // so a third buffer hides one load latency
@@ -1305,9 +1299,10 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     p.n_stg = 2;
     for (int extra = 1; extra <= dbg_nx - 2; ++extra)
       if ((avail - stage_tile) / per_stage >= 3) { p.n_stg += 1; avail -= stage_tile; }
-  } else if (!dbg_one_stg && (avail - stage_tile) / per_stage >= dbg_min_stages2) {
+  } else {
+    // one staging buffer per epilogue group (the groups alternate tiles; a shared buffer would make their parity
+    // waits ambiguous)
     p.n_stg = 2;
-    avail -= stage_tile;
   }
   long long stages = avail / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -239,6 +239,9 @@ int final_bn_relu_gap(const __nv_bfloat16* X, int ldx, int B, int HW, int C, con
 }
 
 // ------------------------------------------------------------------------------------------------ BN/ReLU bwd -> G
+// A thread keeps one channel group; per element: mask*da selected once, two accumulators (sum dy, sum dy*x) and one
+// multiply for G.  The scale factors (0.25 or 1/HW, rstd, mean) are applied to the per-thread sums at the end:
+//   sum dy*xhat = rstd * (sum dy*x - mean * sum dy).
 template <int MODE>
 __global__ void __launch_bounds__(kEwThreads)
 bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* __restrict__ X, int ldx, int B,
@@ -250,14 +253,12 @@ bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* 
   const int cg = threadIdx.x % groups;
   const int ppi = blockDim.x / groups;  // pixels per block iteration
   const long long total = (long long)B * H * W;
-  float sc[8], sf[8], mu[8], rs[8], as[8], aq[8];
+  const float k = MODE == 0 ? 0.25f : 1.f / (float)(H * W);   // avgpool 2x2 / global average pool backward
+  float sc[8], sf[8], gk[8], as[8], aq[8];
   load8f(f.scale + cg * 8, sc);
   load8f(f.shift + cg * 8, sf);
-  load8f(f.mean + cg * 8, mu);
-  load8f(f.rstd + cg * 8, rs);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) as[e] = aq[e] = 0.f;
-  const float inv_hw = 1.f / (float)(H * W);
+  for (int e = 0; e < 8; ++e) { as[e] = aq[e] = 0.f; gk[e] = sc[e] * k; }
   for (long long pix = (long long)blockIdx.x * ppi + threadIdx.x / groups; pix < total;
        pix += (long long)gridDim.x * ppi) {
     const int x_ = (int)(pix % W);
@@ -269,23 +270,29 @@ bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* 
       const __nv_bfloat16* dP = static_cast<const __nv_bfloat16*>(upstream);
       const long long pp = ((long long)b * (H >> 1) + (y_ >> 1)) * (W >> 1) + (x_ >> 1);
       unpack8(__ldg(reinterpret_cast<const uint4*>(dP + pp * C + cg * 8)), da);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) da[e] *= 0.25f;
     } else {
       load8f(static_cast<const float*>(upstream) + (long long)b * C + cg * 8, da);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) da[e] *= inv_hw;
     }
     float x[8], g[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(X + pix * ldx + cg * 8)), x);
+    unpack8(ld_stream_v4(X + pix * ldx + cg * 8), x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? da[e] : 0.f;
+      const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? da[e] : 0.f;   // unscaled: k is applied at the end / in gk
       as[e] += dy;
-      aq[e] += dy * ((x[e] - mu[e]) * rs[e]);
-      g[e] = sc[e] * dy;
+      aq[e] = fmaf(dy, x[e], aq[e]);
+      g[e] = gk[e] * dy;
     }
-    *reinterpret_cast<uint4*>(G + pix * ldx + cg * 8) = pack8(g);
+    st_stream_v4(G + pix * ldx + cg * 8, pack8(g));
+  }
+  {
+    float mu[8], rs[8];
+    load8f(f.mean + cg * 8, mu);
+    load8f(f.rstd + cg * 8, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      aq[e] = k * rs[e] * (aq[e] - mu[e] * as[e]);
+      as[e] *= k;
+    }
   }
   block_channel_reduce(as, aq, cg, C, dsum, dsq, sh);
 }
@@ -543,11 +550,13 @@ stem_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dPool, const uint8_t* __r
           const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? g[e] : 0.f;
           g[e] = dy;
           as[e] += dy;
-          aq[e] += dy * ((x[e] - mu[e]) * rs[e]);
+          aq[e] = fmaf(dy, x[e], aq[e]);     // sum dy*x; turned into sum dy*xhat once, below
         }
         st_stream_v4(dy0 + (((long long)b * Hs + 2 * q + py) * Ws + 2 * r + px) * 64 + cg * 8, pack8(g));
       }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) aq[e] = rs[e] * (aq[e] - mu[e] * as[e]);
   block_channel_reduce(as, aq, cg, 64, dsum, dsq, sh);
 }
 
