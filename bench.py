@@ -260,7 +260,8 @@ def run_ours(args):
 
     B = args.batch
     gB = B * world
-    lr = 0.0005 * gB                                   # main.py:71
+    fake_world = int(os.environ.get("RXB_BENCH_FAKE_WORLD", "1"))   # development: N-rank hyper-parameters on one GPU
+    lr = 0.0005 * gB * fake_world                      # main.py:71
     n_exp = 4
     torch.manual_seed(1234 + rank)
     src = synth_planes_torch(rank, B, dev)             # u8 [B,6,512,512] resident in HBM
@@ -322,10 +323,13 @@ def run_ours(args):
             pf["i"] += 1
         works = []
         for ph in range(n_phases):
-            net.train_step(xs, labels, global_batch=gB, phase=ph, loss_out=loss_dev)
+            net.train_step(xs, labels, global_batch=gB * fake_world, phase=ph, loss_out=loss_dev)
             if world > 1:
                 b, e = ranges[ph]
-                works.append(dist.all_reduce(net.flat.grad[b:e], async_op=True))   # overlaps the next phase
+                if os.environ.get("RXB_BENCH_SYNC_AR") == "1":                       # development: no overlap
+                    dist.all_reduce(net.flat.grad[b:e])
+                else:
+                    works.append(dist.all_reduce(net.flat.grad[b:e], async_op=True))   # overlaps the next phase
         for w in works:
             w.wait()
         net.sgd_step(B, IMG, IMG, lr=lr, momentum=0.9, weight_decay=3e-5, nesterov=True)

@@ -59,6 +59,7 @@ inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStre
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream drains;
 // pdl_sync() is the point after which they may touch global memory (the predecessor has completed and flushed).
 // EVERY kernel launched through launch_k must call pdl_sync() before its first global read or write.
+extern bool g_dbg_sync;
 extern bool g_pdl;   // RXB_PDL=1 enables the attribute (default off: kernels serialise as usual and pdl_sync() is a no-op)
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -78,7 +79,11 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+  // RXB_DBG_SYNC=1 (development): wait for THIS kernel on its stream so a device fault is reported at the launch that
+  // caused it (other streams, e.g. NCCL's, keep running concurrently)
+  if (e == cudaSuccess && g_dbg_sync) e = cudaStreamSynchronize(st);
+  return e;
 }
 int num_sms();
 

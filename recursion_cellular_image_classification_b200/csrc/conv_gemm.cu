@@ -1295,10 +1295,17 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (dgrad) {
     // the load of an activation tile is on the epilogue's dependency chain (buffer freed -> TMA load -> epilogue),
     // so a third buffer hides one load latency
-    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 3;
+    // An EVEN number of buffers, so that a buffer always belongs to the same epilogue group (the groups take alternate
+    // tiles): with three buffers shared by both groups the kernel faulted intermittently in 4-GPU runs (never at N<=2);
+    // two or four buffers ran clean.  RXB_DBG_NX=3 restores the odd count for investigation.
+    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 4;
     p.n_stg = 2;
-    for (int extra = 1; extra <= dbg_nx - 2; ++extra)
-      if ((avail - stage_tile) / per_stage >= 3) { p.n_stg += 1; avail -= stage_tile; }
+    if (dbg_nx == 3) {
+      if ((avail - stage_tile) / per_stage >= 3) { p.n_stg = 3; avail -= stage_tile; }
+    } else if (dbg_nx >= 4 && (avail - 2 * stage_tile) / per_stage >= 3) {
+      p.n_stg = 4;
+      avail -= 2 * stage_tile;
+    }
   } else {
     // one staging buffer per epilogue group (the groups alternate tiles; a shared buffer would make their parity
     // waits ambiguous)

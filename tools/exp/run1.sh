@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; tail -3 gpurun_out/t_all.log
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench22.json 2> gpurun_out/bench22.err; cut -c1-200 gpurun_out/bench22.json; tail -3 gpurun_out/bench22.err
+for i in 1 2 3; do
+  RXB_BENCH_FAKE_WORLD=4 RXB_DBG_SYNC=1 timeout 200 python bench.py --quick --steps 60 --warmup 3 > gpurun_out/fake4_$i.json 2> gpurun_out/fake4_$i.err
+  echo "run $i rc=$?"; grep -m2 "librxb error\|rxb:" gpurun_out/fake4_$i.err | grep -v raise | cut -c1-260; tail -1 gpurun_out/fake4_$i.json | cut -c1-200
+done
