@@ -173,7 +173,7 @@ def cpu_baseline(seconds_budget=25.0):
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of each representative conv kernel at batch
 # 128, from the committed `ncu --set full` capture profiles/r01_conv_kernels_b128_ncu_raw.csv (tools/bench_conv.py prof).
-NCU_TRAFFIC_B128 = {"fwd_3x3": 658048928, "fwd_1x1": 1579492136, "dgrad_3x3_bn": 1167182728, "dgrad_1x1_bn_accum": 3518633296, "wgrad_3x3": 688328408, "wgrad_1x1": 1615582872}
+NCU_TRAFFIC_B128 = {"fwd_3x3": 657641176, "fwd_1x1": 1577551888, "dgrad_3x3_bn": 1171553048, "dgrad_1x1_bn_accum": 3577494384, "wgrad_3x3": 686420504, "wgrad_1x1": 1615986728}
 
 
 def conv_kernel_rooflines(B, dev, peaks):
