@@ -59,7 +59,9 @@ struct __align__(16) GemmAux {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t epi_in_full[4];
+  uint64_t epi_in_full[4][2];   // [buffer][epilogue group that will consume the tile]: each barrier has ONE waiting
+                                // group that observes every one of its phases (a parity wait tells only adjacent
+                                // phases apart, so two groups must not alternate on one barrier)
   uint64_t epi_in_empty[4];
   uint64_t stg_full[4];    // staged output tile complete in shared memory (epilogue -> MMA warp, store warp)
   uint64_t stg_free[4];    // store warp has read the staged tile and the statistics MMAs over it are complete
@@ -283,7 +285,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 64);  // one arrival per warp of the stage's epilogue group
     }
     for (int a = 0; a < 4; ++a) {
-      ptx::mbar_init(&aux->epi_in_full[a], 1);
+      ptx::mbar_init(&aux->epi_in_full[a][0], 1);
+      ptx::mbar_init(&aux->epi_in_full[a][1], 1);
       ptx::mbar_init(&aux->epi_in_empty[a], p.mma_stats ? 2 : 1);   // dgrad: store warp has read it + stats MMAs done
       ptx::mbar_init(&aux->stg_full[a], 1);
       ptx::mbar_init(&aux->stg_free[a], p.mma_stats ? 2 : 1);   // store warp has read it (+ statistics MMAs done)
@@ -393,9 +396,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int xb = it % p.n_stg;
           ptx::mbar_wait(&aux->epi_in_empty[xb], ((it / p.n_stg) & 1) ^ 1, 6);
           RXB_TL(0, it, 1);
-          ptx::mbar_arrive_expect_tx(&aux->epi_in_full[xb], stage_tile);
+          ptx::mbar_arrive_expect_tx(&aux->epi_in_full[xb][it & 1], stage_tile);
           for (int bx = 0; bx < n_boxes; ++bx)
-            ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, &aux->epi_in_full[xb],
+            ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, &aux->epi_in_full[xb][it & 1],
                              n0 + bx * cw, x0, y0, b0);
         }
         for (int g = 0; g < groups; ++g) {
@@ -593,11 +596,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // (stores always have TWO staging buffers, one per epilogue group, so a group waits on every phase of its buffer)
       if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       if (leader) RXB_TL(2, it, 2);
-      // (Three buffers are shared by the two epilogue groups, so a group waits on every SECOND phase of a buffer.  A
-      // parity wait tells only adjacent phases apart; it is exact here because the barrier cannot lag: the load of this
-      // tile is issued only after the tile three back released the buffer, and that tile's load was issued before every
-      // load and MMA this group has already consumed.)
-      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb], use & 1, 7);
+      // this group's own barrier of the buffer, used (it / period) times before; period = lcm(n_stg, 2) tiles
+      if (dgrad) {
+        const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
+        ptx::mbar_wait(&aux->epi_in_full[sb][g2], (it / period) & 1, 7);
+      }
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
@@ -1298,7 +1301,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     // An EVEN number of buffers, so that a buffer always belongs to the same epilogue group (the groups take alternate
     // tiles): with three buffers shared by both groups the kernel faulted intermittently in 4-GPU runs (never at N<=2);
     // two or four buffers ran clean.  RXB_DBG_NX=3 restores the odd count for investigation.
-    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 4;
+    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 4;   // 3: odd count, per-group barriers
     p.n_stg = 2;
     if (dbg_nx == 3) {
       if ((avail - stage_tile) / per_stage >= 3) { p.n_stg = 3; avail -= stage_tile; }
