@@ -36,6 +36,19 @@ STATS_BYTES_PER_IMG = 6 * IMG * IMG            # 1,572,864
 LOADER_BYTES_PER_IMG = 3 * 6 * IMG * IMG       # 1 B read + 2 B bf16 written per element = 4,718,592
 
 
+OUT = sys.stdout
+
+
+def claim_stdout():
+    """Keep stdout for the JSON line alone: fd 1 is re-pointed at stderr so that C-level prints (NCCL's version
+    banner at N>1, library warnings) cannot land in front of it; the line goes to the saved descriptor."""
+    global OUT
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    OUT = os.fdopen(saved, "w")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -138,7 +151,7 @@ def run_reference(args):
                        "batch": B},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -379,7 +392,7 @@ def run_ours(args):
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "warmup": n_warm, "ms_per_step": ms / args.steps, "quick": True,
                               "host_enqueue_ms": host_enqueue_ms,
-                              "gpu_launches": int(launches)}), flush=True)
+                              "gpu_launches": int(launches)}), file=OUT, flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -476,7 +489,7 @@ def run_ours(args):
                 "hbm_kernels": hbm_kernels, "kernel_breakdown": breakdown,
                 "cpu_baseline": cpu,
                 "loss": {"after_warmup": loss_first, "last": loss_last}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -494,6 +507,7 @@ def main():
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): exactly --warmup + --steps steps, no e2e / breakdown / cpu baseline")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
