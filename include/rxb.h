@@ -89,6 +89,21 @@ int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W, const int
                       const float* norm_m, const float* norm_d, int n_exp, void* dst, int B, int Ho,
                       int Wo, int out_format, rxb_stream_t stream);
 
+/* Arbitrary-angle variant of the loader: the reference's full train transform
+ * VerticalFlip -> HorizontalFlip -> ShiftScaleRotate(rotate_limit=180) -> RandomCrop -> Normalize
+ * (dataloader.py:42-48, 128-139).  ShiftScaleRotate is cv2.warpAffine(img, M, (W,H), INTER_LINEAR,
+ * BORDER_REFLECT_101) on u8; the kernel restates OpenCV's fixed-point arithmetic (1/32-pixel
+ * coordinates, 10-bit weights, round-half-up) so the u8 gather is bit-identical to OpenCV's.
+ *   flip_code u8[B]     bit0 vflip, bit1 hflip (applied to the source before the warp)
+ *   M         f64[B,2,3] FORWARD matrices, exactly what cv2.warpAffine receives (host-side
+ *                        cv2.getRotationMatrix2D((W/2,H/2), angle, 1.0)); inverted on the device the
+ *                        way cv::warpAffine does
+ *   the other arguments are rxb_load_norm_aug's; H and W need not be equal or multiples of 16. */
+int rxb_load_norm_affine(const uint8_t* src, int64_t n_src, int H, int W, const int32_t* src_idx,
+                         const int32_t* exp_id, const uint8_t* flip_code, const double* M,
+                         const int32_t* crop_yx, const float* norm_m, const float* norm_d, int n_exp,
+                         void* dst, int B, int Ho, int Wo, int out_format, rxb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Family 4 — test-time averaging, plate-group masking, rescale and greedy assignment.
  * Replaces test.py:27 (softmax), :42-46 (mask + rescale) and :48-56 (greedy loop).

@@ -8,6 +8,9 @@ Parity status
   * compute_mean_std_arrays, mask_rescale, greedy_assign: PINNED — checked against outputs of the
     reference's own functions (compute_stats_experiments.compute_mean_std, cell_classifier.test.test)
     run in the build container; fixtures under tests/golden/ (tests/golden/make_golden.py).
+  * warp_affine_u8 (ShiftScaleRotate at any angle): restates cv2.warpAffine's fixed-point bilinear remap; PINNED
+    against cv2.warpAffine itself (OpenCV 4.13, the library call albumentations makes) executed in the tests and
+    against tests/golden/warp_golden.npz; rotation_matrix is pinned bitwise against cv2.getRotationMatrix2D.
   * d4_augment / normalize: restate albumentations==0.3.0 (requirement.txt:1), which is NOT installed
     and has no tests in the reference -> "parity unpinned" for that third-party boundary; the OpenCV
     calls it makes (cv2.flip, cv2.warpAffine) are executed for real here.
@@ -63,6 +66,98 @@ def d4_augment(img_hwc, vflip=False, hflip=False, k=0, ref_compat=False):
     else:
         img = np.rot90(img, k)
     return np.ascontiguousarray(img)
+
+
+def rotation_matrix(w, h, angle, scale=1.0):
+    """cv2.getRotationMatrix2D((w/2, h/2), angle, scale) as albumentations 0.3.0 ShiftScaleRotate calls it
+    (dataloader.py:45-46): float64 [2,3].  OpenCV scales the angle by the folded constant pi/180."""
+    import math
+    cx, cy = w / 2, h / 2
+    a = angle * (math.pi / 180.0)
+    al, be = math.cos(a) * scale, math.sin(a) * scale
+    return np.array([[al, be, (1 - al) * cx - be * cy], [-be, al, be * cx + (1 - al) * cy]], dtype=np.float64)
+
+
+def invert_affine(M):
+    """The inversion cv::warpAffine applies to a forward matrix, in its operation order."""
+    M = np.array(M, dtype=np.float64).reshape(6).copy()
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    M[0] = A11
+    M[1] *= -D
+    M[3] *= -D
+    M[4] = A22
+    b1 = -M[0] * M[2] - M[1] * M[5]
+    b2 = -M[3] * M[2] - M[4] * M[5]
+    M[2], M[5] = b1, b2
+    return M
+
+
+def reflect101(p, n):
+    """cv::borderInterpolate(p, n, BORDER_REFLECT_101) on an integer array."""
+    p = np.array(p, dtype=np.int64)
+    if n == 1:
+        return np.zeros_like(p)
+    while True:
+        out = (p < 0) | (p >= n)
+        if not out.any():
+            return p
+        p = np.where(p < 0, -p, p)
+        p = np.where(p >= n, 2 * n - 2 - p, p)
+
+
+def warp_affine_u8(img, M):
+    """cv2.warpAffine(img, M, (w, h), flags=INTER_LINEAR, borderMode=BORDER_REFLECT_101) for uint8 HW or HWC,
+    restated from OpenCV's fixed-point path: destination (x, y) maps to the source at 1/1024-pixel resolution
+    (AB_BITS = 10), is rounded to 1/32 pixel (INTER_BITS = 5, round_delta = 16), and the four reflected taps are
+    blended with the 15-bit integer table, which for bilinear weights is exactly 32*(32-fx|fx)*(32-fy|fy), so
+    out = (sum w*p + 512) >> 10."""
+    H, W = img.shape[:2]
+    Mi = invert_affine(M)
+    x = np.arange(W, dtype=np.float64)
+    y = np.arange(H, dtype=np.float64)
+    adelta = np.rint(Mi[0] * x * 1024).astype(np.int64)
+    bdelta = np.rint(Mi[3] * x * 1024).astype(np.int64)
+    X0 = np.rint((Mi[1] * y + Mi[2]) * 1024).astype(np.int64) + 16
+    Y0 = np.rint((Mi[4] * y + Mi[5]) * 1024).astype(np.int64) + 16
+    X = (X0[:, None] + adelta[None, :]) >> 5
+    Y = (Y0[:, None] + bdelta[None, :]) >> 5
+    sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+    fx, fy = X & 31, Y & 31
+    xa, xb = reflect101(sx, W), reflect101(sx + 1, W)
+    ya, yb = reflect101(sy, H), reflect101(sy + 1, H)
+    im = img.astype(np.int64).reshape(H, W, -1)
+    acc = (((32 - fx) * (32 - fy))[..., None] * im[ya, xa] + (fx * (32 - fy))[..., None] * im[ya, xb] +
+           ((32 - fx) * fy)[..., None] * im[yb, xa] + (fx * fy)[..., None] * im[yb, xb])
+    return ((acc + 512) >> 10).astype(np.uint8).reshape(img.shape)
+
+
+def shift_scale_rotate(img_hwc, angle, use_cv2=False):
+    """albumentations 0.3.0 ShiftScaleRotate(shift_limit=0, scale_limit=0) at a given angle (dataloader.py:45-46)."""
+    h, w = img_hwc.shape[:2]
+    M = rotation_matrix(w, h, angle)
+    if use_cv2:
+        import cv2
+        return cv2.warpAffine(np.ascontiguousarray(img_hwc), M, (w, h), flags=cv2.INTER_LINEAR,
+                              borderMode=cv2.BORDER_REFLECT_101)
+    return warp_affine_u8(img_hwc, M)
+
+
+def transform_affine(img_chw_u8, mean, std, vflip=False, hflip=False, angle=0.0, crop_yx=(0, 0), out_hw=None,
+                     use_cv2=False):
+    """The reference's full train transform (dataloader.py:42-48, 128-139) with explicit parameters: flips ->
+    ShiftScaleRotate(angle) -> crop -> Normalize.  Returns float32 CHW."""
+    img = np.moveaxis(img_chw_u8, 0, 2)
+    if vflip:
+        img = img[::-1]
+    if hflip:
+        img = img[:, ::-1]
+    img = shift_scale_rotate(np.ascontiguousarray(img), angle, use_cv2)
+    if out_hw is not None:
+        img = crop(img, crop_yx[0], crop_yx[1], out_hw[0], out_hw[1])
+    img = normalize(img, mean, std)
+    return np.ascontiguousarray(np.moveaxis(img, 2, 0))
 
 
 def crop(img_hwc, y0, x0, h, w):

@@ -46,6 +46,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p]),
     "rxb_load_norm_aug": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rxb_load_norm_affine": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rxb_tta_softmax_avg_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rxb_mask_rescale": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "rxb_greedy_assign_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -8,6 +8,8 @@ crop / normalize (:128-139) run in the fused GPU loader (rxb_load_norm_aug), wit
 explicitly (albumentations' RNG stream is not reproducible):
   vflip, hflip ~ Bernoulli(.5) (:43-44); rotation k*90 degrees, k ~ U{0..3} — the D4 subset of
   ShiftScaleRotate(rotate_limit=180) (:45-46); crop offsets ~ U{0..H-crop} (RandomCrop, :47) or centred (:50).
+  `augment='rotate'` restores the reference's full train transform: angle ~ U(-180, 180) about (w/2, h/2), bilinear,
+  BORDER_REFLECT_101, through rxb_load_norm_affine (u8 result bit-identical to cv2.warpAffine).
 
 Two ways to consume it:
   * `ds[i]` — reference-compatible: a float32 tensor [3,6,h,w] (train/val) or [6,6,H,W] (test) and the label /
@@ -27,7 +29,10 @@ from .. import ops
 
 class ImagesDS(torch.utils.data.Dataset):
     def __init__(self, df, df_controls, stats_experiments, img_dir, mode, verbose=True,
-                 channels=[1, 2, 3, 4, 5, 6], crop=364, device="cuda"):
+                 channels=[1, 2, 3, 4, 5, 6], crop=364, device="cuda", augment="d4"):
+        if augment not in ("d4", "rotate"):
+            raise ValueError("augment must be 'd4' or 'rotate'")
+        self.augment = augment
         self.records = deepcopy(df).to_records(index=False)
         df_conts = deepcopy(df_controls)
         mask = (df_conts['well_type'] == 'negative_control') & (df_conts['well'] == 'B02')
@@ -77,14 +82,19 @@ class ImagesDS(torch.utils.data.Dataset):
 
     # ------------------------------------------------------------ augmentation draw (explicit parameters)
     def _draw(self, S):
+        """(aug code, crop offset, output size, forward warp matrix or None) for one image."""
         if self.mode == 'train':
-            code = ops.aug_code(random.random() < 0.5, random.random() < 0.5, random.randint(0, 3))
+            vflip, hflip = random.random() < 0.5, random.random() < 0.5
+            if self.augment == 'rotate':
+                code, M = ops.aug_code(vflip, hflip), ops.rotation_matrix(S, S, random.uniform(-180, 180))
+            else:
+                code, M = ops.aug_code(vflip, hflip, random.randint(0, 3)), None
             c = self.crop
-            return code, (int((S - c) * random.random()), int((S - c) * random.random())), c
+            return code, (int((S - c) * random.random()), int((S - c) * random.random())), c, M
         if self.mode == 'val':
             c = self.crop
-            return 0, ((S - c) // 2, (S - c) // 2), c
-        return 0, (0, 0), S
+            return 0, ((S - c) // 2, (S - c) // 2), c, None
+        return 0, (0, 0), S, None
 
     def raw_item(self, index):
         """Decoded u8 planes and augmentation parameters; no arithmetic on the host."""
@@ -105,8 +115,11 @@ class ImagesDS(torch.utils.data.Dataset):
         draws = [self._draw(S) for _ in picks]                                   # independent per image (:159-173)
         codes = np.array([d[0] for d in draws], dtype=np.uint8)
         crops = np.array([d[1] for d in draws], dtype=np.int32)
-        return {"planes": torch.from_numpy(planes), "codes": torch.from_numpy(codes), "crops": torch.from_numpy(crops),
+        item = {"planes": torch.from_numpy(planes), "codes": torch.from_numpy(codes), "crops": torch.from_numpy(crops),
                 "exp": self.exp_index[exp], "out": draws[0][2], "label": label}
+        if draws[0][3] is not None:
+            item["mats"] = torch.from_numpy(np.stack([d[3] for d in draws]))     # [G,2,3] float64
+        return item
 
     def _norm(self, dev):
         if self._norm_dev is None or self._norm_dev[0].device != dev:
@@ -119,12 +132,18 @@ class ImagesDS(torch.utils.data.Dataset):
         planes = batch["planes"].to(dev, non_blocking=True)                      # [B,G,6,H,W] u8
         B, G = planes.shape[:2]
         codes, crops = batch["codes"].to(dev), batch["crops"].to(dev)
+        mats = batch["mats"].to(dev) if "mats" in batch else None
         if first_only:
             planes, codes, crops, G = planes[:, :1], codes[:, :1], crops[:, :1], 1
+            mats = mats[:, :1] if mats is not None else None
         planes = planes.reshape(B * G, *planes.shape[2:]).contiguous()
         exp = batch["exp"].to(dev).to(torch.int32).repeat_interleave(G)
         norm_m, norm_d = self._norm(dev)
         out = batch["out"]
+        if mats is not None:
+            return ops.load_norm_affine(planes, torch.arange(B * G, dtype=torch.int32, device=dev), exp,
+                                        codes.reshape(-1).contiguous(), mats.reshape(-1, 2, 3).contiguous(),
+                                        crops.reshape(-1, 2).contiguous(), norm_m, norm_d, (out, out), out_format)
         return ops.load_norm_aug(planes, torch.arange(B * G, dtype=torch.int32, device=dev), exp,
                                  codes.reshape(-1).contiguous(), crops.reshape(-1, 2).contiguous(), norm_m, norm_d,
                                  (out, out), out_format)
@@ -142,6 +161,13 @@ class ImagesDS(torch.utils.data.Dataset):
 
 
 def collate_raw(items):
+    out = _collate_common(items)
+    if "mats" in items[0]:
+        out["mats"] = torch.stack([it["mats"] for it in items])
+    return out
+
+
+def _collate_common(items):
     return {"planes": torch.stack([it["planes"] for it in items]),
             "codes": torch.stack([it["codes"] for it in items]),
             "crops": torch.stack([it["crops"] for it in items]),

@@ -161,6 +161,109 @@ loader_kernel(const __grid_constant__ CUtensorMap tmap_src, const LoaderArgs a) 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Arbitrary-angle variant: VerticalFlip -> HorizontalFlip -> ShiftScaleRotate -> crop ->
+// Normalize, i.e. the reference's full train transform (dataloader.py:42-48).  ShiftScaleRotate is
+// cv2.warpAffine(img, M, (W,H), INTER_LINEAR, BORDER_REFLECT_101) on u8; its arithmetic is integer and is
+// restated here operation by operation so the u8 result is bit-identical to OpenCV's:
+//   * the 2x3 matrix is inverted in double exactly like cv::warpAffine (no fused multiply-adds),
+//   * source coordinates are fixed point with 10 fractional bits, rounded to 1/32 pixel:
+//       X = (round((Mi01*y + Mi02)*1024) + 16 + round(Mi00*x*1024)) >> 5,   sx = X >> 5, fx = X & 31,
+//   * the four taps go through BORDER_REFLECT_101, the weights are (32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy
+//     (OpenCV's 15-bit table holds exactly 32x these) and the sum is rounded as (acc + 512) >> 10.
+// The gather reads the source through the read-only path (an image's six planes are 1.5 MB: L2-resident);
+// a rotated footprint is not a TMA box.  Output formats and stores are the D4 loader's.
+struct AffineArgs {
+  LoaderArgs l;       // aug_code carries the flips only (bit0 vflip, bit1 hflip)
+  const double* M;    // [B][2][3] forward matrices as passed to cv2.warpAffine
+  int H, W;
+};
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while ((unsigned)p >= (unsigned)n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+
+__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
+
+constexpr int kAfTileW = 64, kAfTileH = 16, kAfThreads = 256;
+
+__global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineArgs a) {
+  __shared__ double s_mi[6];
+  __shared__ float s_m[kLdPlanes], s_d[kLdPlanes];
+  const int b = blockIdx.y;
+  const int tiles_x = a.l.tiles_x;
+  const int tx0 = (blockIdx.x % tiles_x) * kAfTileW;
+  const int ty0 = (blockIdx.x / tiles_x) * kAfTileH;
+
+  if (threadIdx.x == 0) {
+    const double* M = a.M + 6 * (long long)b;
+    double D = __dsub_rn(__dmul_rn(M[0], M[4]), __dmul_rn(M[1], M[3]));
+    D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
+    const double m0 = __dmul_rn(M[4], D), m4 = __dmul_rn(M[0], D);
+    const double m1 = __dmul_rn(M[1], -D), m3 = __dmul_rn(M[3], -D);
+    s_mi[0] = m0; s_mi[1] = m1; s_mi[3] = m3; s_mi[4] = m4;
+    s_mi[2] = __dsub_rn(__dmul_rn(-m0, M[2]), __dmul_rn(m1, M[5]));
+    s_mi[5] = __dsub_rn(__dmul_rn(-m3, M[2]), __dmul_rn(m4, M[5]));
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kLdPlanes) {
+    const int c = threadIdx.x - 32;
+    int e = a.l.exp_id[b];
+    e = e < 0 ? 0 : (e >= a.l.n_exp ? a.l.n_exp - 1 : e);
+    s_m[c] = a.l.norm_m[e * kLdPlanes + c];
+    s_d[c] = a.l.norm_d[e * kLdPlanes + c];
+  }
+  __syncthreads();
+
+  const int code = a.l.aug_code[b];
+  const bool vflip = code & 1, hflip = code & 2;
+  const int y0 = a.l.crop_yx[2 * b], x0 = a.l.crop_yx[2 * b + 1];
+  const int H = a.H, W = a.W;
+  const long long plane = (long long)H * W;
+  const long long img = min(max((long long)a.l.src_idx[b], 0ll), a.l.n_src - 1);
+  const uint8_t* gsrc = a.l.src + img * kLdPlanes * plane;
+
+  const int ox = tx0 + (threadIdx.x & (kAfTileW - 1));
+  if (ox >= a.l.Wo) return;
+  const double xd = (double)(ox + x0);
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[0], xd), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[3], xd), 1024.0));
+  float m[kLdPlanes], d[kLdPlanes];
+#pragma unroll
+  for (int c = 0; c < kLdPlanes; ++c) {
+    m[c] = s_m[c];
+    d[c] = s_d[c];
+  }
+
+  for (int dy = threadIdx.x / kAfTileW; dy < kAfTileH; dy += kAfThreads / kAfTileW) {
+    const int oy = ty0 + dy;
+    if (oy >= a.l.Ho) break;
+    const double yd = (double)(oy + y0);
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[1], yd), s_mi[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[4], yd), s_mi[5]), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
+    const int fx = X & 31, fy = Y & 31;
+    int xa = reflect101(sx, W), xb = reflect101(sx + 1, W);
+    int ya = reflect101(sy, H), yb = reflect101(sy + 1, H);
+    if (hflip) { xa = W - 1 - xa; xb = W - 1 - xb; }
+    if (vflip) { ya = H - 1 - ya; yb = H - 1 - yb; }
+    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
+    const uint8_t* ra = gsrc + (long long)ya * W;
+    const uint8_t* rb = gsrc + (long long)yb * W;
+    float v[kLdPlanes];
+#pragma unroll
+    for (int c = 0; c < kLdPlanes; ++c) {
+      const int acc = w00 * __ldg(ra + c * plane + xa) + w01 * __ldg(ra + c * plane + xb) +
+                      w10 * __ldg(rb + c * plane + xa) + w11 * __ldg(rb + c * plane + xb);
+      v[c] = __fmul_rn(__fsub_rn((float)((acc + 512) >> 10), m[c]), d[c]);
+    }
+    emit_pixel(a.l, b, oy, ox, v);
+  }
+}
+
 }  // namespace rxb
 
 extern "C" int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W, const int32_t* src_idx,
@@ -202,6 +305,42 @@ extern "C" int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W
   dim3 grid(a.tiles_x * a.tiles_y, B);
   RXB_PROF(as_stream(stream), PROF_LOADER);
   loader_kernel<<<grid, kLdThreads, 0, as_stream(stream)>>>(tm, a);
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+extern "C" int rxb_load_norm_affine(const uint8_t* src, int64_t n_src, int H, int W, const int32_t* src_idx,
+                                    const int32_t* exp_id, const uint8_t* flip_code, const double* M,
+                                    const int32_t* crop_yx, const float* norm_m, const float* norm_d, int n_exp,
+                                    void* dst, int B, int Ho, int Wo, int out_format, rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(B >= 0, "rxb_load_norm_affine: negative batch");
+  if (B == 0) return RXB_OK;  // an empty batch has no addresses to check
+  RXB_CHECK_ARG(src && src_idx && exp_id && flip_code && M && crop_yx && norm_m && norm_d && dst,
+                "rxb_load_norm_affine: null pointer");
+  RXB_CHECK_ARG(H > 0 && W > 0 && H <= 32767 && W <= 32767, "rxb_load_norm_affine: bad image size %dx%d", H, W);
+  RXB_CHECK_ARG(Ho > 0 && Wo > 0 && Ho <= H && Wo <= W, "rxb_load_norm_affine: bad crop size");
+  RXB_CHECK_ARG(n_src > 0 && n_exp > 0 && B >= 0, "rxb_load_norm_affine: bad sizes");
+  RXB_CHECK_ARG(out_format >= RXB_OUT_F32_NCHW && out_format <= RXB_OUT_BF16_S2D32,
+                "rxb_load_norm_affine: bad out_format");
+  if (out_format == RXB_OUT_BF16_S2D32)
+    RXB_CHECK_ARG(Ho % 2 == 0 && Wo % 2 == 0, "rxb_load_norm_affine: S2D32 needs even Ho, Wo");
+  RXB_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(M) & 7) == 0,
+                "rxb_load_norm_affine: dst must be 16-byte aligned, M 8-byte aligned");
+  RXB_CHECK_ARG(B <= 65535, "rxb_load_norm_affine: B > 65535");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+
+  AffineArgs a;
+  a.l.src = src; a.l.src_idx = src_idx; a.l.exp_id = exp_id; a.l.aug_code = flip_code; a.l.crop_yx = crop_yx;
+  a.l.norm_m = norm_m; a.l.norm_d = norm_d; a.l.dst = dst;
+  a.l.S = H; a.l.Ho = Ho; a.l.Wo = Wo; a.l.n_exp = n_exp; a.l.fmt = out_format; a.l.n_src = n_src;
+  a.l.tiles_x = ceil_div(Wo, kAfTileW);
+  a.l.tiles_y = ceil_div(Ho, kAfTileH);
+  a.M = M; a.H = H; a.W = W;
+  dim3 grid(a.l.tiles_x * a.l.tiles_y, B);
+  RXB_PROF(as_stream(stream), PROF_LOADER);
+  loader_affine_kernel<<<grid, kAfThreads, 0, as_stream(stream)>>>(a);
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

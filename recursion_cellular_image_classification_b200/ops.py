@@ -94,6 +94,50 @@ def load_norm_aug(src, src_idx, exp_id, aug, crop_yx, norm_m, norm_d, out_hw, ou
     return out
 
 
+def rotation_matrix(w, h, angle, scale=1.0):
+    """The matrix albumentations 0.3.0 ShiftScaleRotate hands to cv2.warpAffine (dataloader.py:45-46):
+    cv2.getRotationMatrix2D((w/2, h/2), angle, scale), float64 [2,3] — host data, restated so the loader does not
+    depend on OpenCV (bitwise equal to OpenCV's on the tested angles: the angle is scaled by the folded pi/180)."""
+    import math
+    cx, cy = w / 2, h / 2
+    a = angle * (math.pi / 180.0)
+    al, be = math.cos(a) * scale, math.sin(a) * scale
+    return np.array([[al, be, (1 - al) * cx - be * cy], [-be, al, be * cx + (1 - al) * cy]], dtype=np.float64)
+
+
+def load_norm_affine(src, src_idx, exp_id, flips, M, crop_yx, norm_m, norm_d, out_hw, out_format, out=None):
+    """The reference's full train transform on the device: flips -> cv2.warpAffine-exact bilinear warp by the forward
+    matrices M (float64 [B,2,3]) -> crop -> normalise.  Other arguments as load_norm_aug; flips u8 [B] uses bit0
+    vflip, bit1 hflip."""
+    require_gpu()
+    src = _cuda(src, torch.uint8)
+    n, C, H, W = src.shape
+    if C != 6:
+        raise _lib.RxbError("loader expects 6 channels")
+    src_idx = _cuda(src_idx, torch.int32)
+    exp_id = _cuda(exp_id, torch.int32)
+    flips = _cuda(flips, torch.uint8)
+    M = _cuda(M, torch.float64)
+    crop_yx = _cuda(crop_yx, torch.int32)
+    norm_m = _cuda(norm_m, torch.float32)
+    norm_d = _cuda(norm_d, torch.float32)
+    B = src_idx.numel()
+    if M.numel() != 6 * B or flips.numel() != B or crop_yx.numel() != 2 * B or exp_id.numel() != B:
+        raise _lib.RxbError("load_norm_affine: per-image arguments must have B=%d rows" % B)
+    Ho, Wo = out_hw
+    if out is None:
+        if out_format == OUT_F32_NCHW:
+            out = torch.empty(B, 6, Ho, Wo, dtype=torch.float32, device=src.device)
+        elif out_format == OUT_BF16_NHWC8:
+            out = torch.empty(B, Ho, Wo, 8, dtype=torch.bfloat16, device=src.device)
+        else:
+            out = torch.empty(B, Ho // 2, Wo // 2, 32, dtype=torch.bfloat16, device=src.device)
+    check(load().rxb_load_norm_affine(ptr(src), n, H, W, ptr(src_idx), ptr(exp_id), ptr(flips), ptr(M), ptr(crop_yx),
+                                      ptr(norm_m), ptr(norm_d), norm_m.shape[0], ptr(out), B, Ho, Wo, out_format,
+                                      stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------ family 4: TTA / assignment
 def tta_softmax_avg_mask(logits, plate=None, group_col=None):
     """logits f32 [V,N,C] -> rescale(mask(mean_v softmax)) f32 [N,C]."""

@@ -10,6 +10,9 @@ Fixtures written next to this file:
   assign_golden.npz  cell_classifier.test.test (reference test.py:9-58) driven by a seeded logits callable:
                      the masked+rescaled assignment for a 64-well case (inputs stored) and a full
                      1108-well experiment (inputs regenerated from the seed).
+  warp_golden.npz    cv2.getRotationMatrix2D + cv2.warpAffine(INTER_LINEAR, BORDER_REFLECT_101) — the call
+                     albumentations 0.3.0 ShiftScaleRotate makes for dataloader.py:45-46 (albumentations itself is
+                     not installed) — on seeded 6-channel u8 images: full outputs at 48x48, SHA-256 digests at 512x512.
 """
 import os
 import sys
@@ -95,6 +98,35 @@ def make_assign():
     print("assign golden:", r64[:8], r1108[:8])
 
 
+WARP_ANGLES = [-180.0, -137.3, -90.0, -45.0, -0.37, 12.5, 90.0, 151.9]
+
+
+def make_warp():
+    import hashlib
+    import cv2
+
+    def warp(img, ang):
+        h, w = img.shape[:2]
+        M = cv2.getRotationMatrix2D((w / 2, h / 2), ang, 1.0)
+        return M, cv2.warpAffine(img, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+
+    small = np.random.default_rng(7).integers(0, 256, size=(48, 48, 6), dtype=np.uint8)
+    big = np.ascontiguousarray(np.moveaxis(synth_planes(5, n=1)[0], 0, 2))      # [512,512,6]
+    mats, outs, digests = [], [], []
+    for ang in WARP_ANGLES:
+        M, o = warp(small, ang)
+        mats.append(M)
+        outs.append(o)
+        digests.append(hashlib.sha256(warp(big, ang)[1].tobytes()).hexdigest())
+    np.savez_compressed(os.path.join(HERE, "warp_golden.npz"), angles=np.array(WARP_ANGLES), seed_small=7,
+                        seed_big=5, mats=np.array(mats), out_small=np.array(outs), sha256_big=np.array(digests),
+                        cv2_version=cv2.__version__)
+    print("warp golden:", cv2.__version__, digests[1][:16])
+
+
 if __name__ == "__main__":
+    make_warp()
+    if "--warp-only" in sys.argv:
+        sys.exit(0)
     make_stats()
     make_assign()

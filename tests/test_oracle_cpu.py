@@ -97,3 +97,62 @@ def test_s2d_layout():
         for xx in range(6):
             np.testing.assert_array_equal(s[y // 2, xx // 2, (y & 1) * 16 + (xx & 1) * 8:(y & 1) * 16 + (xx & 1) * 8 + 8],
                                           x[y, xx])
+
+
+# ---------------------------------------------------------------- arbitrary-angle ShiftScaleRotate
+def test_rotation_matrix_is_opencvs_bitwise():
+    import cv2
+    rng = np.random.default_rng(4)
+    for ang in [0.0, 90.0, -90.0, 180.0, -180.0, 45.0] + list(rng.uniform(-180, 180, size=2000)):
+        for (w, h) in ((512, 512), (96, 64)):
+            np.testing.assert_array_equal(O.rotation_matrix(w, h, float(ang)),
+                                          cv2.getRotationMatrix2D((w / 2, h / 2), float(ang), 1.0))
+
+
+def test_warp_affine_restatement_matches_golden(golden_dir):
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "warp_golden.npz"))
+    small = np.random.default_rng(int(g["seed_small"])).integers(0, 256, size=(48, 48, 6), dtype=np.uint8)
+    big = np.ascontiguousarray(np.moveaxis(synth_planes(int(g["seed_big"]), n=1)[0], 0, 2))
+    for i, ang in enumerate(g["angles"]):
+        np.testing.assert_array_equal(O.rotation_matrix(48, 48, float(ang)), g["mats"][i])
+        np.testing.assert_array_equal(O.warp_affine_u8(small, g["mats"][i]), g["out_small"][i])
+        got = O.shift_scale_rotate(big, float(ang))
+        assert hashlib.sha256(got.tobytes()).hexdigest() == str(g["sha256_big"][i])
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 6), (40, 72, 6), (33, 17, 6), (96, 96), (1, 9, 6)])
+def test_warp_affine_restatement_is_cv2_warpaffine(shape):
+    """Bit-exact against the OpenCV call albumentations makes, for random angles and general affine maps
+    (scale, shear, shift), square / non-square / single-channel / degenerate images."""
+    import cv2
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    h, w = shape[:2]
+    mats = [O.rotation_matrix(w, h, float(a)) for a in rng.uniform(-180, 180, size=40)]
+    for _ in range(20):
+        M = O.rotation_matrix(w, h, float(rng.uniform(-180, 180)), scale=float(rng.uniform(0.6, 1.6)))
+        M[:, 2] += rng.uniform(-7, 7, size=2)
+        M[0, 1] += rng.uniform(-0.2, 0.2)
+        mats.append(M)
+    for M in mats:
+        ref = cv2.warpAffine(img, M, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+        np.testing.assert_array_equal(O.warp_affine_u8(img, M), ref)
+
+
+def test_warp_affine_at_right_angles_is_the_ref_compat_gather():
+    """At multiples of 90 degrees the fixed-point warp degenerates to the integer gather of SURVEY §A.2."""
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, size=(64, 64, 6), dtype=np.uint8)
+    for k in range(4):
+        np.testing.assert_array_equal(O.shift_scale_rotate(img, 90.0 * k), O.d4_augment(img, k=k, ref_compat=True))
+
+
+def test_transform_affine_restatement_vs_cv2_pipeline():
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, size=(6, 128, 128), dtype=np.uint8)
+    mean, std = rng.random(6) * 0.2 + 0.05, rng.random(6) * 0.1 + 0.05
+    for v, h, ang in [(0, 0, 17.0), (1, 0, -133.7), (0, 1, 90.0), (1, 1, 179.2)]:
+        a = O.transform_affine(img, mean, std, bool(v), bool(h), ang, (5, 9), (92, 92))
+        b = O.transform_affine(img, mean, std, bool(v), bool(h), ang, (5, 9), (92, 92), use_cv2=True)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
