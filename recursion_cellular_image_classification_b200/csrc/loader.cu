@@ -15,6 +15,7 @@
 // with BORDER_REFLECT_101, not affine at the border) take a plain global-gather path.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "warp_fixed.cuh"
 
 namespace rxb {
 
@@ -166,12 +167,9 @@ loader_kernel(const __grid_constant__ CUtensorMap tmap_src, const LoaderArgs a) 
 // Arbitrary-angle variant: VerticalFlip -> HorizontalFlip -> ShiftScaleRotate -> crop ->
 // Normalize, i.e. the reference's full train transform (dataloader.py:42-48).  ShiftScaleRotate is
 // cv2.warpAffine(img, M, (W,H), INTER_LINEAR, BORDER_REFLECT_101) on u8; its arithmetic is integer and is
-// restated here operation by operation so the u8 result is bit-identical to OpenCV's:
-//   * the 2x3 matrix is inverted in double exactly like cv::warpAffine (no fused multiply-adds),
-//   * source coordinates are fixed point with 10 fractional bits, rounded to 1/32 pixel:
-//       X = (round((Mi01*y + Mi02)*1024) + 16 + round(Mi00*x*1024)) >> 5,   sx = X >> 5, fx = X & 31,
-//   * the four taps go through BORDER_REFLECT_101, the weights are (32-fx)(32-fy), fx(32-fy), (32-fx)fy, fx*fy
-//     (OpenCV's 15-bit table holds exactly 32x these) and the sum is rounded as (acc + 512) >> 10.
+// restated in warp_fixed.cuh so the u8 result is bit-identical to OpenCV's: the matrix is inverted in
+// double like cv::warpAffine, source coordinates are fixed point rounded to 1/32 pixel, the four taps go
+// through BORDER_REFLECT_101 and are blended with 10-bit integer weights.
 // The gather reads the source through the read-only path (an image's six planes are 1.5 MB: L2-resident);
 // a rotated footprint is not a TMA box.  Output formats and stores are the D4 loader's.
 struct AffineArgs {
@@ -180,34 +178,16 @@ struct AffineArgs {
   int H, W;
 };
 
-__device__ __forceinline__ int reflect101(int p, int n) {
-  if (n == 1) return 0;
-  while ((unsigned)p >= (unsigned)n) p = p < 0 ? -p : 2 * n - 2 - p;
-  return p;
-}
-
-__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
-
 constexpr int kAfTileW = 64, kAfTileH = 16, kAfThreads = 256;
 
 __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineArgs a) {
   __shared__ double s_mi[6];
   __shared__ float s_m[kLdPlanes], s_d[kLdPlanes];
   const int b = blockIdx.y;
-  const int tiles_x = a.l.tiles_x;
-  const int tx0 = (blockIdx.x % tiles_x) * kAfTileW;
-  const int ty0 = (blockIdx.x / tiles_x) * kAfTileH;
+  const int tx0 = (blockIdx.x % a.l.tiles_x) * kAfTileW;
+  const int ty0 = (blockIdx.x / a.l.tiles_x) * kAfTileH;
 
-  if (threadIdx.x == 0) {
-    const double* M = a.M + 6 * (long long)b;
-    double D = __dsub_rn(__dmul_rn(M[0], M[4]), __dmul_rn(M[1], M[3]));
-    D = D != 0.0 ? __ddiv_rn(1.0, D) : 0.0;
-    const double m0 = __dmul_rn(M[4], D), m4 = __dmul_rn(M[0], D);
-    const double m1 = __dmul_rn(M[1], -D), m3 = __dmul_rn(M[3], -D);
-    s_mi[0] = m0; s_mi[1] = m1; s_mi[3] = m3; s_mi[4] = m4;
-    s_mi[2] = __dsub_rn(__dmul_rn(-m0, M[2]), __dmul_rn(m1, M[5]));
-    s_mi[5] = __dsub_rn(__dmul_rn(-m3, M[2]), __dmul_rn(m4, M[5]));
-  }
+  if (threadIdx.x == 0) warp_invert(a.M + 6 * (long long)b, s_mi);
   if (threadIdx.x >= 32 && threadIdx.x < 32 + kLdPlanes) {
     const int c = threadIdx.x - 32;
     int e = a.l.exp_id[b];
@@ -227,9 +207,8 @@ __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineA
 
   const int ox = tx0 + (threadIdx.x & (kAfTileW - 1));
   if (ox >= a.l.Wo) return;
-  const double xd = (double)(ox + x0);
-  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[0], xd), 1024.0));
-  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(s_mi[3], xd), 1024.0));
+  const int col_x = warp_col_delta(s_mi[0], ox + x0);
+  const int col_y = warp_col_delta(s_mi[3], ox + x0);
   float m[kLdPlanes], d[kLdPlanes];
 #pragma unroll
   for (int c = 0; c < kLdPlanes; ++c) {
@@ -240,25 +219,18 @@ __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineA
   for (int dy = threadIdx.x / kAfTileW; dy < kAfTileH; dy += kAfThreads / kAfTileW) {
     const int oy = ty0 + dy;
     if (oy >= a.l.Ho) break;
-    const double yd = (double)(oy + y0);
-    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[1], yd), s_mi[2]), 1024.0)) + 16;
-    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(s_mi[4], yd), s_mi[5]), 1024.0)) + 16;
-    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-    const int sx = sat_short(X >> 5), sy = sat_short(Y >> 5);
-    const int fx = X & 31, fy = Y & 31;
-    int xa = reflect101(sx, W), xb = reflect101(sx + 1, W);
-    int ya = reflect101(sy, H), yb = reflect101(sy + 1, H);
-    if (hflip) { xa = W - 1 - xa; xb = W - 1 - xb; }
-    if (vflip) { ya = H - 1 - ya; yb = H - 1 - yb; }
-    const int w00 = (32 - fx) * (32 - fy), w01 = fx * (32 - fy), w10 = (32 - fx) * fy, w11 = fx * fy;
-    const uint8_t* ra = gsrc + (long long)ya * W;
-    const uint8_t* rb = gsrc + (long long)yb * W;
+    WarpTaps t = warp_taps(warp_row_base(s_mi[1], s_mi[2], oy + y0), warp_row_base(s_mi[4], s_mi[5], oy + y0),
+                           col_x, col_y, W, H);
+    if (hflip) { t.xa = W - 1 - t.xa; t.xb = W - 1 - t.xb; }   // the warp reads the flipped image
+    if (vflip) { t.ya = H - 1 - t.ya; t.yb = H - 1 - t.yb; }
+    const uint8_t* ra = gsrc + (long long)t.ya * W;
+    const uint8_t* rb = gsrc + (long long)t.yb * W;
     float v[kLdPlanes];
 #pragma unroll
     for (int c = 0; c < kLdPlanes; ++c) {
-      const int acc = w00 * __ldg(ra + c * plane + xa) + w01 * __ldg(ra + c * plane + xb) +
-                      w10 * __ldg(rb + c * plane + xa) + w11 * __ldg(rb + c * plane + xb);
-      v[c] = __fmul_rn(__fsub_rn((float)((acc + 512) >> 10), m[c]), d[c]);
+      const int px = warp_blend(t, __ldg(ra + c * plane + t.xa), __ldg(ra + c * plane + t.xb),
+                                __ldg(rb + c * plane + t.xa), __ldg(rb + c * plane + t.xb));
+      v[c] = __fmul_rn(__fsub_rn((float)px, m[c]), d[c]);
     }
     emit_pixel(a.l, b, oy, ox, v);
   }

@@ -156,3 +156,40 @@ def test_transform_affine_restatement_vs_cv2_pipeline():
         a = O.transform_affine(img, mean, std, bool(v), bool(h), ang, (5, 9), (92, 92))
         b = O.transform_affine(img, mean, std, bool(v), bool(h), ang, (5, 9), (92, 92), use_cv2=True)
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_kernel_warp_arithmetic_compiled_for_the_host_is_cv2_warpaffine(tmp_path):
+    """The header the CUDA loader is built from (csrc/warp_fixed.cuh), compiled for the host with the kernel's
+    per-pixel control flow (tests/warp_host.cpp), against cv2.warpAffine: flips, crops, rotations, general maps."""
+    import ctypes
+    import subprocess
+    import cv2
+    here = os.path.dirname(os.path.abspath(__file__))
+    inc = os.path.join(here, "..", "recursion_cellular_image_classification_b200", "csrc")
+    so = str(tmp_path / "libwarp_host.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-I", inc,
+                    os.path.join(here, "warp_host.cpp"), "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    rng = np.random.default_rng(14)
+    for (H, W) in ((64, 64), (72, 100), (512, 512)):
+        src = rng.integers(0, 256, size=(6, H, W), dtype=np.uint8)
+        for t in range(6 if H == 512 else 40):
+            M = O.rotation_matrix(W, H, float(rng.uniform(-180, 180)) if t > 3 else 90.0 * t,
+                                  scale=1.0 if t % 2 == 0 else float(rng.uniform(0.6, 1.5)))
+            if t % 3 == 2:
+                M[:, 2] += rng.uniform(-6, 6, size=2)
+            vflip, hflip = int(rng.integers(2)), int(rng.integers(2))
+            Ho, Wo = int(rng.integers(1, H + 1)), int(rng.integers(1, W + 1))
+            y0, x0 = int(rng.integers(0, H - Ho + 1)), int(rng.integers(0, W - Wo + 1))
+            dst = np.empty((6, Ho, Wo), dtype=np.uint8)
+            lib.warp_host_planar_u8(src.ctypes.data_as(ctypes.c_void_p), H, W,
+                                    np.ascontiguousarray(M).ctypes.data_as(ctypes.c_void_p), vflip, hflip, y0, x0, Ho,
+                                    Wo, dst.ctypes.data_as(ctypes.c_void_p))
+            img = np.moveaxis(src, 0, 2)
+            if vflip:
+                img = img[::-1]
+            if hflip:
+                img = img[:, ::-1]
+            ref = cv2.warpAffine(np.ascontiguousarray(img), M, (W, H), flags=cv2.INTER_LINEAR,
+                                 borderMode=cv2.BORDER_REFLECT_101)[y0:y0 + Ho, x0:x0 + Wo]
+            np.testing.assert_array_equal(np.moveaxis(dst, 0, 2), ref)
