@@ -89,6 +89,20 @@ int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W, const int
                       const float* norm_m, const float* norm_d, int n_exp, void* dst, int B, int Ho,
                       int Wo, int out_format, rxb_stream_t stream);
 
+/* Baseline grayscale JPEG decode on the device.  Replaces ImagesDS._load_from_buffer,
+ * dataloader.py:141-146 (cv2.imdecode(buffer, -1) per channel file; files written by png_to_jpeg.py:11-15).
+ * Bit-identical to cv2.imdecode / libjpeg's default decoder (Huffman, accurate integer IDCT).
+ *   blob     u8  device: the n files' bytes back to back
+ *   begin, end  i64[n] device: file i is blob[begin[i] .. end[i]).  For files packed back to back pass an
+ *            offsets array o[n+1] as begin = o, end = o + 1; any subset / order of files works the same way
+ *   dst      u8 [n,H,W] device — e.g. [B,6,H,W] planar, the input of rxb_stats_accumulate / rxb_load_norm_*
+ *   status   i32[n] device: 0 ok; 1 not a JPEG / truncated headers; 2 unsupported (progressive, lossless,
+ *            arithmetic, 12-bit, multi-component); 3 missing or malformed table; 4 frame size != (H,W);
+ *            5 corrupt entropy-coded data.  A file with a non-zero status leaves (part of) its plane unwritten.
+ * One warp per file; no workspace. */
+int rxb_jpeg_decode_gray(const uint8_t* blob, const int64_t* begin, const int64_t* end, int n, int H, int W,
+                         uint8_t* dst, int32_t* status, rxb_stream_t stream);
+
 /* Arbitrary-angle variant of the loader: the reference's full train transform
  * VerticalFlip -> HorizontalFlip -> ShiftScaleRotate(rotate_limit=180) -> RandomCrop -> Normalize
  * (dataloader.py:42-48, 128-139).  ShiftScaleRotate is cv2.warpAffine(img, M, (W,H), INTER_LINEAR,

@@ -11,6 +11,9 @@ Parity status
   * warp_affine_u8 (ShiftScaleRotate at any angle): restates cv2.warpAffine's fixed-point bilinear remap; PINNED
     against cv2.warpAffine itself (OpenCV 4.13, the library call albumentations makes) executed in the tests and
     against tests/golden/warp_golden.npz; rotation_matrix is pinned bitwise against cv2.getRotationMatrix2D.
+  * jpeg_decode_gray (baseline grayscale JPEG, dataloader.py:141-146): restates libjpeg's marker parsing, Huffman
+    decoding and jpeg_idct_islow; PINNED bit-exact against cv2.imdecode (OpenCV 4.13 / libjpeg-turbo 3.1.2, the
+    reference's own call) executed in the tests and against tests/golden/jpeg_golden.npz.
   * d4_augment / normalize: restate albumentations==0.3.0 (requirement.txt:1), which is NOT installed
     and has no tests in the reference -> "parity unpinned" for that third-party boundary; the OpenCV
     calls it makes (cv2.flip, cv2.warpAffine) are executed for real here.
@@ -42,6 +45,195 @@ def compute_mean_std_arrays(planes, mean=None, std=None):
     m = sum_x / count
     s = np.sqrt((sum_x2 / count) - m ** 2)
     return m, s
+
+
+# ------------------------------------------------------------------------------------------------
+# L2: dataloader.py:141-146 — cv2.imdecode(buffer, -1) of a single-channel baseline JPEG (png_to_jpeg.py:11-15),
+# i.e. libjpeg: jdmarker.c (segments), jdhuff.c (canonical Huffman codes, DC prediction, run/size AC symbols, 0xFF00
+# unstuffing, restart intervals), jidctint.c jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2) and the range-limit table.
+ZIGZAG_TO_NATURAL = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34,
+                              27, 20, 13, 6, 7, 14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44,
+                              51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63])
+
+
+class JpegError(ValueError):
+    pass
+
+
+def _jpeg_segments(buf):
+    """Yield (marker, payload) up to and including SOS, then ('scan', entropy-coded bytes)."""
+    if buf[:2] != b"\xff\xd8":
+        raise JpegError("no SOI")
+    p = 2
+    while True:
+        if p + 4 > len(buf):
+            raise JpegError("ran off the end before SOS")
+        if buf[p] != 0xFF or buf[p + 1] == 0xFF:
+            p += 1
+            continue
+        m = buf[p + 1]
+        if m in (0x00, 0x01) or 0xD0 <= m <= 0xD8:
+            p += 2
+            continue
+        n = (buf[p + 2] << 8) | buf[p + 3]
+        yield m, buf[p + 4:p + 2 + n]
+        p += 2 + n
+        if m == 0xDA:
+            yield "scan", buf[p:]
+            return
+
+
+def _huff_codes(counts, symbols):
+    """(length, code) -> symbol for the canonical code of a DHT table."""
+    table, code, k = {}, 0, 0
+    for length in range(1, 17):
+        for _ in range(counts[length - 1]):
+            table[(length, code)] = symbols[k]
+            code += 1
+            k += 1
+        code <<= 1
+    return table
+
+
+def _idct_islow(blocks):
+    """jpeg_idct_islow on dequantised coefficients, int64 [n,8,8] -> uint8 [n,8,8]."""
+    F = dict(f0298=2446, f0390=3196, f0541=4433, f0765=6270, f0899=7373, f1175=9633, f1501=12299, f1847=15137,
+             f1961=16069, f2053=16819, f2562=20995, f3072=25172)
+
+    def pass_1d(v, shift):          # v: [..., 8] along the transformed axis
+        z2, z3 = v[..., 2], v[..., 6]
+        z1 = (z2 + z3) * F["f0541"]
+        tmp2 = z1 + z3 * (-F["f1847"])
+        tmp3 = z1 + z2 * F["f0765"]
+        z2, z3 = v[..., 0], v[..., 4]
+        tmp0, tmp1 = (z2 + z3) << 13, (z2 - z3) << 13
+        tmp10, tmp13, tmp11, tmp12 = tmp0 + tmp3, tmp0 - tmp3, tmp1 + tmp2, tmp1 - tmp2
+        tmp0, tmp1, tmp2, tmp3 = v[..., 7], v[..., 5], v[..., 3], v[..., 1]
+        z1, z2, z3, z4 = tmp0 + tmp3, tmp1 + tmp2, tmp0 + tmp2, tmp1 + tmp3
+        z5 = (z3 + z4) * F["f1175"]
+        tmp0, tmp1, tmp2, tmp3 = tmp0 * F["f0298"], tmp1 * F["f2053"], tmp2 * F["f3072"], tmp3 * F["f1501"]
+        z1, z2, z3, z4 = z1 * -F["f0899"], z2 * -F["f2562"], z3 * -F["f1961"] + z5, z4 * -F["f0390"] + z5
+        tmp0, tmp1, tmp2, tmp3 = tmp0 + z1 + z3, tmp1 + z2 + z4, tmp2 + z2 + z3, tmp3 + z1 + z4
+        out = np.stack([tmp10 + tmp3, tmp11 + tmp2, tmp12 + tmp1, tmp13 + tmp0,
+                        tmp13 - tmp0, tmp12 - tmp1, tmp11 - tmp2, tmp10 - tmp3], axis=-1)
+        return (out + (1 << (shift - 1))) >> shift
+
+    ws = pass_1d(np.swapaxes(blocks.astype(np.int64), 1, 2), 13 - 2)        # columns
+    out = pass_1d(np.swapaxes(ws, 1, 2), 13 + 2 + 3)                        # rows
+    i = out & 1023                                                         # range_limit[x & RANGE_MASK]
+    return np.where(i < 128, i + 128, np.where(i < 512, 255, np.where(i < 896, 0, i - 896))).astype(np.uint8)
+
+
+def jpeg_decode_gray(buf):
+    """cv2.imdecode(np.frombuffer(buf, np.uint8), -1) for a baseline, 8-bit, single-component JPEG -> uint8 [H,W]."""
+    buf = bytes(buf)
+    quant, huff, frame, scan_hdr, restart, scan = {}, {}, None, None, 0, None
+    for m, seg in _jpeg_segments(buf):
+        if m == 0xDB:
+            q = 0
+            while q < len(seg):
+                pq, tid = seg[q] >> 4, seg[q] & 15
+                if pq:
+                    vals = [(seg[q + 1 + 2 * i] << 8) | seg[q + 2 + 2 * i] for i in range(64)]
+                else:
+                    vals = list(seg[q + 1:q + 65])
+                quant[tid] = np.array(vals, dtype=np.int64)
+                q += 1 + (128 if pq else 64)
+        elif m == 0xC4:
+            q = 0
+            while q + 17 <= len(seg):
+                counts = list(seg[q + 1:q + 17])
+                total = sum(counts)
+                huff[(seg[q] >> 4, seg[q] & 15)] = _huff_codes(counts, seg[q + 17:q + 17 + total])
+                q += 17 + total
+        elif m in (0xC0, 0xC1):
+            if seg[0] != 8 or seg[5] != 1:
+                raise JpegError("unsupported: not 8-bit single-component")
+            frame = ((seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4], seg[8] & 3)
+        elif isinstance(m, int) and 0xC2 <= m <= 0xCF and m not in (0xC4, 0xC8):
+            raise JpegError("unsupported: progressive / lossless / arithmetic")
+        elif m == 0xDD:
+            restart = (seg[0] << 8) | seg[1]
+        elif m == 0xDA:
+            if seg[0] != 1 or seg[3] != 0 or seg[4] != 63:
+                raise JpegError("unsupported scan")
+            scan_hdr = (seg[2] >> 4, seg[2] & 15)
+        elif m == "scan":
+            scan = seg
+    H, W, tq = frame
+    dc, ac, qz = huff[(0, scan_hdr[0])], huff[(1, scan_hdr[1])], quant[tq]
+
+    # entropy-coded segment -> bits, unstuffed; markers split restart intervals
+    state = {"p": 0, "acc": 0, "n": 0, "marker": 0}
+
+    def fill(need):
+        while state["n"] < need:
+            c = 0
+            if not state["marker"]:
+                if state["p"] >= len(scan):
+                    state["marker"] = 0xD9
+                else:
+                    c = scan[state["p"]]
+                    state["p"] += 1
+                    if c == 0xFF:
+                        c2 = 0xFF
+                        while c2 == 0xFF and state["p"] < len(scan):
+                            c2 = scan[state["p"]]
+                            state["p"] += 1
+                        if c2 == 0xFF:
+                            c2 = 0xD9
+                        if c2 != 0:
+                            state["marker"], c = c2, 0
+            state["acc"] = ((state["acc"] << 8) | c) & 0xFFFFFFFFFFFF
+            state["n"] += 8
+
+    def bits(k):
+        fill(k)
+        v = (state["acc"] >> (state["n"] - k)) & ((1 << k) - 1)
+        state["n"] -= k
+        return v
+
+    def symbol(table):
+        code = 0
+        for length in range(1, 17):
+            code = (code << 1) | bits(1)
+            if (length, code) in table:
+                return table[(length, code)]
+        raise JpegError("invalid Huffman code")
+
+    def extend(v, s):
+        return v - (1 << s) + 1 if v < (1 << (s - 1)) else v
+
+    bw, bh = (W + 7) // 8, (H + 7) // 8
+    coefs = np.zeros((bw * bh, 64), dtype=np.int64)
+    pred = 0
+    for blk in range(bw * bh):
+        if restart and blk and blk % restart == 0:
+            state["acc"], state["n"] = 0, 0
+            if not state["marker"]:
+                while not (scan[state["p"]] == 0xFF and 0xD0 <= scan[state["p"] + 1] <= 0xD7):
+                    state["p"] += 1
+                state["p"] += 2
+            state["marker"] = 0
+            pred = 0
+        s = symbol(dc)
+        pred += extend(bits(s), s) if s else 0
+        coefs[blk, 0] = pred * qz[0]
+        k = 1
+        while k < 64:
+            rs = symbol(ac)
+            r, s = rs >> 4, rs & 15
+            if s:
+                k += r
+                coefs[blk, ZIGZAG_TO_NATURAL[k]] = extend(bits(s), s) * qz[k]
+                k += 1
+            elif r == 15:
+                k += 16
+            else:
+                break
+    px = _idct_islow(coefs.reshape(-1, 8, 8))
+    img = px.reshape(bh, bw, 8, 8).transpose(0, 2, 1, 3).reshape(bh * 8, bw * 8)
+    return np.ascontiguousarray(img[:H, :W])
 
 
 # ------------------------------------------------------------------------------------------------

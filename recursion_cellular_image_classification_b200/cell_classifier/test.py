@@ -19,7 +19,7 @@ def _model_logits(model, ds, batch, dev, code):
         b = dict(batch)
         b["codes"] = torch.full_like(batch["codes"], code)
         xs = ds.device_batch(b, dev)                                  # [B*G, H/2, W/2, 32]
-        G = batch["planes"].shape[1]
+        G = batch["codes"].shape[1]
         out = model(xs)                                               # [B*G, C]
         out = out.to(dev).float()
         return out.view(-1, G, out.shape[-1]).mean(1)                # site / control average (linear head)

@@ -94,6 +94,65 @@ def load_norm_aug(src, src_idx, exp_id, aug, crop_yx, norm_m, norm_d, out_hw, ou
     return out
 
 
+JPEG_STATUS = {1: "not a JPEG / truncated headers", 2: "unsupported JPEG (progressive, lossless, arithmetic, 12-bit or "
+               "multi-component)", 3: "missing or malformed quantisation / Huffman table",
+               4: "frame size differs from the expected size", 5: "corrupt entropy-coded data"}
+
+
+def jpeg_frame_size(buf):
+    """(H, W) from the SOF segment of a JPEG byte string (host-side header peek: sizes the output tensor)."""
+    p = 2
+    while p + 9 < len(buf):
+        if buf[p] != 0xFF or buf[p + 1] == 0xFF:
+            p += 1
+            continue
+        m = buf[p + 1]
+        if m in (0x00, 0x01) or 0xD0 <= m <= 0xD8:
+            p += 2
+            continue
+        if 0xC0 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            return (buf[p + 5] << 8) | buf[p + 6], (buf[p + 7] << 8) | buf[p + 8]
+        p += 2 + ((buf[p + 2] << 8) | buf[p + 3])
+    raise _lib.RxbError("no JPEG frame header found")
+
+
+def pack_jpeg_buffers(buffers):
+    """List of JPEG byte strings -> (blob uint8 [total], offsets int64 [n+1]) host tensors for jpeg_decode_gray."""
+    sizes = np.fromiter((len(b) for b in buffers), dtype=np.int64, count=len(buffers))
+    offsets = np.zeros(len(buffers) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    blob = np.frombuffer(b"".join(buffers), dtype=np.uint8) if len(buffers) else np.zeros(0, np.uint8)
+    return torch.from_numpy(blob.copy()), torch.from_numpy(offsets)
+
+
+def jpeg_decode_gray(blob, offsets, hw, select=None, out=None, check_status=True):
+    """Decode single-channel baseline JPEG files on the device (cv2.imdecode(buf, -1) bit-exact).
+    blob u8 [total] and offsets int64 [n_files+1] are CUDA tensors (see pack_jpeg_buffers); `select` (int64 CUDA
+    tensor of file indices) decodes that subset, in that order.  Returns u8 [n,H,W] (and the int32 [n] status tensor
+    when check_status is False — checking costs a device->host sync)."""
+    require_gpu()
+    blob = _cuda(blob, torch.uint8)
+    offsets = _cuda(offsets, torch.int64)
+    if select is None:
+        begin, end = offsets[:-1], offsets[1:]            # views into the same array: 8-byte aligned
+    else:
+        select = _cuda(select, torch.int64)
+        begin, end = offsets[:-1][select].contiguous(), offsets[1:][select].contiguous()
+    n = begin.numel()
+    H, W = hw
+    if out is None:
+        out = torch.empty(n, H, W, dtype=torch.uint8, device=blob.device)
+    status = torch.zeros(max(n, 1), dtype=torch.int32, device=blob.device)
+    check(load().rxb_jpeg_decode_gray(ptr(blob), ptr(begin), ptr(end), n, H, W, ptr(out), ptr(status), stream_ptr()))
+    if not check_status:
+        return out, status[:n]
+    bad = torch.nonzero(status[:n]).flatten().tolist()
+    if bad:
+        code = int(status[bad[0]])
+        raise _lib.RxbError("JPEG file %d of %d: %s (status %d)" % (bad[0], n, JPEG_STATUS.get(code, "?"), code))
+    return out
+
+
 def rotation_matrix(w, h, angle, scale=1.0):
     """The matrix albumentations 0.3.0 ShiftScaleRotate hands to cv2.warpAffine (dataloader.py:45-46):
     cv2.getRotationMatrix2D((w/2, h/2), angle, scale), float64 [2,3] — host data, restated so the loader does not

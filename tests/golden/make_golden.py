@@ -10,6 +10,9 @@ Fixtures written next to this file:
   assign_golden.npz  cell_classifier.test.test (reference test.py:9-58) driven by a seeded logits callable:
                      the masked+rescaled assignment for a 64-well case (inputs stored) and a full
                      1108-well experiment (inputs regenerated from the seed).
+  jpeg_golden.npz    the reference's own PNG->JPEG converter (png_to_jpeg.convert_png_to_jpeg, :11-15: PIL 'L', quality 95)
+                     run on seeded synthetic planes, and cv2.imdecode(buf, -1) of the result — the reference's decode
+                     call (cell_classifier/dataloader.py:141-146): file bytes + decoded planes.
   warp_golden.npz    cv2.getRotationMatrix2D + cv2.warpAffine(INTER_LINEAR, BORDER_REFLECT_101) — the call
                      albumentations 0.3.0 ShiftScaleRotate makes for dataloader.py:45-46 (albumentations itself is
                      not installed) — on seeded 6-channel u8 images: full outputs at 48x48, SHA-256 digests at 512x512.
@@ -124,7 +127,39 @@ def make_warp():
     print("warp golden:", cv2.__version__, digests[1][:16])
 
 
+def make_jpeg():
+    import cv2
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)       # png_to_jpeg.py is a script: it globs data/**/*.png in the CWD (nothing there) when imported
+    try:
+        sys.path.insert(0, REF)
+        import png_to_jpeg
+        files, planes, shapes = [], [], []
+        for i, (seed, H, W) in enumerate([(21, 64, 64), (22, 64, 64), (23, 40, 72), (24, 256, 256)]):
+            img = synth_planes(seed, n=1, C=1, H=H, W=W)[0, 0]
+            path = os.path.join(tmp, "w%d.png" % i)
+            cv2.imwrite(path, img)
+            png_to_jpeg.convert_png_to_jpeg(path)
+            buf = open(os.path.join(tmp, "w%d.jpeg" % i), "rb").read()
+            dec = cv2.imdecode(np.frombuffer(buf, dtype=np.uint8), -1)
+            assert dec.shape == (H, W) and dec.dtype == np.uint8
+            files.append(np.frombuffer(buf, dtype=np.uint8))
+            planes.append(dec.reshape(-1))
+            shapes.append((H, W))
+        np.savez_compressed(os.path.join(HERE, "jpeg_golden.npz"), shapes=np.array(shapes),
+                            file_sizes=np.array([len(f) for f in files]), files=np.concatenate(files),
+                            planes=np.concatenate(planes), cv2_version=cv2.__version__)
+        print("jpeg golden:", [len(f) for f in files])
+    finally:
+        os.chdir(cwd)
+
+
 if __name__ == "__main__":
+    if "--jpeg-only" in sys.argv:
+        make_jpeg()
+        sys.exit(0)
+    make_jpeg()
     make_warp()
     if "--warp-only" in sys.argv:
         sys.exit(0)

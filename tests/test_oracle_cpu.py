@@ -193,3 +193,89 @@ def test_kernel_warp_arithmetic_compiled_for_the_host_is_cv2_warpaffine(tmp_path
             ref = cv2.warpAffine(np.ascontiguousarray(img), M, (W, H), flags=cv2.INTER_LINEAR,
                                  borderMode=cv2.BORDER_REFLECT_101)[y0:y0 + Ho, x0:x0 + Wo]
             np.testing.assert_array_equal(np.moveaxis(dst, 0, 2), ref)
+
+
+# ---------------------------------------------------------------- baseline JPEG decode
+def _jpeg_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "jpeg_golden.npz"))
+    fo = np.concatenate([[0], np.cumsum(g["file_sizes"])])
+    po = np.concatenate([[0], np.cumsum([h * w for h, w in g["shapes"]])])
+    return [(g["files"][fo[i]:fo[i + 1]].tobytes(), g["planes"][po[i]:po[i + 1]].reshape(tuple(g["shapes"][i])))
+            for i in range(len(g["shapes"]))]
+
+
+def _jpeg_cases():
+    """(bytes, cv2.imdecode output): sizes that are / are not multiples of 8, three qualities, default and optimised
+    Huffman tables, restart intervals, fluorescence-like / noise / smooth content."""
+    import cv2
+    rng = np.random.default_rng(15)
+    for (H, W) in [(64, 64), (8, 8), (37, 53), (1, 1), (96, 40)]:
+        yy, xx = np.mgrid[0:H, 0:W]
+        for img in (synth_planes(3, 1, C=1, H=H, W=W)[0, 0], rng.integers(0, 256, size=(H, W), dtype=np.uint8),
+                    ((np.sin(yy / 7.0) + np.cos(xx / 5.0)) * 60 + 128).clip(0, 255).astype(np.uint8)):
+            for q in (95, 40, 100):
+                for extra in ([], [cv2.IMWRITE_JPEG_OPTIMIZE, 1], [cv2.IMWRITE_JPEG_RST_INTERVAL, 3]):
+                    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q] + extra)
+                    assert ok
+                    yield buf.tobytes(), cv2.imdecode(buf, -1)
+
+
+def test_jpeg_oracle_matches_reference_golden(golden_dir):
+    for buf, plane in _jpeg_golden(golden_dir):
+        np.testing.assert_array_equal(O.jpeg_decode_gray(buf), plane)
+
+
+def test_jpeg_oracle_is_cv2_imdecode():
+    n = 0
+    for buf, ref in _jpeg_cases():
+        np.testing.assert_array_equal(O.jpeg_decode_gray(buf), ref)
+        n += 1
+    assert n == 135
+    import cv2
+    ok, buf = cv2.imencode(".jpg", np.zeros((16, 16), np.uint8), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(O.JpegError):
+        O.jpeg_decode_gray(buf.tobytes())
+    with pytest.raises(O.JpegError):
+        O.jpeg_decode_gray(b"not a jpeg at all")
+
+
+def test_kernel_jpeg_code_compiled_for_the_host_is_cv2_imdecode(tmp_path, golden_dir):
+    """The header the CUDA decoder is built from (csrc/jpeg_fixed.cuh), compiled for the host (tests/jpeg_host.cpp):
+    bit-exact against the reference golden, cv2.imdecode at 512x512, and the status codes."""
+    import ctypes
+    import subprocess
+    import cv2
+    here = os.path.dirname(os.path.abspath(__file__))
+    inc = os.path.join(here, "..", "recursion_cellular_image_classification_b200", "csrc")
+    so = str(tmp_path / "libjpeg_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-I", inc, os.path.join(here, "jpeg_host.cpp"),
+                    "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+
+    def dec(buf, H, W):
+        a = np.frombuffer(buf, dtype=np.uint8)
+        dst = np.zeros((H, W), np.uint8)
+        st = lib.jpeg_host_decode_gray(a.ctypes.data_as(ctypes.c_void_p), len(a), H, W,
+                                       dst.ctypes.data_as(ctypes.c_void_p))
+        return st, dst
+
+    for buf, plane in _jpeg_golden(golden_dir):
+        st, got = dec(buf, *plane.shape)
+        assert st == 0
+        np.testing.assert_array_equal(got, plane)
+    for buf, ref in _jpeg_cases():
+        st, got = dec(buf, *ref.shape)
+        assert st == 0
+        np.testing.assert_array_equal(got, ref)
+    for seed in (3, 4):
+        ok, buf = cv2.imencode(".jpg", synth_planes(seed, 1, C=1)[0, 0], [cv2.IMWRITE_JPEG_QUALITY, 95])
+        st, got = dec(buf.tobytes(), 512, 512)
+        assert st == 0
+        np.testing.assert_array_equal(got, cv2.imdecode(buf, -1))
+    assert dec(buf.tobytes(), 256, 256)[0] == 4                      # frame size != expected
+    assert dec(b"not a jpeg at all....", 8, 8)[0] == 1
+    assert dec(buf.tobytes()[:300], 512, 512)[0] == 1                # headers cut short
+    ok, pbuf = cv2.imencode(".jpg", np.zeros((16, 16), np.uint8), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert dec(pbuf.tobytes(), 16, 16)[0] == 2
+    ok, cbuf = cv2.imencode(".jpg", np.zeros((16, 16, 3), np.uint8))
+    assert dec(cbuf.tobytes(), 16, 16)[0] == 2                       # three components
