@@ -13,12 +13,12 @@
 
 #if defined(__CUDACC__)
 #define RXB_JFN __device__ __forceinline__
-#define RXB_JTABLE __device__ const
-#define RXB_JLD(p) __ldg(p)
+#define RXB_JLD(p) (*(p))       // generic loads: the bit reader's window lives in shared memory
+#define RXB_JSYNC() __syncwarp()
 #else
 #define RXB_JFN inline
-#define RXB_JTABLE static const
 #define RXB_JLD(p) (*(p))
+#define RXB_JSYNC()
 #endif
 
 namespace rxb {
@@ -35,10 +35,14 @@ enum Status {
 
 constexpr int kLook = 9;     // look-ahead bits (libjpeg uses 8; longer codes take the canonical-code walk)
 
-// zigzag position -> natural (row-major) position, jpeg_natural_order
-RXB_JTABLE uint8_t kNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+// natural (row-major) position -> zigzag position (inverse of jpeg_natural_order).  Coefficients are kept in the
+// order they are decoded; the inverse DCT reads them through this map, which folds away in its unrolled loops.
+RXB_JFN constexpr int zigzag_of_natural(int j) {
+  constexpr uint8_t t[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                             41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                             46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+  return t[j];
+}
 
 struct HuffTable {
   int maxcode[18];           // largest code of each length (-1 if none); [17] is a sentinel
@@ -194,6 +198,22 @@ RXB_JFN void br_fill(BitReader* b) {
   }
 }
 
+// At least 32 valid bits (a code of up to 16 bits plus up to 15 value bits).  Common case: the next four bytes hold
+// no 0xFF, so they are appended at once; otherwise the byte-wise path sorts out stuffing and markers.
+RXB_JFN void br_need32(BitReader* b) {
+  if (b->nbits >= 32) return;
+  if (!b->marker && b->p + 4 <= b->end) {
+    const uint32_t b0 = RXB_JLD(b->p), b1 = RXB_JLD(b->p + 1), b2 = RXB_JLD(b->p + 2), b3 = RXB_JLD(b->p + 3);
+    if (b0 != 0xFF && b1 != 0xFF && b2 != 0xFF && b3 != 0xFF) {
+      b->acc = (b->acc << 32) | (uint64_t)((b0 << 24) | (b1 << 16) | (b2 << 8) | b3);
+      b->nbits += 32;
+      b->p += 4;
+      return;
+    }
+  }
+  br_fill(b);
+}
+
 RXB_JFN int br_peek(const BitReader* b, int n) { return (int)((b->acc >> (b->nbits - n)) & ((1u << n) - 1)); }
 
 RXB_JFN int huff_decode(BitReader* b, const HuffTable* t, int* err) {
@@ -238,33 +258,47 @@ RXB_JFN void br_restart(BitReader* b) {
   }
 }
 
-// decode_mcu for one 8x8 block.  `coef` (64 ints, zeroed by the caller) receives DEQUANTISED coefficients in natural
+// decode_mcu for one 8x8 block.  `coef` (64 ints, zeroed by the caller) receives DEQUANTISED coefficients in ZIGZAG
 // order: the JCOEF (short) value times the quantiser, which is what jpeg_idct_islow's DEQUANTIZE computes.
 RXB_JFN void decode_block(BitReader* b, const HuffTable* dc, const HuffTable* ac, const uint16_t* quant, int* pred,
                           int* coef, int* err) {
-  br_fill(b);
+  br_need32(b);
   int s = huff_decode(b, dc, err);
-  if (s) {
-    br_fill(b);
-    s = receive_extend(b, s & 15);
-  }
+  if (s) s = receive_extend(b, s & 15);
   *pred += s;
   coef[0] = (int)(int16_t)*pred * (int)quant[0];
   for (int k = 1; k < 64; ++k) {
-    br_fill(b);
+    br_need32(b);
     const int rs = huff_decode(b, ac, err);
     const int r = rs >> 4;
     s = rs & 15;
     if (s) {
       k += r;
       if (k > 63) { *err = RXB_JPG_BAD_CODE; return; }
-      const int v = receive_extend(b, s);
-      coef[kNatural[k]] = (int)(int16_t)v * (int)quant[k];
+      coef[k] = (int)(int16_t)receive_extend(b, s) * (int)quant[k];
     } else {
       if (r != 15) return;                                    // EOB
       k += 15;                                                // ZRL
     }
   }
+}
+
+// The entropy-coded bytes are read through a sliding window (shared memory on the device): `win` holds file bytes
+// [file_pos, file_pos + valid).  Before a block is decoded at least kWinGuard unread bytes must be in the window
+// (a block consumes at most 64 symbols x 31 bits, doubled by byte stuffing = 496 bytes) unless the file ends there.
+// `lane`/`nlanes`: the copy is shared by the lanes of a warp (host: 0, 1).  All lanes pass the same arguments;
+// returns the new number of valid bytes (the unread bytes now start at win[0]).
+constexpr int kWin = 2048, kWinGuard = 512;
+
+RXB_JFN int win_slide(uint8_t* win, int valid, int consumed, const uint8_t* rest, int rest_len, int lane, int nlanes) {
+  const int keep = valid - consumed;                          // < kWinGuard <= consumed: source and target disjoint
+  RXB_JSYNC();                                                // the decoding lane is done with the old window
+  for (int i = lane; i < keep; i += nlanes) win[i] = win[consumed + i];
+  RXB_JSYNC();                                                // the fresh bytes may land on the bytes just moved
+  const int fresh = rest_len < kWin - keep ? rest_len : kWin - keep;
+  for (int i = lane; i < fresh; i += nlanes) win[keep + i] = RXB_JLD(rest + i);
+  RXB_JSYNC();
+  return keep + fresh;
 }
 
 // ---- jidctint.c jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2) ----
@@ -323,9 +357,12 @@ RXB_JFN int range_limit(int x) {
   return i < 128 ? i + 128 : (i < 512 ? 255 : (i < 896 ? 0 : i - 896));
 }
 
-// coef: 64 dequantised coefficients (natural order, element stride `cstride` ints) -> 8 rows of 8 samples, each row
-// packed little-endian into two 32-bit words (row r: px[2r] = samples 0-3, px[2r+1] = samples 4-7).
-RXB_JFN void idct_islow(const int* coef, uint32_t* px) {
+// zz: 64 dequantised coefficients in zigzag order -> 8 rows of 8 samples, each row packed little-endian into two
+// 32-bit words (row r: px[2r] = samples 0-3, px[2r+1] = samples 4-7).
+RXB_JFN void idct_islow(const int* zz, uint32_t* px) {
+  int coef[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) coef[j] = zz[zigzag_of_natural(j)];
   int ws[64];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {

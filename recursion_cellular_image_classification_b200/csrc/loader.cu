@@ -178,7 +178,8 @@ struct AffineArgs {
   int H, W;
 };
 
-constexpr int kAfTileW = 64, kAfTileH = 16, kAfThreads = 256;
+constexpr int kAfTileW = 64, kAfTileH = 16, kAfThreads = 256;   // 8 warps x 8 columns
+static_assert(kAfThreads / 32 * 8 == kAfTileW, "one 8-column strip per warp");
 
 __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineArgs a) {
   __shared__ double s_mi[6];
@@ -205,7 +206,11 @@ __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineA
   const long long img = min(max((long long)a.l.src_idx[b], 0ll), a.l.n_src - 1);
   const uint8_t* gsrc = a.l.src + img * kLdPlanes * plane;
 
-  const int ox = tx0 + (threadIdx.x & (kAfTileW - 1));
+  // A warp covers an 8x4 pixel patch (lane = 4 rows x 8 columns), so its rotated source footprint stays compact
+  // (about 10x10 pixels: a third of the sectors a 32x1 row of pixels touches) and its stores still form full
+  // 128/256-byte runs in the NHWC8 / space-to-depth layouts.  Warp w owns columns [8w, 8w+8) of the 64x16 tile.
+  const int lane = threadIdx.x & 31;
+  const int ox = tx0 + (threadIdx.x >> 5) * 8 + (lane & 7);
   if (ox >= a.l.Wo) return;
   const int col_x = warp_col_delta(s_mi[0], ox + x0);
   const int col_y = warp_col_delta(s_mi[3], ox + x0);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kAfThreads) loader_affine_kernel(const AffineA
     d[c] = s_d[c];
   }
 
-  for (int dy = threadIdx.x / kAfTileW; dy < kAfTileH; dy += kAfThreads / kAfTileW) {
+  for (int dy = lane >> 3; dy < kAfTileH; dy += 4) {
     const int oy = ty0 + dy;
     if (oy >= a.l.Ho) break;
     WarpTaps t = warp_taps(warp_row_base(s_mi[1], s_mi[2], oy + y0), warp_row_base(s_mi[4], s_mi[5], oy + y0),

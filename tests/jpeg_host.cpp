@@ -11,11 +11,23 @@ extern "C" int jpeg_host_decode_gray(const uint8_t* data, int len, int H, int W,
   int st = parse_headers(data, len, &f, &dc, &ac);
   if (st) return st;
   if (f.H != H || f.W != W) return RXB_JPG_BAD_SIZE;
+  // the kernel's control flow: a sliding window over the entropy-coded bytes, one block at a time
+  static uint8_t win[kWin];
+  int file_pos = f.scan;
+  int valid = win_slide(win, 0, 0, data + file_pos, len - file_pos, 0, 1);
   BitReader br;
-  br_init(&br, data + f.scan, data + len);
+  br_init(&br, win, win + valid);
   const int bw = (W + 7) / 8, bh = (H + 7) / 8;
   int pred = 0, err = 0;
   for (int blk = 0; blk < bw * bh; ++blk) {
+    const int consumed = (int)(br.p - win);
+    const int more = len - (file_pos + valid);
+    if (valid - consumed < kWinGuard && more > 0) {
+      valid = win_slide(win, valid, consumed, data + file_pos + valid, more, 0, 1);
+      file_pos += consumed;
+      br.p = win;
+      br.end = win + valid;
+    }
     if (f.restart_interval && blk && blk % f.restart_interval == 0) {
       br_restart(&br);
       pred = 0;
