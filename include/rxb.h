@@ -99,9 +99,14 @@ int rxb_load_norm_aug(const uint8_t* src, int64_t n_src, int H, int W, const int
  *   status   i32[n] device: 0 ok; 1 not a JPEG / truncated headers; 2 unsupported (progressive, lossless,
  *            arithmetic, 12-bit, multi-component); 3 missing or malformed table; 4 frame size != (H,W);
  *            5 corrupt entropy-coded data.  A file with a non-zero status leaves (part of) its plane unwritten.
- * One warp per file; no workspace. */
+ *   workspace  device, 16-byte aligned, rxb_jpeg_decode_workspace_bytes(n,H,W) bytes (the quantised coefficients,
+ *            128 bytes per 8x8 block), or NULL.  With a workspace all 32 lanes of a file's warp decode
+ *            (speculative, self-synchronising subsequences); without one a single lane per file decodes — same
+ *            result, several times slower.  Files with restart intervals always take the single-lane kernel. */
+size_t rxb_jpeg_decode_workspace_bytes(int n, int H, int W);
 int rxb_jpeg_decode_gray(const uint8_t* blob, const int64_t* begin, const int64_t* end, int n, int H, int W,
-                         uint8_t* dst, int32_t* status, rxb_stream_t stream);
+                         uint8_t* dst, int32_t* status, void* workspace, size_t workspace_bytes,
+                         rxb_stream_t stream);
 
 /* Arbitrary-angle variant of the loader: the reference's full train transform
  * VerticalFlip -> HorizontalFlip -> ShiftScaleRotate(rotate_limit=180) -> RandomCrop -> Normalize

@@ -46,8 +46,9 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p]),
     "rxb_load_norm_aug": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "rxb_jpeg_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "rxb_jpeg_decode_gray": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
-                                     c_void_p]),
+                                     c_void_p, c_size_t, c_void_p]),
     "rxb_load_norm_affine": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "rxb_tta_softmax_avg_mask": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -171,10 +171,11 @@ struct BitReader {
   uint64_t acc;
   int nbits;
   int marker;                // 0 = none pending
+  int fake;                  // zero bits appended after the end of the data (a consumed one means truncation)
 };
 
 RXB_JFN void br_init(BitReader* b, const uint8_t* p, const uint8_t* end) {
-  b->p = p; b->end = end; b->acc = 0; b->nbits = 0; b->marker = 0;
+  b->p = p; b->end = end; b->acc = 0; b->nbits = 0; b->marker = 0; b->fake = 0;
 }
 
 RXB_JFN void br_fill(BitReader* b) {
@@ -193,10 +194,14 @@ RXB_JFN void br_fill(BitReader* b) {
         }
       }
     }
+    if (b->marker) b->fake += 8;
     b->acc = (b->acc << 8) | (uint64_t)c;
     b->nbits += 8;
   }
 }
+
+// True if decoding consumed bits that were not in the file (the scan ended before the last block did).
+RXB_JFN bool br_overran(const BitReader* b) { return b->fake > b->nbits; }
 
 // At least 32 valid bits (a code of up to 16 bits plus up to 15 value bits).  Common case: the next four bytes hold
 // no 0xFF, so they are appended at once; otherwise the byte-wise path sorts out stuffing and markers.
@@ -248,6 +253,7 @@ RXB_JFN int receive_extend(BitReader* b, int s) {
 RXB_JFN void br_restart(BitReader* b) {
   b->acc = 0;
   b->nbits = 0;
+  b->fake = 0;
   if (!b->marker) {                                           // marker not reached yet: scan forward to it
     while (b->p + 1 < b->end && !(RXB_JLD(b->p) == 0xFF && RXB_JLD(b->p + 1) >= 0xD0 && RXB_JLD(b->p + 1) <= 0xD7))
       ++b->p;
@@ -300,6 +306,135 @@ RXB_JFN int win_slide(uint8_t* win, int valid, int consumed, const uint8_t* rest
   RXB_JSYNC();
   return keep + fresh;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Speculative parallel decoding inside ONE file (the warp-scope form of self-synchronising Huffman decoding).
+// A Huffman-coded stream can only be decoded from a known symbol boundary, but a decoder started at a wrong bit
+// falls into step with the true symbol sequence after a few symbols.  The unstuffed ("clean") stream is cut into
+// chunks of 32 subsequences of kSubBits bits, one per lane:
+//   1. every lane decodes its subsequence speculatively from its first bit, assuming a block starts there, and
+//      records its exit state (bit position just past the subsequence end, zigzag index k) and block count;
+//   2. lane l takes lane l-1's exit state as its true entry state (lane 0: the carry from the previous chunk); lanes
+//      whose entry changed re-decode; repeated until no entry changes (2-4 rounds in practice, at most 31);
+//   3. a prefix sum over the block counts gives every lane its first block index;
+//   4. every lane decodes once more from its true entry state and writes the quantised coefficients (JCOEF, zigzag
+//      order, DC still a difference) to the file's coefficient buffer.
+// A state is (bit position, k): k = 0 means a DC symbol comes next.  The DC predictor is not part of it — DC values
+// are a running sum, taken afterwards.  Files with restart intervals take the sequential path.
+constexpr int kSubBits = 512;
+constexpr int kChunkBytes = 32 * kSubBits / 8;   // 2048 clean bytes per round
+constexpr int kSlack = 64;                       // look-ahead bytes behind the chunk (a symbol may straddle its end)
+
+struct SubState {
+  int pos;   // bit position relative to the chunk start
+  int k;     // zigzag index of the next coefficient; 0 = a DC symbol is next
+};
+
+RXB_JFN uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x0123);
+#else
+  return __builtin_bswap32(x);
+#endif
+}
+
+// 32 bits of the clean stream starting at bit `pos` (win is 4-byte aligned)
+RXB_JFN uint32_t cr_peek32(const uint8_t* win, int pos) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(win) + (pos >> 5);
+  const uint32_t a = bswap32(w[0]), b = bswap32(w[1]);
+  const int sh = pos & 31;
+  return sh ? (a << sh) | (b >> (32 - sh)) : a;
+}
+
+RXB_JFN int huff_lookup(const HuffTable* t, uint32_t bits, int* len) {
+  const uint16_t e = t->lut[bits >> (32 - kLook)];
+  if (e) {
+    *len = e >> 8;
+    return e & 255;
+  }
+  int l = kLook + 1;
+  int code = (int)(bits >> (32 - l));
+  while (l <= 16 && code > t->maxcode[l]) {
+    ++l;
+    code = (int)(bits >> (32 - l));
+  }
+  if (l > 16) {
+    *len = 16;
+    return 0;
+  }
+  *len = l;
+  return t->huffval[(code + t->valoffset[l]) & 255];
+}
+
+RXB_JFN int extend_bits(uint32_t bits, int len, int s) {       // the s value bits that follow a len-bit code
+  const int x = (int)((bits << len) >> (32 - s));
+  return x < (1 << (s - 1)) ? x - (1 << s) + 1 : x;
+}
+
+// Decode from *st until the bit position reaches end_bit (always stopping on a symbol boundary).  *block is the index
+// of the block in progress.  With OUT, coefficients of blocks below nblk are stored to coef[block*64 + k] and
+// *done_pos receives the bit position at which the file's last block (nblk - 1) ended, if that happens here.
+template <bool OUT>
+RXB_JFN void sub_decode(const uint8_t* win, SubState* st, int end_bit, const HuffTable* dc, const HuffTable* ac,
+                        int* block, int16_t* coef, int nblk, int* done_pos) {
+  int pos = st->pos, k = st->k, bi = *block;
+  while (pos < end_bit) {
+    const uint32_t bits = cr_peek32(win, pos);
+    int len;
+    if (k == 0) {
+      const int s = huff_lookup(dc, bits, &len) & 15;
+      if (OUT && bi < nblk) coef[(long long)bi * 64] = (int16_t)(s ? extend_bits(bits, len, s) : 0);
+      pos += len + s;
+      k = 1;
+    } else {
+      const int rs = huff_lookup(ac, bits, &len);
+      const int r = rs >> 4, s = rs & 15;
+      if (s) {
+        k += r;
+        if (k > 63) k = 63;                                   // corrupt data: keep the store in bounds
+        if (OUT && bi < nblk) coef[(long long)bi * 64 + k] = (int16_t)extend_bits(bits, len, s);
+        pos += len + s;
+        ++k;
+      } else {
+        pos += len;
+        k = r == 15 ? k + 16 : 64;                            // ZRL / EOB
+      }
+      if (k >= 64) {
+        k = 0;
+        ++bi;
+        if (OUT && bi == nblk) *done_pos = pos;
+      }
+    }
+  }
+  st->pos = pos;
+  st->k = k;
+  *block = bi;
+}
+
+// Unstuffing, one lane's share: up to four raw bytes at [base, base+4) below `limit`.  keep bit j = byte j is
+// entropy-coded data (a 0x00 that follows 0xFF is stuffing); *marker = index of the first byte that starts a marker
+// (0xFF followed by anything but 0x00, or by the end of the file), 4 if none — the data ends there.
+RXB_JFN void classify4(const uint8_t* raw, int raw_len, int base, int limit, int* keep, int* marker, uint8_t* bytes) {
+  *keep = 0;
+  *marker = 4;
+  int prev = base > 0 ? RXB_JLD(raw + base - 1) : 0;
+  for (int j = 0; j < 4; ++j) {
+    const int i = base + j;
+    if (i >= limit) break;
+    const int b = RXB_JLD(raw + i);
+    const int next = i + 1 < raw_len ? RXB_JLD(raw + i + 1) : 0xD9;
+    if (b == 0xFF && next != 0x00) {
+      *marker = j;
+      break;
+    }
+    if (!(b == 0x00 && prev == 0xFF)) *keep |= 1 << j;
+    bytes[j] = (uint8_t)b;
+    prev = b;
+  }
+}
+
+// Inverse DCT of one block of the coefficient buffer: JCOEF values (zigzag order) times the quantiser (DEQUANTIZE).
+RXB_JFN void idct_islow_q(const int16_t* zz, const uint16_t* quant, uint32_t* px);
 
 // ---- jidctint.c jpeg_idct_islow (CONST_BITS 13, PASS1_BITS 2) ----
 constexpr int kF0298 = 2446, kF0390 = 3196, kF0541 = 4433, kF0765 = 6270, kF0899 = 7373, kF1175 = 9633,
@@ -380,6 +515,13 @@ RXB_JFN void idct_islow(const int* zz, uint32_t* px) {
     px[2 * r + 1] = (uint32_t)range_limit(o[4]) | ((uint32_t)range_limit(o[5]) << 8) |
                     ((uint32_t)range_limit(o[6]) << 16) | ((uint32_t)range_limit(o[7]) << 24);
   }
+}
+
+RXB_JFN void idct_islow_q(const int16_t* zz, const uint16_t* quant, uint32_t* px) {
+  int deq[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) deq[k] = (int)zz[k] * (int)quant[k];
+  idct_islow(deq, px);
 }
 
 }  // namespace jpg

@@ -125,11 +125,12 @@ def pack_jpeg_buffers(buffers):
     return torch.from_numpy(blob.copy()), torch.from_numpy(offsets)
 
 
-def jpeg_decode_gray(blob, offsets, hw, select=None, out=None, check_status=True):
+def jpeg_decode_gray(blob, offsets, hw, select=None, out=None, check_status=True, parallel=True):
     """Decode single-channel baseline JPEG files on the device (cv2.imdecode(buf, -1) bit-exact).
     blob u8 [total] and offsets int64 [n_files+1] are CUDA tensors (see pack_jpeg_buffers); `select` (int64 CUDA
     tensor of file indices) decodes that subset, in that order.  Returns u8 [n,H,W] (and the int32 [n] status tensor
-    when check_status is False — checking costs a device->host sync)."""
+    when check_status is False — checking costs a device->host sync).  parallel=True gives the kernel a coefficient
+    workspace so all lanes of a file's warp decode; False uses the single-lane kernel (same result)."""
     require_gpu()
     blob = _cuda(blob, torch.uint8)
     offsets = _cuda(offsets, torch.int64)
@@ -143,7 +144,10 @@ def jpeg_decode_gray(blob, offsets, hw, select=None, out=None, check_status=True
     if out is None:
         out = torch.empty(n, H, W, dtype=torch.uint8, device=blob.device)
     status = torch.zeros(max(n, 1), dtype=torch.int32, device=blob.device)
-    check(load().rxb_jpeg_decode_gray(ptr(blob), ptr(begin), ptr(end), n, H, W, ptr(out), ptr(status), stream_ptr()))
+    ws_bytes = load().rxb_jpeg_decode_workspace_bytes(n, H, W) if parallel else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=blob.device) if ws_bytes else None
+    check(load().rxb_jpeg_decode_gray(ptr(blob), ptr(begin), ptr(end), n, H, W, ptr(out), ptr(status), ptr(ws),
+                                      ws_bytes, stream_ptr()))
     if not check_status:
         return out, status[:n]
     bad = torch.nonzero(status[:n]).flatten().tolist()

@@ -20,22 +20,25 @@ def _decode(cuda, buffers, hw, **kw):
     return out
 
 
-def test_jpeg_decode_matches_reference_golden(cuda, golden_dir):
+@pytest.mark.parametrize("parallel", [True, False])
+def test_jpeg_decode_matches_reference_golden(cuda, golden_dir, parallel):
     for buf, plane in _jpeg_golden(golden_dir):
-        got = _decode(cuda, [buf], plane.shape)
+        got = _decode(cuda, [buf], plane.shape, parallel=parallel)
         np.testing.assert_array_equal(got[0].cpu().numpy(), plane)
         np.testing.assert_array_equal(O.jpeg_decode_gray(buf), plane)
 
 
-def test_jpeg_decode_is_cv2_imdecode_over_formats(cuda):
-    """Sizes that are not multiples of 8, qualities, optimised Huffman tables, restart intervals; files of one size
-    are decoded in one launch (several warps per CTA, a partial last CTA)."""
+@pytest.mark.parametrize("parallel", [True, False])
+def test_jpeg_decode_is_cv2_imdecode_over_formats(cuda, parallel):
+    """Sizes that are not multiples of 8, qualities, optimised Huffman tables, restart intervals (which the parallel
+    kernel hands to the single-lane kernel); files of one size are decoded in one launch (several warps per CTA, a
+    partial last CTA).  parallel: all lanes decode speculative subsequences / one lane per file."""
     by_shape = {}
     for buf, ref in _jpeg_cases():
         by_shape.setdefault(ref.shape, []).append((buf, ref))
     assert sum(len(v) for v in by_shape.values()) == 135
     for hw, cases in by_shape.items():
-        got = _decode(cuda, [c[0] for c in cases], hw).cpu().numpy()
+        got = _decode(cuda, [c[0] for c in cases], hw, parallel=parallel).cpu().numpy()
         for i, (_, ref) in enumerate(cases):
             np.testing.assert_array_equal(got[i], ref)
 
@@ -55,6 +58,13 @@ def test_jpeg_decode_full_size_batch_feeds_stats_and_loader(cuda):
     got = _decode(cuda, bufs, (512, 512)).view(2, 6, 512, 512)
     ref = np.stack(refs).reshape(2, 6, 512, 512)
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    np.testing.assert_array_equal(_decode(cuda, bufs, (512, 512), parallel=False).view(2, 6, 512, 512).cpu().numpy(), ref)
+    smooth = [cv2.GaussianBlur(planes[0, c], (0, 0), 2.0) for c in range(6)]     # long zero runs, few bits per block
+    sb = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes() for im in smooth]
+    flat = cv2.imencode(".jpg", np.full((512, 512), 7, np.uint8))[1].tobytes()    # hundreds of blocks per subsequence
+    gs = _decode(cuda, sb + [flat], (512, 512)).cpu().numpy()
+    for i, b_ in enumerate(sb + [flat]):
+        np.testing.assert_array_equal(gs[i], cv2.imdecode(np.frombuffer(b_, np.uint8), -1))
     acc = ops.stats_accumulate(got, torch.zeros(2, dtype=torch.int32, device=cuda), 1)
     mean, std = ops.stats_finalize(acc)
     om, os_ = O.compute_mean_std_arrays(ref)
@@ -69,12 +79,13 @@ def test_jpeg_decode_status_codes_and_empty(cuda):
     ok, rgb = cv2.imencode(".jpg", np.zeros((32, 32, 3), np.uint8))
     ok, other = cv2.imencode(".jpg", np.zeros((16, 16), np.uint8))
     bufs = [good.tobytes(), b"not a jpeg at all....", prog.tobytes(), rgb.tobytes(), other.tobytes(),
-            good.tobytes()[:60], good.tobytes()]
-    out, status = _decode(cuda, bufs, (32, 32), check_status=False)
-    assert status.cpu().tolist() == [0, 1, 2, 2, 4, 1, 0]
+            good.tobytes()[:60], good.tobytes(), good.tobytes()[:len(good) * 3 // 4], good.tobytes()[:-4]]
     ref = cv2.imdecode(good, -1)
-    np.testing.assert_array_equal(out[0].cpu().numpy(), ref)
-    np.testing.assert_array_equal(out[6].cpu().numpy(), ref)
+    for parallel in (True, False):
+        out, status = _decode(cuda, bufs, (32, 32), check_status=False, parallel=parallel)
+        assert status.cpu().tolist() == [0, 1, 2, 2, 4, 1, 0, 5, 5]
+        np.testing.assert_array_equal(out[0].cpu().numpy(), ref)
+        np.testing.assert_array_equal(out[6].cpu().numpy(), ref)
     with pytest.raises(_lib.RxbError):
         _decode(cuda, bufs, (32, 32))
     empty = _decode(cuda, [], (32, 32))

@@ -257,6 +257,15 @@ def test_kernel_jpeg_code_compiled_for_the_host_is_cv2_imdecode(tmp_path, golden
         dst = np.zeros((H, W), np.uint8)
         st = lib.jpeg_host_decode_gray(a.ctypes.data_as(ctypes.c_void_p), len(a), H, W,
                                        dst.ctypes.data_as(ctypes.c_void_p))
+        # the speculative parallel path (warp emulated lane by lane) must agree wherever it applies
+        dst2 = np.zeros((H, W), np.uint8)
+        rounds = ctypes.c_int(0)
+        st2 = lib.jpeg_host_decode_gray_parallel(a.ctypes.data_as(ctypes.c_void_p), len(a), H, W,
+                                                 dst2.ctypes.data_as(ctypes.c_void_p), ctypes.byref(rounds))
+        if st2 == -1:                                                # restart intervals: sequential path only
+            assert b"\xff\xdd" in buf
+        else:
+            assert st2 == st and (st != 0 or np.array_equal(dst, dst2))
         return st, dst
 
     for buf, plane in _jpeg_golden(golden_dir):
@@ -275,6 +284,8 @@ def test_kernel_jpeg_code_compiled_for_the_host_is_cv2_imdecode(tmp_path, golden
     assert dec(buf.tobytes(), 256, 256)[0] == 4                      # frame size != expected
     assert dec(b"not a jpeg at all....", 8, 8)[0] == 1
     assert dec(buf.tobytes()[:300], 512, 512)[0] == 1                # headers cut short
+    assert dec(buf.tobytes()[:len(buf) // 2], 512, 512)[0] == 5      # scan cut short (both decode paths agree)
+    assert dec(buf.tobytes()[:-4], 512, 512)[0] == 5                 # ... inside the last block
     ok, pbuf = cv2.imencode(".jpg", np.zeros((16, 16), np.uint8), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
     assert dec(pbuf.tobytes(), 16, 16)[0] == 2
     ok, cbuf = cv2.imencode(".jpg", np.zeros((16, 16, 3), np.uint8))
