@@ -17,6 +17,8 @@ Parity status
   * d4_augment / normalize: restate albumentations==0.3.0 (requirement.txt:1), which is NOT installed
     and has no tests in the reference -> "parity unpinned" for that third-party boundary; the OpenCV
     calls it makes (cv2.flip, cv2.warpAffine) are executed for real here.
+  * the stem recipe and two_sites_features: PINNED against the reference's own TwoSitesNN (models.py:8-57) built in
+    the build container under a seed (tests/golden/model_golden.npz).
   * densenet121_6ch: torchvision's densenet121 with the reference's 6-channel stem recipe
     (models.py:17-27); the north star's trunk, fp32 on CPU.
 """

@@ -10,6 +10,9 @@ Fixtures written next to this file:
   assign_golden.npz  cell_classifier.test.test (reference test.py:9-58) driven by a seeded logits callable:
                      the masked+rescaled assignment for a 64-well case (inputs stored) and a full
                      1108-well experiment (inputs regenerated from the seed).
+  model_golden.npz   cell_classifier.models.TwoSitesNN (reference models.py:8-57) built with pretrained=False under a
+                     seed: the 6-channel stem it derives from the 3-channel kernel (:17-27), and its forward's
+                     site/control averaging (:41-53) run with a stub trunk and an identity head on seeded input.
   jpeg_golden.npz    the reference's own PNG->JPEG converter (png_to_jpeg.convert_png_to_jpeg, :11-15: PIL 'L', quality 95)
                      run on seeded synthetic planes, and cv2.imdecode(buf, -1) of the result — the reference's decode
                      call (cell_classifier/dataloader.py:141-146): file bytes + decoded planes.
@@ -127,6 +130,35 @@ def make_warp():
     print("warp golden:", cv2.__version__, digests[1][:16])
 
 
+def make_model():
+    import torch
+    sys.path.insert(0, REF)
+    from cell_classifier.models import TwoSitesNN
+    from torchvision import models
+    torch.manual_seed(123)
+    net = TwoSitesNN(pretrained=False, nb_classes=1108)
+    torch.manual_seed(123)
+    rgb = models.resnet50(weights=None).conv1.weight.detach().numpy()        # the kernel the surgery started from
+    stem6 = net.base_nn.conv1.weight.detach().numpy()
+
+    class Trunk(torch.nn.Module):                                            # features = per-image channel means
+        def forward(self, x):
+            return x.mean(dim=(2, 3)) * torch.arange(1, 7, dtype=x.dtype)
+
+    net.base_nn = Trunk()
+    net.mlp = torch.nn.Identity()
+    net.eval()
+    g = torch.Generator().manual_seed(5)
+    outs = {}
+    for G in (3, 6):                                                         # train/val: 3 images, test: 6 (two sites)
+        x = torch.randn(4, G, 6, 8, 8, generator=g)
+        outs["x%d" % G] = x.numpy()
+        outs["y%d" % G] = net(x).detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "model_golden.npz"), rgb_sample=rgb[:4], stem6_sample=stem6[:4],
+                        stem6_sum=np.float64(stem6.astype(np.float64).sum()), **outs)
+    print("model golden:", stem6.shape, outs["y3"].shape, outs["y6"].shape)
+
+
 def make_jpeg():
     import cv2
     cwd = os.getcwd()
@@ -156,9 +188,13 @@ def make_jpeg():
 
 
 if __name__ == "__main__":
+    if "--model-only" in sys.argv:
+        make_model()
+        sys.exit(0)
     if "--jpeg-only" in sys.argv:
         make_jpeg()
         sys.exit(0)
+    make_model()
     make_jpeg()
     make_warp()
     if "--warp-only" in sys.argv:

@@ -290,3 +290,54 @@ def test_kernel_jpeg_code_compiled_for_the_host_is_cv2_imdecode(tmp_path, golden
     assert dec(pbuf.tobytes(), 16, 16)[0] == 2
     ok, cbuf = cv2.imencode(".jpg", np.zeros((16, 16, 3), np.uint8))
     assert dec(cbuf.tobytes(), 16, 16)[0] == 2                       # three components
+
+
+# ---------------------------------------------------------------- model glue (reference models.py, M1/M2)
+def test_stem_recipe_and_site_averaging_match_reference_golden(golden_dir):
+    """The reference's own TwoSitesNN (tests/golden/make_golden.py): its 6-channel stem is the channel-mean of the
+    3-channel kernel replicated six times (models.py:17-27) — the recipe the oracle nets and DenseNet121.
+    reset_parameters use — and its forward averages sites per image / negative / positive third (:41-53)."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "model_golden.npz"))
+    rgb = torch.from_numpy(g["rgb_sample"])
+    stem = torch.stack([torch.mean(rgb, 1)] * 6, dim=1).numpy()              # the oracle's recipe
+    np.testing.assert_array_equal(stem, g["stem6_sample"])
+    net = O.densenet121_6ch(16, seed=3)
+    w = net.features.conv0.weight.detach().numpy()
+    assert w.shape == (64, 6, 7, 7)
+    for c in range(1, 6):
+        np.testing.assert_array_equal(w[:, 0], w[:, c])
+    for G in (3, 6):
+        x = torch.from_numpy(g["x%d" % G])
+        feats = (x.reshape(-1, 6, 8, 8).mean(dim=(2, 3)) * torch.arange(1, 7, dtype=x.dtype))   # the golden's stub trunk
+        np.testing.assert_array_equal(O.two_sites_features(feats, x.shape[0]).numpy(), g["y%d" % G])
+
+
+# ---------------------------------------------------------------- product host helpers (no GPU needed)
+def test_product_host_helpers_agree_with_oracle_and_opencv():
+    import cv2
+    from recursion_cellular_image_classification_b200 import ops
+    rng = np.random.default_rng(17)
+    for ang in rng.uniform(-180, 180, size=200):
+        np.testing.assert_array_equal(ops.rotation_matrix(512, 512, float(ang)),
+                                      cv2.getRotationMatrix2D((256.0, 256.0), float(ang), 1.0))
+    mean, std = rng.random((3, 6)) * 0.2 + 0.05, rng.random((3, 6)) * 0.1 + 0.05
+    m, d = ops.normalize_constants(mean, std)
+    om, od = O.normalize_constants(mean, std)
+    np.testing.assert_array_equal(m, om)
+    np.testing.assert_array_equal(d, od)
+    imgs = [rng.integers(0, 256, size=hw, dtype=np.uint8) for hw in ((40, 72), (8, 8), (512, 512))]
+    bufs = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes() for im in imgs]
+    for im, b in zip(imgs, bufs):
+        assert ops.jpeg_frame_size(b) == im.shape
+    blob, offsets = ops.pack_jpeg_buffers(bufs)
+    assert offsets.tolist() == [0] + list(np.cumsum([len(b) for b in bufs]))
+    for i, b in enumerate(bufs):
+        assert blob[offsets[i]:offsets[i + 1]].numpy().tobytes() == b
+    blob0, offsets0 = ops.pack_jpeg_buffers([])
+    assert blob0.numel() == 0 and offsets0.tolist() == [0]
+    assert [ops.aug_code(v, h, k, r) for v, h, k, r in ((1, 0, 0, 0), (0, 1, 0, 0), (0, 0, 3, 0), (1, 1, 2, 1))] == \
+        [1, 2, 12, 27]
+    from recursion_cellular_image_classification_b200 import _lib
+    with pytest.raises(_lib.RxbError):
+        ops.jpeg_frame_size(b"\xff\xd8 nothing useful here")
