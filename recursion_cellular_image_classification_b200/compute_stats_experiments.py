@@ -3,7 +3,9 @@
 `compute_mean_std(paths, mean=None, std=None)` keeps the reference signature and return value
 (compute_stats_experiments.py:8-24: two float64[6] arrays); the per-pixel reduction runs in
 rxb_stats_accumulate on the GPU (exact integer sums) instead of the Python/numpy loop at :13-20.
-JPEG decode stays on the host (cv2), like the reference (:15) — SURVEY §8f lists GPU decode as "next".
+JPEG decode stays on the host by default (cv2, like the reference :15); `decode='gpu'` moves it to the device too
+(rxb_jpeg_decode_gray, bit-identical to cv2 for the baseline grayscale files png_to_jpeg.py writes) — decode is 75 % of
+the reference function's time.
 
 Unlike the reference module, importing this file has no side effects; `python -m
 recursion_cellular_image_classification_b200.compute_stats_experiments` reproduces the script
@@ -28,17 +30,27 @@ def _channel_of(path):
     return int(os.path.basename(path).split('_')[2][1]) - 1
 
 
-def compute_mean_std(paths, mean=None, std=None, device="cuda", chunk=384):
-    import cv2
+def compute_mean_std(paths, mean=None, std=None, device="cuda", chunk=384, decode="host"):
+    if decode not in ("host", "gpu"):
+        raise ValueError("decode must be 'host' or 'gpu'")
     dev = torch.device(device)
     acc = None
     for i in range(0, len(paths), chunk):
         part = paths[i:i + chunk]
-        ims = [cv2.imread(p, cv2.IMREAD_GRAYSCALE) for p in part]
-        for p, im in zip(part, ims):
-            if im is None:
-                raise FileNotFoundError(p)
-        planes = torch.from_numpy(np.stack(ims)[:, None]).to(dev)                 # [n,1,H,W] u8
+        if decode == "gpu":
+            bufs = []
+            for p in part:
+                with open(p, "rb") as f:
+                    bufs.append(f.read())
+            blob, offsets = ops.pack_jpeg_buffers(bufs)
+            planes = ops.jpeg_decode_gray(blob.to(dev), offsets.to(dev), ops.jpeg_frame_size(bufs[0]))[:, None]
+        else:
+            import cv2
+            ims = [cv2.imread(p, cv2.IMREAD_GRAYSCALE) for p in part]
+            for p, im in zip(part, ims):
+                if im is None:
+                    raise FileNotFoundError(p)
+            planes = torch.from_numpy(np.stack(ims)[:, None]).to(dev)             # [n,1,H,W] u8
         slot = torch.tensor([_channel_of(p) for p in part], dtype=torch.int32, device=dev)
         acc = ops.stats_accumulate(planes, slot, NB_CHANNELS, acc)                # one "experiment slot" per channel
     if acc is None:
