@@ -90,3 +90,153 @@ def test_compute_mean_std_host_logic(tmp_path, fake_kernels, decode):
         cse.compute_mean_std(paths, device="cpu", decode="nvjpeg")
     m0, s0 = cse.compute_mean_std([], device="cpu", decode=decode)      # empty path list: 0/0 like the reference
     assert m0.shape == (6,)
+
+
+# ---------------------------------------------------------------- ImagesDS / test(): host logic with stand-in kernels
+def _tree(root, S=32, jpeg=False):
+    """Two experiments x one plate x (B02 negative control, C03 positive control, three sample wells) x two sites."""
+    import cv2
+    import pandas as pd
+    rows, ctrl, planes = [], [], {}
+    for ei, exp in enumerate(("HEPG2-01", "U2OS-02")):
+        for split in ("train", "test"):
+            d = root / split / exp / "Plate1"
+            d.mkdir(parents=True)
+            for wi, well in enumerate(("B02", "C03", "D04", "E05", "F06")):
+                for site in (1, 2):
+                    p = synth_planes(1000 * ei + 10 * wi + site, n=1, H=S, W=S)[0]
+                    for ch in range(6):
+                        path = str(d / ("%s_s%d_w%d.jpeg" % (well, site, ch + 1)))
+                        if jpeg:
+                            cv2.imwrite(path, p[ch], [cv2.IMWRITE_JPEG_QUALITY, 95])
+                            p[ch] = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+                        else:                                   # lossless PNG bytes under the .jpeg name
+                            open(path, "wb").write(cv2.imencode(".png", p[ch])[1].tobytes())
+                    planes[(split, exp, well, site)] = p
+        for wi, well in enumerate(("B02", "C03", "D04", "E05", "F06")):
+            rec = {"id_code": "%s_1_%s" % (exp, well), "experiment": exp, "plate": 1, "well": well, "sirna": 10 * ei + wi}
+            if well == "B02":
+                ctrl.append(dict(rec, well_type="negative_control"))
+            elif well == "C03":
+                ctrl.append(dict(rec, well_type="positive_control"))
+            else:
+                rows.append(rec)
+    return pd.DataFrame(rows), pd.DataFrame(ctrl), planes
+
+
+@pytest.fixture
+def fake_loader(monkeypatch, fake_kernels):
+    def load_norm_aug(src, src_idx, exp_id, aug, crop_yx, norm_m, norm_d, out_hw, out_format, out=None):
+        assert out_format == ops.OUT_F32_NCHW
+        outs = []
+        for b in range(src_idx.numel()):
+            c, e = int(aug[b]), int(exp_id[b])
+            img = O.d4_augment(np.moveaxis(src[int(src_idx[b])].numpy(), 0, 2), bool(c & 1), bool(c & 2), (c >> 2) & 3,
+                               bool(c & 16))
+            y0, x0 = (int(v) for v in crop_yx[b])
+            x = img[y0:y0 + out_hw[0], x0:x0 + out_hw[1]].astype(np.float32)
+            outs.append(np.moveaxis((x - norm_m[e].numpy()) * norm_d[e].numpy(), 2, 0))
+        return torch.from_numpy(np.stack(outs))
+
+    def load_norm_affine(src, src_idx, exp_id, flips, M, crop_yx, norm_m, norm_d, out_hw, out_format, out=None):
+        outs = []
+        for b in range(src_idx.numel()):
+            c, e = int(flips[b]), int(exp_id[b])
+            img = np.moveaxis(src[int(src_idx[b])].numpy(), 0, 2)
+            img = img[::-1] if c & 1 else img
+            img = img[:, ::-1] if c & 2 else img
+            y0, x0 = (int(v) for v in crop_yx[b])
+            x = O.warp_affine_u8(np.ascontiguousarray(img), M[b].numpy())[y0:y0 + out_hw[0], x0:x0 + out_hw[1]]
+            outs.append(np.moveaxis((x.astype(np.float32) - norm_m[e].numpy()) * norm_d[e].numpy(), 2, 0))
+        return torch.from_numpy(np.stack(outs))
+
+    monkeypatch.setattr(ops, "load_norm_aug", load_norm_aug)
+    monkeypatch.setattr(ops, "load_norm_affine", load_norm_affine)
+
+
+@pytest.mark.parametrize("decode", ["host", "gpu"])
+def test_images_ds_host_logic(tmp_path, fake_loader, decode):
+    """Per-experiment statistics reach the right images, the image / negative / positive thirds keep their order,
+    crops and modes follow dataloader.py:128-209 — for both decode paths and both augmentations."""
+    from recursion_cellular_image_classification_b200.cell_classifier import dataloader as dl
+    df, dfc, planes = _tree(tmp_path, jpeg=decode == "gpu")
+    stats = {"U2OS-02": {"mean": np.linspace(0.2, 0.3, 6), "std": np.linspace(0.1, 0.2, 6)},
+             "HEPG2-01": {"mean": np.linspace(0.05, 0.1, 6), "std": np.linspace(0.04, 0.08, 6)}}
+    kw = dict(verbose=False, device="cpu", decode=decode)
+
+    def expect(split, exp, well, site, **t):
+        return O.transform(planes[(split, exp, well, site)], stats[exp]["mean"], stats[exp]["std"], **t)
+
+    def is_one_of(x, cands):
+        return any(np.array_equal(x.numpy().view(np.uint32), c.view(np.uint32)) for c in cands)
+
+    val = dl.ImagesDS(df, dfc, stats, str(tmp_path), "val", crop=20, **kw)
+    assert len(val) == 6
+    for i in (0, 4):                                            # one sample of each experiment
+        x, label = val[i]
+        exp, well = df.iloc[i].experiment, df.iloc[i].well
+        assert tuple(x.shape) == (3, 6, 20, 20) and label == int(df.iloc[i].sirna)
+        t = dict(crop_yx=(6, 6), out_hw=(20, 20))
+        assert is_one_of(x[0], [expect("train", exp, well, s, **t) for s in (1, 2)])
+        assert is_one_of(x[1], [expect("train", exp, "B02", s, **t) for s in (1, 2)])
+        assert is_one_of(x[2], [expect("train", exp, "C03", s, **t) for s in (1, 2)])
+    tst = dl.ImagesDS(df, dfc, stats, str(tmp_path), "test", **kw)
+    x, idc = tst[5]
+    exp, well = df.iloc[5].experiment, df.iloc[5].well
+    assert tuple(x.shape) == (6, 6, 32, 32) and idc == df.iloc[5].id_code
+    for j, (w, s) in enumerate([(well, 1), (well, 2), ("B02", 1), ("B02", 2), ("C03", 1), ("C03", 2)]):
+        assert is_one_of(x[j], [expect("test", exp, w, s)])
+    for augment in ("d4", "rotate"):
+        trn = dl.ImagesDS(df, dfc, stats, str(tmp_path), "train", crop=20, augment=augment, **kw)
+        items = [trn.raw_item(i) for i in (1, 3, 4)]
+        batch = dl.collate_raw(items)
+        got = trn.device_batch(batch, torch.device("cpu"), out_format=ops.OUT_F32_NCHW).numpy().reshape(3, 3, 6, 20, 20)
+        first = trn.device_batch(batch, torch.device("cpu"), out_format=ops.OUT_F32_NCHW, first_only=True).numpy()
+        for bi, (i, item) in enumerate(zip((1, 3, 4), items)):
+            exp = df.iloc[i].experiment
+            src = (batch["planes"][bi].numpy() if decode == "host" else
+                   np.stack([O.jpeg_decode_gray(b) for b in item["jpeg"]]).reshape(3, 6, 32, 32))
+            for g_ in range(3):
+                c, crop = int(item["codes"][g_]), tuple(int(v) for v in item["crops"][g_])
+                if augment == "d4":
+                    ref = O.transform(src[g_], stats[exp]["mean"], stats[exp]["std"], vflip=bool(c & 1),
+                                      hflip=bool(c & 2), k=(c >> 2) & 3, crop_yx=crop, out_hw=(20, 20))
+                else:
+                    img = np.moveaxis(src[g_], 0, 2)
+                    img = img[::-1] if c & 1 else img
+                    img = img[:, ::-1] if c & 2 else img
+                    w = O.warp_affine_u8(np.ascontiguousarray(img), item["mats"][g_].numpy())
+                    w = w[crop[0]:crop[0] + 20, crop[1]:crop[1] + 20]
+                    ref = np.ascontiguousarray(np.moveaxis(O.normalize(w, stats[exp]["mean"], stats[exp]["std"]), 2, 0))
+                assert np.array_equal(got[bi, g_].view(np.uint32), ref.view(np.uint32))
+            assert np.array_equal(first[bi], got[bi, 0])
+
+
+def test_test_shim_host_logic_matches_reference_golden(golden_dir, monkeypatch):
+    """test() with stand-ins for the two kernels (oracle softmax/mask/rescale + greedy): batching, view stacking, the
+    plate / plate-group column plumbing and the float64 return type, against the reference's own output."""
+    import os
+    import pandas as pd
+    from recursion_cellular_image_classification_b200.cell_classifier import test as shim
+    g = np.load(os.path.join(golden_dir, "assign_golden.npz"))
+
+    def tta_softmax_avg_mask(logits, plate=None, group_col=None):
+        probs = np.mean([O.softmax(v) for v in logits.numpy()], axis=0).astype(np.float32)
+        return torch.from_numpy(O.mask_rescale(probs, group_col.numpy(), plate.numpy()))
+
+    monkeypatch.setattr(ops, "tta_softmax_avg_mask", tta_softmax_avg_mask)
+    monkeypatch.setattr(ops, "greedy_assign", lambda p: torch.from_numpy(O.greedy_assign(p.numpy()).astype(np.int32)))
+    logits = g["logits64"]
+    N = logits.shape[0]
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return N
+
+        def __getitem__(self, i):
+            return torch.tensor([float(i)]), "id%d" % i
+
+    res = shim.test(pd.DataFrame({"plate": g["plates64"]}), DS(), g["pg64"], int(g["et64"]),
+                    lambda x: torch.from_numpy(logits[x[:, 0].long().numpy()]), bs=16, num_workers=0, device="cpu")
+    assert res.dtype == np.float64
+    np.testing.assert_array_equal(res, g["res64"])
