@@ -44,3 +44,41 @@ def test_product_path_fails_loudly_without_gpu():
     from recursion_cellular_image_classification_b200 import ops
     with pytest.raises(_lib.RxbError):
         ops.stats_accumulate(torch.zeros(1, 6, 16, 16, dtype=torch.uint8), torch.zeros(1, dtype=torch.int32), 1)
+
+
+def test_widening_entry_points_validate_arguments(lib):
+    """rxb_jpeg_decode_gray / rxb_load_norm_affine: sizes and pointers are checked before any device work."""
+    assert lib.rxb_jpeg_decode_workspace_bytes(768, 512, 512) == 768 * 64 * 64 * 128     # 128 B per 8x8 block
+    assert lib.rxb_jpeg_decode_workspace_bytes(1, 37, 53) == 5 * 7 * 128                 # partial blocks count
+    assert lib.rxb_jpeg_decode_workspace_bytes(0, 512, 512) == 0
+    assert lib.rxb_jpeg_decode_gray(None, None, None, 0, 512, 512, None, None, None, 0, None) == 0   # empty batch
+    assert lib.rxb_jpeg_decode_gray(None, None, None, 3, 512, 512, None, None, None, 0, None) == -1
+    assert b"null" in lib.rxb_last_error()
+    assert lib.rxb_jpeg_decode_gray(None, None, None, -1, 512, 512, None, None, None, 0, None) == -1
+    buf = (ctypes.c_uint8 * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.rxb_jpeg_decode_gray(p, p, p, 1, 0, 512, p, p, None, 0, None) == -1
+    assert b"size" in lib.rxb_last_error()
+    assert lib.rxb_jpeg_decode_gray(p, p, p, 1, 512, 512, p, p, p, 16, None) == -1       # workspace too small
+    assert b"workspace" in lib.rxb_last_error()
+    assert lib.rxb_load_norm_affine(None, 1, 512, 512, None, None, None, None, None, None, None, 1, None, 0, 512, 512, 0,
+                                    None) == 0                                           # empty batch
+    assert lib.rxb_load_norm_affine(None, 1, 512, 512, None, None, None, None, None, None, None, 1, None, 2, 512, 512, 0,
+                                    None) == -1
+    assert lib.rxb_load_norm_affine(p, 1, 32, 32, p, p, p, p, p, p, p, 1, p, 1, 48, 48, 0, None) == -1   # crop > image
+    assert b"crop" in lib.rxb_last_error()
+    assert lib.rxb_load_norm_affine(p, 1, 32, 32, p, p, p, p, p, p, p, 1, p, 1, 31, 31, 2, None) == -1   # S2D32 odd
+    assert lib.rxb_load_norm_affine(p, 1, 32, 32, p, p, p, p, p, p, p, 1, p, 1, 32, 32, 7, None) == -1   # bad format
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_widening_ops_fail_loudly_without_gpu():
+    from recursion_cellular_image_classification_b200 import ops
+    blob, offsets = ops.pack_jpeg_buffers([b"\xff\xd8\xff\xd9"])
+    with pytest.raises(_lib.RxbError):
+        ops.jpeg_decode_gray(blob, offsets, (8, 8))
+    z = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(_lib.RxbError):
+        ops.load_norm_affine(torch.zeros(1, 6, 8, 8, dtype=torch.uint8), z, z, torch.zeros(1, dtype=torch.uint8),
+                             torch.zeros(1, 2, 3, dtype=torch.float64), torch.zeros(1, 2, dtype=torch.int32),
+                             torch.zeros(1, 6), torch.ones(1, 6), (8, 8), ops.OUT_F32_NCHW)
