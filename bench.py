@@ -439,6 +439,46 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    # development switch (round-2 experiment, N=1): the same step replayed from ONE CUDA graph, to measure how much of
+    # the ~10 us per-launch fixed cost is stream-launch latency.  Fixed augmentation codes (the
+    # generator is not captured); never the headline number.
+    graph_result = None
+    if args.graph and world == 1:
+        try:
+            fixed_aug = torch.randint(0, 16, (B,), device=dev, dtype=torch.uint8)
+
+            def graph_step():
+                ops.load_norm_aug(src, src_idx, exp_id, fixed_aug, crop, norm_m, norm_d, (IMG, IMG),
+                                  ops.OUT_BF16_S2D32, out=xs)
+                for ph in range(n_phases):
+                    net.train_step(xs, labels, global_batch=gB * fake_world, phase=ph, loss_out=loss_dev)
+                net.sgd_step(B, IMG, IMG, lr=lr, momentum=0.9, weight_decay=3e-5, nesterov=True)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph_step()                                             # warm-up on the capture stream
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                graph_step()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            g_ms = e0.elapsed_time(e1)
+            graph_result = {"value": gB * args.steps / (g_ms * 1e-3), "ms_per_step": g_ms / args.steps,
+                            "note": "one CUDA graph per step, fixed augmentation codes"}
+        except Exception as e:
+            graph_result = {"error": repr(e)}
+            torch.cuda.synchronize()
+
     for _ in range(2):
         step(True)
     ms_e2e = timed(True, args.steps)
@@ -538,6 +578,8 @@ def run_ours(args):
                 "hbm_kernels": hbm_kernels, "widen_kernels": widen_kernels, "kernel_breakdown": breakdown,
                 "cpu_baseline": cpu,
                 "loss": {"after_warmup": loss_first, "last": loss_last}}
+        if graph_result is not None:
+            line["cuda_graph_experiment"] = graph_result
         print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -553,6 +595,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="development: also time the step replayed from one CUDA graph (N=1; reported separately)")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): exactly --warmup + --steps steps, no e2e / breakdown / cpu baseline")
     args = ap.parse_args()
