@@ -513,6 +513,39 @@ def resnet18_6ch(num_classes=1108, seed=0):
     return net
 
 
+def two_sites_resnet50(nb_classes=1108, size_features=1024, dropout=0.3, seed=0):
+    """The reference's real model surface (models.py:8-57) restated: torchvision resnet50 trunk with the
+    6-channel stem recipe and fc -> Identity, site/control feature averaging (two_sites_features) and the
+    BatchNorm1d -> Dropout -> Linear -> ReLU -> BatchNorm1d -> Dropout -> Linear head.  Module construction order
+    follows models.py so that a seed gives the reference's initial weights."""
+    import torch
+    import torch.nn as nn
+    from torchvision import models
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.base_nn = models.resnet50(weights=None)
+            trained_kernel = self.base_nn.conv1.weight
+            new_conv = nn.Conv2d(6, 64, kernel_size=7, stride=2, padding=3, bias=False)
+            with torch.no_grad():
+                new_conv.weight[:, :] = torch.stack([torch.mean(trained_kernel, 1)] * 6, dim=1)
+            self.base_nn.conv1 = new_conv
+            n_feat = 3 * self.base_nn.fc.in_features
+            self.base_nn.fc = nn.Identity()
+            self.mlp = nn.Sequential(nn.BatchNorm1d(n_feat), nn.Dropout(dropout), nn.Linear(n_feat, size_features),
+                                     nn.ReLU(), nn.BatchNorm1d(size_features), nn.Dropout(dropout),
+                                     nn.Linear(size_features, nb_classes))
+
+        def forward(self, x):
+            bs = x.shape[0]
+            feats = self.base_nn(x.reshape([-1, x.shape[2], x.shape[3], x.shape[4]]))
+            return self.mlp(two_sites_features(feats, bs))
+
+    torch.manual_seed(seed)
+    return Net()
+
+
 def sgd_reference(params, lr, momentum=0.9, nesterov=True, weight_decay=3e-5):
     """main.py:89-93."""
     import torch

@@ -154,6 +154,14 @@ def make_model():
         x = torch.randn(4, G, 6, 8, 8, generator=g)
         outs["x%d" % G] = x.numpy()
         outs["y%d" % G] = net(x).detach().numpy()
+    # the whole reference model (ResNet-50 trunk + MLP head) in eval mode on seeded input
+    torch.manual_seed(321)
+    full = TwoSitesNN(pretrained=False, nb_classes=1108)
+    full.eval()
+    xf = torch.randn(2, 3, 6, 64, 64, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        outs["full_logits"] = full(xf).numpy()
+    outs["full_seed"] = 321
     np.savez_compressed(os.path.join(HERE, "model_golden.npz"), rgb_sample=rgb[:4], stem6_sample=stem6[:4],
                         stem6_sum=np.float64(stem6.astype(np.float64).sum()), **outs)
     print("model golden:", stem6.shape, outs["y3"].shape, outs["y6"].shape)

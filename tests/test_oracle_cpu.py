@@ -341,3 +341,16 @@ def test_product_host_helpers_agree_with_oracle_and_opencv():
     from recursion_cellular_image_classification_b200 import _lib
     with pytest.raises(_lib.RxbError):
         ops.jpeg_frame_size(b"\xff\xd8 nothing useful here")
+
+
+def test_two_sites_resnet50_oracle_matches_reference_golden(golden_dir):
+    """The oracle's restatement of the reference's real model (ResNet-50 trunk + MLP head, SURVEY §8f-3, the next
+    model row) gives the reference's own eval-mode logits for the same seed and input."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "model_golden.npz"))
+    net = O.two_sites_resnet50(seed=int(g["full_seed"]))
+    net.eval()
+    x = torch.randn(2, 3, 6, 64, 64, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        y = net(x).numpy()
+    np.testing.assert_allclose(y, g["full_logits"], rtol=1e-5, atol=1e-6)
