@@ -72,13 +72,13 @@ RXB_JFN int build_huff(const uint8_t* seg /*16 counts then the symbols*/, int av
     const int cnt = RXB_JLD(seg + l - 1);
     t->valoffset[l] = p - code;
     for (int i = 0; i < cnt; ++i, ++code, ++p) {
+      if (code >= (1 << l)) return RXB_JPG_BAD_TABLE;         // more codes than the length allows
       if (l <= kLook) {
         const int first = code << (kLook - l);
         const uint16_t e = (uint16_t)((l << 8) | t->huffval[p]);
         for (int j = 0; j < (1 << (kLook - l)); ++j) t->lut[first + j] = e;
       }
     }
-    if (code > (1 << l)) return RXB_JPG_BAD_TABLE;   // more codes than the length allows
     t->maxcode[l] = cnt ? code - 1 : -1;
     code <<= 1;
   }
@@ -269,8 +269,8 @@ RXB_JFN void br_restart(BitReader* b) {
 RXB_JFN void decode_block(BitReader* b, const HuffTable* dc, const HuffTable* ac, const uint16_t* quant, int* pred,
                           int* coef, int* err) {
   br_need32(b);
-  int s = huff_decode(b, dc, err);
-  if (s) s = receive_extend(b, s & 15);
+  int s = huff_decode(b, dc, err) & 15;                       // a DC category is at most 11 (15 for 12-bit files)
+  if (s) s = receive_extend(b, s);
   *pred += s;
   coef[0] = (int)(int16_t)*pred * (int)quant[0];
   for (int k = 1; k < 64; ++k) {
@@ -417,7 +417,7 @@ RXB_JFN void sub_decode(const uint8_t* win, SubState* st, int end_bit, const Huf
 RXB_JFN void classify4(const uint8_t* raw, int raw_len, int base, int limit, int* keep, int* marker, uint8_t* bytes) {
   *keep = 0;
   *marker = 4;
-  int prev = base > 0 ? RXB_JLD(raw + base - 1) : 0;
+  int prev = (base > 0 && base < limit) ? RXB_JLD(raw + base - 1) : 0;   // lanes past the limit read nothing
   for (int j = 0; j < 4; ++j) {
     const int i = base + j;
     if (i >= limit) break;
