@@ -93,3 +93,86 @@ def test_cosine_schedule_matches_torch():
         assert abs(opt.param_groups[0]["lr"] - cosine_lr(0.008, epoch, 20)) < 1e-12
         opt.step()
         sched.step()
+
+
+# ---------------------------------------------------------------- the statistics script sharded over ranks
+def _fake_stat_kernels():
+    """numpy stand-ins for the two statistics wrappers (the kernels are tested on the GPU)."""
+    from recursion_cellular_image_classification_b200 import ops
+
+    def stats_accumulate(imgs, exp_id, n_exp, acc=None):
+        if acc is None:
+            acc = tuple(torch.zeros(n_exp, imgs.shape[1], dtype=torch.int64) for _ in range(3))
+        x = imgs.to(torch.int64)
+        for i, e in enumerate(exp_id.tolist()):
+            acc[0][e] += x[i].sum(dim=(1, 2))
+            acc[1][e] += (x[i] ** 2).sum(dim=(1, 2))
+            acc[2][e] += imgs.shape[2] * imgs.shape[3]
+        return acc
+
+    def stats_finalize(acc, pre_mean=None, pre_std=None):
+        s, q, c = (a.double() for a in acc)
+        mean, ex2 = s / c / 255.0, q / c / 255.0 ** 2
+        if pre_mean is not None:
+            mean, ex2 = (mean - pre_mean) / pre_std, (ex2 - 2 * pre_mean * (s / c / 255.0) + pre_mean ** 2) / pre_std ** 2
+        return mean, torch.sqrt(ex2 - mean ** 2)
+
+    ops.stats_accumulate, ops.stats_finalize = stats_accumulate, stats_finalize
+
+
+def _write_corpus(root):
+    import cv2
+    from recursion_cellular_image_classification_b200.synth import synth_planes
+    for split, exps in (("train", ("HEPG2-01", "RPE-03", "U2OS-02")), ("test", ("HUVEC-17", "HEPG2-08"))):
+        for ei, exp in enumerate(exps):
+            d = os.path.join(root, "data", split, exp, "Plate1")
+            os.makedirs(d)
+            planes = synth_planes(len(exp) * 10 + ei, n=2, H=32, W=32)
+            for site in (1, 2):
+                for ch in range(6):
+                    with open(os.path.join(d, "B02_s%d_w%d.jpeg" % (site, ch + 1)), "wb") as f:
+                        f.write(cv2.imencode(".png", planes[site - 1, ch])[1].tobytes())   # lossless bytes
+
+
+def _stats_worker(rank, world, port, root, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    os.chdir(root)
+    from recursion_cellular_image_classification_b200 import compute_stats_experiments as cse
+    _fake_stat_kernels()
+    if world > 1:
+        parallel.init_from_env(backend="gloo")
+    stats = cse.main(device="cpu")
+    q.put((rank, {e: (v["mean"].tolist(), v["std"].tolist()) for e, v in stats.items()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_stats_script_sharded_over_two_ranks_equals_one_rank(tmp_path):
+    """compute_stats_experiments.main(): five experiments split 3 + 2 over two gloo ranks give the dictionary (and the
+    pickle, written by rank 0) that a single rank gives — same keys, same order, identical float64 values."""
+    import pickle
+    ctx = mp.get_context("spawn")
+    results = {}
+    for world in (1, 2):
+        root = str(tmp_path / ("w%d" % world))
+        os.makedirs(root)
+        _write_corpus(root)
+        q, port = ctx.Queue(), _free_port()
+        procs = [ctx.Process(target=_stats_worker, args=(r, world, port, root, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = dict(q.get(timeout=120) for _ in range(world))
+        for p in procs:
+            p.join(timeout=30)
+            assert p.exitcode == 0
+        assert all(got[r] == got[0] for r in range(world))          # every rank holds the full dictionary
+        with open(os.path.join(root, "stats_experiments.pickle"), "rb") as f:
+            pk = pickle.load(f)
+        assert list(pk.keys()) == list(got[0].keys()) and len(pk) == 5
+        for e in pk:
+            assert pk[e]["mean"].tolist() == got[0][e][0] and pk[e]["std"].tolist() == got[0][e][1]
+        results[world] = got[0]
+    assert results[1] == results[2]
+    assert list(results[1].keys()) == ["HEPG2-01", "RPE-03", "U2OS-02", "HEPG2-08", "HUVEC-17"]
