@@ -176,3 +176,130 @@ def test_stats_script_sharded_over_two_ranks_equals_one_rank(tmp_path):
         results[world] = got[0]
     assert results[1] == results[2]
     assert list(results[1].keys()) == ["HEPG2-01", "RPE-03", "U2OS-02", "HEPG2-08", "HUVEC-17"]
+
+
+# ---------------------------------------------------------------- train(): the multi-rank loop with a stand-in model
+class _LinearNet:
+    """Stands in for DenseNet121 behind the interface train() uses: a softmax-regression model on a flat float64
+    parameter buffer whose train_step leaves d(mean loss over the GLOBAL batch)/d(flat) in flat.grad."""
+    F, C = 6, 5
+
+    def __init__(self):
+        self.flat = torch.nn.Parameter(torch.zeros(self.F * self.C + self.C, dtype=torch.float64))
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.mom = torch.zeros_like(self.flat.data)
+        self.training = True
+        self.steps = 0
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def _wb(self):
+        return self.flat.data[:self.F * self.C].view(self.F, self.C), self.flat.data[self.F * self.C:]
+
+    def __call__(self, xs):
+        W, b = self._wb()
+        return xs.reshape(xs.shape[0], -1).double() @ W + b
+
+    def phase_grad_range(self, B, H, W, phase):
+        n, L = 5, self.flat.numel()
+        return (L * (n - 1 - phase)) // n, (L * (n - phase)) // n        # contiguous tails, last slice first
+
+    def train_step(self, xs, y, global_batch=None, phase=-1, loss_out=None):
+        if phase in (-1, 0):
+            x = xs.reshape(xs.shape[0], -1).double()
+            p = torch.softmax(self(xs), dim=1)
+            loss_out[0] = -(torch.log(p[torch.arange(len(y)), y]).sum() / global_batch)
+            p[torch.arange(len(y)), y] -= 1.0
+            p /= global_batch
+            self.flat.grad[:self.F * self.C] = (x.t() @ p).reshape(-1)
+            self.flat.grad[self.F * self.C:] = p.sum(0)
+        return loss_out
+
+    def sgd_step(self, B, H, W, lr, momentum=0.9, weight_decay=3e-5, nesterov=True, grad_scale=1.0):
+        g = self.flat.grad * grad_scale + weight_decay * self.flat.data
+        self.mom.mul_(momentum).add_(g)
+        self.flat.data.add_(g + momentum * self.mom if nesterov else self.mom, alpha=-lr)
+        self.steps += 1
+
+    def state_dict(self):
+        return {"flat": self.flat.data.clone()}
+
+
+class _FeatureDS:
+    """Stands in for ImagesDS behind the interface train() uses (raw_item / device_batch / crop)."""
+
+    def __init__(self, n, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.x = torch.randn(n, _LinearNet.F, generator=g)
+        self.y = torch.randint(0, _LinearNet.C, (n,), generator=g)
+        self.crop = None
+
+    def __len__(self):
+        return len(self.y)
+
+    def raw_item(self, i):
+        return {"planes": self.x[i][None], "codes": torch.zeros(1, dtype=torch.uint8),
+                "crops": torch.zeros(1, 2, dtype=torch.int32), "exp": 0, "out": 0, "label": int(self.y[i])}
+
+    def device_batch(self, batch, dev, out_format=None, first_only=False):
+        return batch["planes"][:, 0, :, None]                            # [B, F, 1]
+
+
+def _train_worker(rank, world, port, root, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    os.chdir(root)
+    from recursion_cellular_image_classification_b200 import ops
+    from recursion_cellular_image_classification_b200.cell_classifier import train as T
+
+    def softmax_ce(logits, target, grad_scale=None):
+        lp = torch.log_softmax(logits.double(), dim=1)
+        return -lp[torch.arange(len(target)), target], None
+
+    ops.softmax_ce = softmax_ce
+    if world > 1:
+        parallel.init_from_env(backend="gloo")
+    net = _LinearNet()
+    opt = torch.optim.SGD([net.flat], lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-5)   # main.py:89-93
+    hp = {"bs": 8, "nb_epochs": 3, "scheduler": True, "lr": 0.05, "early_stopping": False, "patience": 10,
+          "pretrained": False, "crop": 32}
+    hist = T.train("w%d" % world, _FeatureDS(8, 1), _FeatureDS(8, 1), net, opt, hp, num_workers=0, device="cpu",
+                   debug=True)
+    q.put((rank, net.flat.data.tolist(), net.steps, [h["val_loss"] for h in hist],
+           os.path.exists("models/best_model_w%d.pth" % world)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_train_loop_two_ranks_equals_one_rank(tmp_path):
+    """train() with hyperparams['bs'] as the GLOBAL batch: two gloo ranks (4 samples each, gradients all-reduced slice
+    by slice as the backward phases finish, loss pre-divided by the global batch, replicated SGD) follow exactly the
+    trajectory of one rank with the whole batch — same weights, same validation history; rank 0 saves the checkpoint
+    with DataParallel-style keys."""
+    ctx = mp.get_context("spawn")
+    out = {}
+    for world in (1, 2):
+        q, port = ctx.Queue(), _free_port()
+        procs = [ctx.Process(target=_train_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = sorted(q.get(timeout=200) for _ in range(world))
+        for p in procs:
+            p.join(timeout=30)
+            assert p.exitcode == 0
+        for r, flat, steps, vloss, saved in got:
+            assert steps == 3 and len(vloss) == 4
+            np.testing.assert_allclose(flat, got[0][1], rtol=0, atol=1e-15)      # replicas stay identical
+        assert got[0][4]
+        out[world] = got[0]
+    np.testing.assert_allclose(out[2][1], out[1][1], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(out[2][3], out[1][3], rtol=1e-12)
+    assert out[1][3][-1] < out[1][3][0]                                          # it learns (validation set = training set)
+    sd = torch.load(str(tmp_path / "models" / "best_model_w2.pth"))
+    assert all(k.startswith("module.") for k in sd)
