@@ -240,3 +240,55 @@ def test_test_shim_host_logic_matches_reference_golden(golden_dir, monkeypatch):
                     lambda x: torch.from_numpy(logits[x[:, 0].long().numpy()]), bs=16, num_workers=0, device="cpu")
     assert res.dtype == np.float64
     np.testing.assert_array_equal(res, g["res64"])
+
+
+def test_test_shim_with_dataset_and_eight_d4_views(tmp_path, fake_loader, monkeypatch):
+    """test() over an ImagesDS with tta_views=8 (BASELINE config 4: 2 sites x 8 D4 views, controls included): every
+    view re-normalises and re-augments all six images of a well, logits are averaged over the images, probabilities
+    over the views, then mask + rescale + greedy assignment — against the same computation spelled out with the oracle."""
+    from recursion_cellular_image_classification_b200.cell_classifier import dataloader as dl
+    from recursion_cellular_image_classification_b200.cell_classifier import test as shim
+    df, dfc, planes = _tree(tmp_path)
+    stats = {"U2OS-02": {"mean": np.linspace(0.2, 0.3, 6), "std": np.linspace(0.1, 0.2, 6)},
+             "HEPG2-01": {"mean": np.linspace(0.05, 0.1, 6), "std": np.linspace(0.04, 0.08, 6)}}
+    C = 8
+    proj = torch.from_numpy(np.random.default_rng(3).standard_normal((6 * 4, C)).astype(np.float32))
+
+    def fold(x):                              # [n,6,H,W] float32 -> [n,24]: channel means of the four image quadrants
+        n, c, H, W = x.shape                  # (sensitive to flips and rotations)
+        q = x.reshape(n, c, 2, H // 2, 2, W // 2).mean(dim=(3, 5))
+        return q.reshape(n, -1)
+
+    def model(x):
+        return (fold(x) @ proj) * 3.0
+
+    def tta_softmax_avg_mask(logits, plate=None, group_col=None):
+        probs = np.mean([O.softmax(v) for v in logits.numpy()], axis=0).astype(np.float32)
+        return torch.from_numpy(O.mask_rescale(probs, group_col.numpy(), plate.numpy()))
+
+    monkeypatch.setattr(ops, "tta_softmax_avg_mask", tta_softmax_avg_mask)
+    monkeypatch.setattr(ops, "greedy_assign", lambda p: torch.from_numpy(O.greedy_assign(p.numpy()).astype(np.int32)))
+    ds = dl.ImagesDS(df, dfc, stats, str(tmp_path), "test", verbose=False, device="cpu")
+    real = dl.ImagesDS.device_batch         # test() asks for the stem layout; the stand-in loader produces fp32 NCHW
+    monkeypatch.setattr(dl.ImagesDS, "device_batch",
+                        lambda self, batch, dev, out_format=None, first_only=False:
+                        real(self, batch, dev, ops.OUT_F32_NCHW, first_only))
+    pg = np.stack([np.array([1, 1, 1, 1, 2, 2, 2, 2])] * 4, axis=1)        # classes 0-3 on plate 1, 4-7 on plate 2
+    res = shim.test(df, ds, pg, 1, model, bs=4, num_workers=0, device="cpu", tta_views=8)
+    # the same thing, spelled out
+    codes = [ops.aug_code(v, False, k) for v in (False, True) for k in range(4)]
+    assert len(set(codes)) == 8
+    views = []
+    for c in codes:
+        rows = []
+        for i in range(len(df)):
+            exp, well = df.iloc[i].experiment, df.iloc[i].well
+            imgs = [planes[("test", exp, w, s)] for w in (well, "B02", "C03") for s in (1, 2)]
+            x = np.stack([O.transform(im, stats[exp]["mean"], stats[exp]["std"], vflip=bool(c & 1), hflip=bool(c & 2),
+                                      k=(c >> 2) & 3) for im in imgs])
+            rows.append(model(torch.from_numpy(x)).mean(0).numpy())
+        views.append(np.stack(rows))
+    probs = np.mean([O.softmax(v) for v in views], axis=0).astype(np.float32)
+    ref = O.greedy_assign(O.mask_rescale(probs, pg[:, 1], df.plate.values))
+    np.testing.assert_array_equal(res, ref.astype(np.float64))
+    assert set(res.astype(int)) <= {0, 1, 2, 3}                              # every well sits on plate 1
