@@ -292,3 +292,44 @@ def test_test_shim_with_dataset_and_eight_d4_views(tmp_path, fake_loader, monkey
     ref = O.greedy_assign(O.mask_rescale(probs, pg[:, 1], df.plate.values))
     np.testing.assert_array_equal(res, ref.astype(np.float64))
     assert set(res.astype(int)) <= {0, 1, 2, 3}                              # every well sits on plate 1
+
+
+def test_densenet_parameter_layout_is_torchvisions(tmp_path):
+    """The flat parameter / buffer layout of the executor (host side of DenseNet121, no GPU): names, order and shapes
+    are torchvision densenet121's (6-channel stem), the element counts are what librxb plans for, checkpoints load
+    with and without DataParallel's `module.` prefix (main.py:147), and the stem follows the reference recipe."""
+    import ctypes
+    from recursion_cellular_image_classification_b200 import _lib
+    from recursion_cellular_image_classification_b200.cell_classifier.models import DenseNet121, TwoSitesNN
+    ref = O.densenet121_6ch(1108, seed=4)
+    net = DenseNet121(1108, device="cpu", seed=1)
+    named = [(k, tuple(v.shape)) for k, v in ref.named_parameters()]
+    assert [(k, tuple(s)) for k, s in net.specs] == named
+    bufs = [(k, tuple(v.shape)) for k, v in ref.named_buffers() if not k.endswith("num_batches_tracked")]
+    assert [(k, tuple(s)) for k, s in net.buf_specs] == bufs
+    cfg = _lib.Dn121Config(8, 256, 256, 1108, 1e-5, 0.1)
+    lib = _lib.load()
+    assert lib.rxb_dn121_param_count(ctypes.byref(cfg)) == net.flat.numel() == 8098964      # SURVEY 8a-T2
+    assert lib.rxb_dn121_buffer_count(ctypes.byref(cfg)) == net.bn_buffers.numel()
+    # fresh initialisation: BatchNorm at identity, stem = one kernel replicated over the six channels (models.py:24-26)
+    w = net.view("features.conv0.weight")
+    assert all(torch.equal(w[:, 0], w[:, c]) for c in range(1, 6))
+    assert float(net.view("features.norm0.weight").min()) == 1.0 and float(net.buffer_view("features.norm0.running_var").min()) == 1.0
+    # checkpoints
+    net.load_state_dict(ref.state_dict())
+    sd = net.state_dict()
+    for k, v in ref.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            assert torch.equal(sd[k], v), k
+    net2 = TwoSitesNN(pretrained=False, nb_classes=1108, device="cpu")
+    net2.load_state_dict({"module." + k: v for k, v in sd.items()})
+    assert torch.equal(net2.flat.data, net.flat.data) and torch.equal(net2.bn_buffers, net.bn_buffers)
+    with pytest.raises(KeyError):
+        net2.load_state_dict({k: v for k, v in sd.items() if k != "classifier.bias"})
+    with pytest.raises(_lib.RxbError):
+        TwoSitesNN(pretrained=True, nb_classes=1108, device="cpu")
+    # torch.optim.SGD as main.py:89-93 builds it sees one flat parameter
+    assert [p.numel() for p in net.parameters()] == [8098964]
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.RxbError):                   # compute needs the GPU: no CPU path
+            net(torch.zeros(1, 6, 32, 32))
