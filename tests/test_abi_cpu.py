@@ -82,3 +82,18 @@ def test_widening_ops_fail_loudly_without_gpu():
         ops.load_norm_affine(torch.zeros(1, 6, 8, 8, dtype=torch.uint8), z, z, torch.zeros(1, dtype=torch.uint8),
                              torch.zeros(1, 2, 3, dtype=torch.float64), torch.zeros(1, 2, dtype=torch.int32),
                              torch.zeros(1, 6), torch.ones(1, 6), (8, 8), ops.OUT_F32_NCHW)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(lib, tmp_path):
+    """include/rxb.h compiles as C99 with -pedantic and a C program linked against librxb.so gets answers from the
+    host-side entry points (version, planning queries, argument validation)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cabi_smoke")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cabi_smoke.c"), "-o", exe, "-L", libdir, "-lrxb",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "version 100" in out and "params 8098964" in out and "jpeg_ws 402653184" in out
+    assert "rc -1: rxb_stats_accumulate: null pointer" in out
