@@ -333,3 +333,30 @@ def test_densenet_parameter_layout_is_torchvisions(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(_lib.RxbError):                   # compute needs the GPU: no CPU path
             net(torch.zeros(1, 6, 32, 32))
+
+
+def test_bench_host_helpers():
+    """bench.py's host-side pieces: the nvidia-smi sample parser behind the `clocks` key, the peaks file reader, and
+    the stdout claim (only the JSON line may reach stdout)."""
+    import importlib.util
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.samples = [["1965", "1965", "700.1", "Not Active", "Not Active", "Not Active", "Active"],
+                 ["1950", "1965", "710.0", "Not Active", "Not Active", "Not Active", "Not Active"],
+                 ["garbage"], ["1935", "1965", "690.0", "Not Active", "Not Active", "Not Active", "Not Active"]]
+    c = s.finish()
+    assert c == {"sm_mhz": 1950.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    p = bench.measured_peaks()
+    assert p["hbm_gbs"] > 1000 and p["bf16_tflops_sustained"] <= p["bf16_tflops"] * 1.001
+    # a child that writes to fd 1 from C level (like NCCL's banner) before the line: stdout must hold the line alone
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'NCCL version x\\n');"
+            "print('python print'); print(json.dumps({'ok': 1}), file=bench.OUT, flush=True)" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    assert json.loads(r.stdout) == {"ok": 1} and "NCCL version x" in r.stderr and "python print" in r.stderr
