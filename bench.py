@@ -147,8 +147,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DenseNet-121 6x512x512 train step incl. normalise+D4 loader, CPU oracle port",
-                       "batch": B},
+            "config": {"workload": "DenseNet-121 6-channel 512x512 training step: normalise+D4 loader, fwd, CE, bwd, "
+                                   "nesterov SGD (the same step as the default arm; fp32 CPU port, bounded sample)",
+                       "batch_per_gpu": B, "global_batch": B, "num_classes": NUM_CLASSES, "parallelism": "cpu",
+                       "lr": 0.0005 * B},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=OUT, flush=True)
