@@ -375,3 +375,49 @@ def test_sanitizer_fuzz_of_the_kernel_headers():
                        text=True)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
     assert "warp cases" in p.stdout and p.stdout.count("statuses") == 2
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cell_classifier"), reason="the reference tree is only in the build container")
+def test_assignment_oracle_vs_the_reference_run_live_on_edge_cases():
+    """cell_classifier.test.test of the reference itself (imported from /root/reference — build container only) against
+    the oracle on seeded edge cases: wells on a plate no class belongs to (all-zero rows: the loop then writes
+    results[0] = 0, test.py:50-53), identical wells (exact ties), more wells on a plate than it has classes, one well."""
+    import sys
+    import pandas as pd
+    import torch
+    sys.path.insert(0, "/root/reference")
+    try:
+        from cell_classifier.test import test as ref_test
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.default_rng(21)
+    for case in range(24):
+        N = int(rng.choice([1, 2, 7, 19, 40]))
+        logits = (rng.standard_normal((N, 1108)) * rng.choice([0.5, 3.0, 9.0])).astype(np.float32)
+        pg = synth_plate_groups(100 + case)
+        plates = rng.integers(1, 5, size=N)
+        kind = case % 4
+        if kind == 1 and N > 2:
+            plates[rng.integers(N)] = 7                                   # a plate without classes
+            logits[1] = logits[0]                                         # two identical wells
+            plates[1] = plates[0]
+        elif kind == 2:
+            pg[:, :] = 2                                                  # every class on plate 2 ...
+            pg[:3, :] = 1                                                 # ... except three: plate 1 has 3 classes
+            plates[:] = 1                                                 # and N wells
+        elif kind == 3:
+            logits[:] = 0.0                                               # uniform probabilities everywhere
+        et = int(rng.integers(4))
+
+        class DS(torch.utils.data.Dataset):
+            def __len__(self):
+                return N
+
+            def __getitem__(self, i):
+                return torch.tensor([float(i)]), "id%d" % i
+
+        ref = ref_test(pd.DataFrame({"plate": plates}), DS(), pg, et,
+                       lambda x: torch.from_numpy(logits[x[:, 0].long().numpy()]), bs=16, num_workers=0, device="cpu")
+        probs = torch.softmax(torch.from_numpy(logits), 1).numpy()
+        mine = O.greedy_assign(O.mask_rescale(probs, pg[:, et], plates))
+        np.testing.assert_array_equal(mine, ref)
