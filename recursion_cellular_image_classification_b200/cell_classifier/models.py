@@ -66,8 +66,10 @@ def to_s2d32(x_nchw):
 
 
 class DenseNet121(torch.nn.Module):
-    def __init__(self, nb_classes=1108, device="cuda", bn_eps=1e-5, bn_momentum=0.1, seed=None):
+    def __init__(self, nb_classes=1108, device=None, bn_eps=1e-5, bn_momentum=0.1, seed=None):
         super().__init__()
+        if device is None:       # buffers live where compute will run; without a GPU only the host-side surface works
+            device = "cuda" if torch.cuda.is_available() else "cpu"
         self.nb_classes = nb_classes
         self.bn_eps, self.bn_momentum = bn_eps, bn_momentum
         self.specs, self.buf_specs = densenet121_param_specs(nb_classes)
@@ -133,29 +135,42 @@ class DenseNet121(torch.nn.Module):
                 self.buffer_view(name).fill_(1.0 if name.endswith("running_var") else 0.0)
         self._weights_dirty = True
 
-    def state_dict(self, *args, **kwargs):
-        sd = OrderedDict()
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """torchvision densenet121 names (clones of the flat buffers' views).  Honours nn.Module's destination / prefix
+        arguments, so a wrapper's state_dict() (torch.nn.DataParallel, main.py:94 and train.py:96) yields
+        `module.`-prefixed keys like the reference's checkpoints."""
+        if args:                                                     # legacy positional form
+            destination, prefix, keep_vars = (list(args) + [prefix, keep_vars])[:3] if len(args) < 3 else args[:3]
+        sd = OrderedDict() if destination is None else destination
         for name in self._views:
-            sd[name] = self.view(name).clone()
+            sd[prefix + name] = self.view(name).clone()
         for name in self._bviews:
-            sd[name] = self.buffer_view(name).clone()
+            sd[prefix + name] = self.buffer_view(name).clone()
         return sd
 
-    def load_state_dict(self, sd, strict=True):
+    def _copy_from(self, sd, prefix, strict, missing):
         with torch.no_grad():
-            for name in self._views:
-                key = name if name in sd else "module." + name   # DataParallel-prefixed checkpoints (train.py:96)
-                if key in sd:
-                    self.view(name).copy_(sd[key])
-                elif strict:
-                    raise KeyError(name)
-            for name in self._bviews:
-                key = name if name in sd else "module." + name
-                if key in sd:
-                    self.buffer_view(name).copy_(sd[key])
-                elif strict:
-                    raise KeyError(name)
+            for table, getter in ((self._views, self.view), (self._bviews, self.buffer_view)):
+                for name in table:
+                    key = prefix + name
+                    if key not in sd and not prefix and "module." + name in sd:
+                        key = "module." + name                       # DataParallel-prefixed checkpoint (train.py:96)
+                    if key in sd:
+                        getter(name).copy_(sd[key])
+                    elif strict:
+                        missing.append(key)
         self._weights_dirty = True
+
+    def load_state_dict(self, sd, strict=True):
+        missing = []
+        self._copy_from(sd, "", strict, missing)
+        if missing:
+            raise KeyError(missing[0])
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # reached when a WRAPPER loads (main.py:147: DataParallel(model).load_state_dict(torch.load(...))): the keys
+        # carry the wrapper's prefix and the torchvision names, not this module's flat buffers
+        self._copy_from(state_dict, prefix, strict, missing_keys)
 
     # ---------------------------------------------------------------- plans
     def _plan(self, B, H, W, training):
@@ -246,7 +261,7 @@ class DenseNet121(torch.nn.Module):
 class TwoSitesNN(DenseNet121):
     """Reference constructor signature (models.py:8-12); DenseNet-121 trunk per the north star."""
 
-    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device="cuda"):
+    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None):
         if pretrained:
             raise _lib.RxbError("pretrained ImageNet weights need network access; load a state_dict instead")
         super().__init__(nb_classes=nb_classes, device=device)
