@@ -69,7 +69,8 @@ class DenseNet121(torch.nn.Module):
     def __init__(self, nb_classes=1108, device=None, bn_eps=1e-5, bn_momentum=0.1, seed=None):
         super().__init__()
         if device is None:       # buffers live where compute will run; without a GPU only the host-side surface works
-            device = "cuda" if torch.cuda.is_available() else "cpu"
+            from ..parallel import default_device
+            device = default_device()
         self.nb_classes = nb_classes
         self.bn_eps, self.bn_momentum = bn_eps, bn_momentum
         self.specs, self.buf_specs = densenet121_param_specs(nb_classes)

@@ -15,6 +15,8 @@ from .dataloader import ImagesDS, RawView, collate_raw
 
 
 def _model_logits(model, ds, batch, dev, code):
+    if isinstance(model, torch.nn.DataParallel):      # main.py:94 wraps the model; one process drives one GPU here
+        model = model.module
     if isinstance(ds, ImagesDS):
         b = dict(batch)
         b["codes"] = torch.full_like(batch["codes"], code)

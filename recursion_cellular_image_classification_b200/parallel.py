@@ -27,6 +27,19 @@ def init_from_env(backend=None):
     return rank, local_rank, world
 
 
+def default_device():
+    """Where a model built without an explicit device lives: the rank's own GPU under torchrun (also made the current
+    device, so that main.py's `model.to('cuda')` and `device = 'cuda'` mean that GPU on every rank), plain "cuda" in a
+    single process, "cpu" when there is no GPU (host-side surface only: compute still fails loudly)."""
+    if not torch.cuda.is_available():
+        return "cpu"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        return "cuda:%d" % local_rank
+    return "cuda"
+
+
 def world_size():
     return dist.get_world_size() if dist.is_initialized() else 1
 

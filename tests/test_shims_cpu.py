@@ -360,3 +360,51 @@ def test_bench_host_helpers():
             "print('python print'); print(json.dumps({'ok': 1}), file=bench.OUT, flush=True)" % root)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
     assert json.loads(r.stdout) == {"ok": 1} and "NCCL version x" in r.stderr and "python print" in r.stderr
+
+
+def test_test_shim_unwraps_dataparallel_and_default_device(monkeypatch, golden_dir):
+    """main.py:94 hands test() a torch.nn.DataParallel wrapper: the shim calls the wrapped module itself (one process
+    drives one GPU; the wrapper's scatter/replicate must not run).  Models built without a device follow the rank."""
+    import os
+    import pandas as pd
+    from recursion_cellular_image_classification_b200 import parallel
+    from recursion_cellular_image_classification_b200.cell_classifier import test as shim
+    g = np.load(os.path.join(golden_dir, "assign_golden.npz"))
+    logits = torch.from_numpy(g["logits64"])
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.calls = 0
+
+        def forward(self, x):
+            self.calls += 1
+            return logits[x[:, 0].long()]
+
+    def tta_softmax_avg_mask(lg, plate=None, group_col=None):
+        probs = np.mean([O.softmax(v) for v in lg.numpy()], axis=0).astype(np.float32)
+        return torch.from_numpy(O.mask_rescale(probs, group_col.numpy(), plate.numpy()))
+
+    monkeypatch.setattr(ops, "tta_softmax_avg_mask", tta_softmax_avg_mask)
+    monkeypatch.setattr(ops, "greedy_assign", lambda p: torch.from_numpy(O.greedy_assign(p.numpy()).astype(np.int32)))
+    net = Net()
+    wrapper = torch.nn.DataParallel(net)
+    monkeypatch.setattr(wrapper, "forward", lambda *a, **k: (_ for _ in ()).throw(AssertionError("wrapper forward used")))
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 64
+
+        def __getitem__(self, i):
+            return torch.tensor([float(i)]), "id%d" % i
+
+    res = shim.test(pd.DataFrame({"plate": g["plates64"]}), DS(), g["pg64"], int(g["et64"]), wrapper, bs=16, num_workers=0,
+                    device="cpu")
+    np.testing.assert_array_equal(res, g["res64"])
+    assert net.calls == 4
+    if not torch.cuda.is_available():
+        assert parallel.default_device() == "cpu"
+        monkeypatch.setenv("WORLD_SIZE", "4")
+        monkeypatch.setenv("LOCAL_RANK", "3")
+        assert parallel.default_device() == "cpu"            # no GPU: the host-side surface only
