@@ -157,7 +157,13 @@ class DenseNet121(torch.nn.Module):
                     if key not in sd and not prefix and "module." + name in sd:
                         key = "module." + name                       # DataParallel-prefixed checkpoint (train.py:96)
                     if key in sd:
-                        getter(name).copy_(sd[key])
+                        v = sd[key]
+                        if name == "features.conv0.weight" and v.dim() == 4 and v.shape[1] == 3:
+                            # a stock 3-channel (ImageNet) stem: the reference's surgery, models.py:24-26
+                            v = torch.stack([torch.mean(v, 1)] * 6, dim=1)
+                        if name.startswith("classifier.") and tuple(v.shape) != tuple(getter(name).shape) and not strict:
+                            continue                                 # another label set (ImageNet's 1000): keep our head
+                        getter(name).copy_(v)
                     elif strict:
                         missing.append(key)
         self._weights_dirty = True
@@ -250,8 +256,21 @@ class DenseNet121(torch.nn.Module):
         check(load().rxb_dn121_phase_grad_range(plan["handle"], phase, ctypes.byref(b), ctypes.byref(e)))
         return b.value, e.value
 
-    def sgd_step(self, B, H, W, lr, momentum=0.9, weight_decay=3e-5, nesterov=True, grad_scale=1.0):
-        """torch.optim.SGD semantics (main.py:89-93) on the flat buffers, then refresh the bf16 operands."""
+    def head_range(self):
+        """[begin, end) of the classifier (the last two tensors) in the flat buffers — the part that stays trainable
+        while a pretrained trunk is frozen (train.py:46-58: children named 'mlp' or 'classifier')."""
+        off, _, _ = self._views["classifier.weight"]
+        return off, self.flat.numel()
+
+    def sgd_step(self, B, H, W, lr, momentum=0.9, weight_decay=3e-5, nesterov=True, grad_scale=1.0, head_only=False):
+        """torch.optim.SGD semantics (main.py:89-93) on the flat buffers, then refresh the bf16 operands.
+        head_only: update the classifier alone, as if every other parameter had requires_grad=False."""
+        if head_only:
+            b, e = self.head_range()
+            ops.sgd_step_(self.flat.data[b:e], self.flat.grad[b:e], self.momentum_buf[b:e], lr, momentum, weight_decay,
+                          nesterov, grad_scale)
+            self._weights_dirty = True
+            return
         plan = self._plan(B, H, W, True)
         check(load().rxb_dn121_sgd(plan["handle"], lr, momentum, weight_decay, 1 if nesterov else 0, grad_scale,
                                    stream_ptr()))

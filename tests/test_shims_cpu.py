@@ -408,3 +408,52 @@ def test_test_shim_unwraps_dataparallel_and_default_device(monkeypatch, golden_d
         monkeypatch.setenv("WORLD_SIZE", "4")
         monkeypatch.setenv("LOCAL_RANK", "3")
         assert parallel.default_device() == "cpu"            # no GPU: the host-side surface only
+
+
+def test_pretrained_runs_freeze_everything_but_the_head_for_two_epochs(tmp_path, monkeypatch):
+    """train.py:46-67: with hyperparams['pretrained'] only the head ('mlp' / 'classifier' children) learns during
+    epochs 1-2, everything from epoch 3.  The loop asks the model for head-only updates accordingly; a stock 3-channel
+    torchvision checkpoint (what `pretrained=True` would download) loads through the reference's stem surgery."""
+    from test_parallel_cpu import _FeatureDS, _LinearNet
+    from recursion_cellular_image_classification_b200.cell_classifier import train as T
+    from recursion_cellular_image_classification_b200.cell_classifier.models import DenseNet121
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+
+    def softmax_ce(logits, target, grad_scale=None):
+        lp = torch.log_softmax(logits.double(), dim=1)
+        return -lp[torch.arange(len(target)), target], None
+
+    monkeypatch.setattr(ops, "softmax_ce", softmax_ce)
+
+    class Net(_LinearNet):
+        def __init__(self):
+            super().__init__()
+            self.flags = []
+
+        def sgd_step(self, B, H, W, lr, head_only=False, **kw):
+            self.flags.append(head_only)
+            super().sgd_step(B, H, W, lr, **kw)
+
+    for pretrained, expect in ((True, [True, True, False, False]), (False, [False] * 4)):
+        net = Net()
+        opt = torch.optim.SGD([net.flat], lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-5)
+        hp = {"bs": 8, "nb_epochs": 4, "scheduler": True, "lr": 0.05, "early_stopping": False, "patience": 10,
+              "pretrained": pretrained}
+        T.train("fz", _FeatureDS(8, 1), _FeatureDS(8, 1), net, opt, hp, num_workers=0, device="cpu", debug=True)
+        assert net.flags == expect
+    # the head of the real model is the tail of its flat buffer; an ImageNet-shaped checkpoint loads non-strictly
+    from torchvision import models as tvm
+    torch.manual_seed(0)
+    tv = tvm.densenet121(weights=None)
+    net = DenseNet121(1108, device="cpu")
+    head = net.view("classifier.weight").clone()
+    with pytest.raises(RuntimeError):
+        net.load_state_dict(tv.state_dict())                           # 1000-class head, strict
+    net.load_state_dict(tv.state_dict(), strict=False)
+    assert torch.equal(net.view("features.conv0.weight"),
+                       torch.stack([tv.features.conv0.weight.detach().mean(1)] * 6, dim=1))      # models.py:24-26
+    assert torch.equal(net.view("classifier.weight"), head)
+    b, e = net.head_range()
+    assert e == net.flat.numel() and e - b == 1024 * 1108 + 1108
+    assert net.flat.data[b:b + 5].tolist() == net.view("classifier.weight").reshape(-1)[:5].tolist()
