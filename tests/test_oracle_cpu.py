@@ -421,3 +421,35 @@ def test_assignment_oracle_vs_the_reference_run_live_on_edge_cases():
         probs = torch.softmax(torch.from_numpy(logits), 1).numpy()
         mine = O.greedy_assign(O.mask_rescale(probs, pg[:, et], plates))
         np.testing.assert_array_equal(mine, ref)
+
+
+@pytest.mark.timeout(300)
+def test_baseline_config0_runs_on_the_oracle():
+    """BASELINE config 0, the reference's own CPU-runnable case, end to end on the oracle: per-experiment statistics
+    and normalisation of a batch of 8 synthetic 6x256x256 images (two experiments), then a ResNet-18-style 6-channel
+    network (reference stem recipe) forward / CrossEntropy / backward / nesterov SGD, 1108 classes."""
+    import torch
+    torch.manual_seed(0)
+    exp_of = [0, 0, 0, 0, 1, 1, 1, 1]
+    planes = np.concatenate([synth_planes(11, n=4, H=256, W=256), synth_planes(12, n=4, H=256, W=256)])
+    stats = [O.compute_mean_std_arrays(planes[:4]), O.compute_mean_std_arrays(planes[4:])]
+    assert abs(stats[0][0][0] - stats[1][0][0]) > 1e-3                    # the experiments differ (scale factor)
+    x = np.stack([O.transform(planes[i], *stats[exp_of[i]]) for i in range(8)])
+    for e in (0, 1):                                                      # normalised: zero mean, unit std per channel
+        sel = x[[i for i in range(8) if exp_of[i] == e]]
+        np.testing.assert_allclose(sel.mean(axis=(0, 2, 3)), 0, atol=2e-5)
+        np.testing.assert_allclose(sel.std(axis=(0, 2, 3)), 1, rtol=1e-4)
+    net = O.resnet18_6ch(1108, seed=0)
+    net.train()
+    opt = O.sgd_reference(net.parameters(), lr=0.0005 * 8)                # main.py:71
+    y = torch.arange(8) * 137 % 1108
+    xt = torch.from_numpy(x)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = torch.nn.CrossEntropyLoss()(net(xt), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert tuple(net.conv1.weight.shape) == (64, 6, 7, 7)
