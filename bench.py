@@ -561,6 +561,43 @@ def run_ours(args):
                                                      norm_d)
             except Exception as e:       # the widening rows never take the headline line down
                 widen_kernels = {"error": repr(e)}
+            # the same step fed with JPEG FILES from pinned host memory (ImagesDS(decode='gpu')): H2D of the compressed
+            # bytes, device decode, loader, forward/backward, SGD, loss read back — on the two synthetic corpora
+            try:
+                import cv2
+                from recursion_cellular_image_classification_b200.synth import synth_planes
+                base = synth_planes(6, n=2)
+                fixed_codes = torch.randint(0, 16, (B,), device=dev, dtype=torch.uint8)
+                planes_dev = torch.empty(B * 6, IMG, IMG, dtype=torch.uint8, device=dev)
+                e2e_jpeg = {}
+                for cname, imgs in (("dense_noise", [base[i, c] for i in range(2) for c in range(6)]),
+                                    ("smooth", [cv2.GaussianBlur(base[i, c], (0, 0), 2.0) for i in range(2) for c in range(6)])):
+                    files = [cv2.imencode(".jpg", im, [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes() for im in imgs]
+                    blob, offs = ops.pack_jpeg_buffers((files * ((B * 6 + 11) // 12))[:B * 6])
+                    h_blob, h_offs = blob.pin_memory(), offs.pin_memory()
+                    d_blob, d_offs = torch.empty_like(blob, device=dev), torch.empty_like(offs, device=dev)
+
+                    def jpeg_step():
+                        d_blob.copy_(h_blob, non_blocking=True)
+                        d_offs.copy_(h_offs, non_blocking=True)
+                        ops.jpeg_decode_gray(d_blob, d_offs, (IMG, IMG), out=planes_dev, check_status=False)
+                        ops.load_norm_aug(planes_dev.view(B, 6, IMG, IMG), src_idx, exp_id, fixed_codes, crop, norm_m,
+                                          norm_d, (IMG, IMG), ops.OUT_BF16_S2D32, out=xs)
+                        for ph in range(n_phases):
+                            net.train_step(xs, labels, global_batch=gB * fake_world, phase=ph, loss_out=loss_dev)
+                        net.sgd_step(B, IMG, IMG, lr=lr, momentum=0.9, weight_decay=3e-5, nesterov=True)
+                        host_loss.copy_(loss_dev, non_blocking=True)
+
+                    t = time_kernel(jpeg_step, reps=max(args.steps, 3))
+                    e2e_jpeg[cname] = {"value": B / (t * 1e-3), "unit": UNIT, "ms_per_step": t,
+                                       "h2d_bytes_per_step": int(blob.numel() + 8 * offs.numel()), "d2h_bytes_per_step": 4,
+                                       "files_per_step": B * 6}
+                    del d_blob, d_offs
+                widen_kernels["e2e_from_jpeg_files"] = e2e_jpeg
+                del planes_dev
+            except Exception as e:
+                if isinstance(widen_kernels, dict):
+                    widen_kernels["e2e_from_jpeg_files"] = {"error": repr(e)}
 
     if rank == 0:
         cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
