@@ -6,7 +6,8 @@ an evaluation before the first epoch and after every epoch with Loss and Accurac
 validation accuracy's state_dict saved to models/best_model_<id>.pth with DataParallel's `module.` key prefix
 (:88-96, main.py:147), cosine annealing per epoch with eta_min = lr/100 (:104-112) and optional early stopping
 (:74-80), and with hyperparams['pretrained'] the two-epoch freeze of everything but the head (:46-67).
-TensorBoard/progress-bar handlers (:114-139) are out of scope.
+TensorBoard scalars go to board/<id> with the reference's tags (:114-135); gradient histograms and the progress bar
+(:69-70,136-138) are not reproduced.
 
 The step itself runs natively: workers decode JPEGs, the u8 batch goes to the GPU, the fused loader normalises
 and augments it into the stem conv's layout, the DenseNet-121 executor does forward / loss / backward, gradients
@@ -71,6 +72,16 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     loader = torch.utils.data.DataLoader(RawView(ds_train), batch_size=bs, shuffle=sampler is None, sampler=sampler,
                                          num_workers=num_workers, collate_fn=collate_raw, drop_last=world > 1)
     net.train()
+    # TensorBoard scalars under board/<id> like train.py:114-138 (tags 'training/loss' and 'lr/group_0' per iteration,
+    # 'validation/accuracy' and 'validation/loss' per epoch); gradient histograms (:136-138) are not written.
+    writer = None
+    if rank == 0 and hyperparams.get('tensorboard', True):
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter('board/' + experiment_id)
+        except Exception:                                                     # logging is optional, compute is not
+            writer = None
+    iteration = 0
     best_acc, best_epoch, history = -1.0, 0, []
     loss_dev = torch.zeros(1, device=dev)
     n_phases = None
@@ -79,6 +90,9 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
         nonlocal best_acc, best_epoch
         acc, loss = evaluate(model, ds_val, bs, num_workers, device)
         history.append({"epoch": epoch, "val_acc": acc, "val_loss": loss})
+        if writer is not None:
+            writer.add_scalar('validation/accuracy', acc, epoch)
+            writer.add_scalar('validation/loss', loss, epoch)
         if rank == 0:
             print("Validation Results - Epoch: {}  Average accuracy: {:.4f} Average loss: {:.4f}".format(epoch, acc, loss))
         if acc > best_acc:                                                    # train.py:88-96
@@ -98,6 +112,8 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
             print('classifier is unfrozen' if epoch == 1 else 'Turn on all the layers')
         if sampler is not None:
             sampler.set_epoch(epoch)
+        loss_hist = torch.zeros(max(len(loader), 1), device=dev)             # per-iteration losses, read back once per epoch
+        n_it = 0
         for batch in loader:
             xs = ds_train.device_batch(batch, dev, first_only=True)
             y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
@@ -112,7 +128,18 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
                 ar.after_phase(p)
             ar.wait()
             net.sgd_step(B, H, W, lr=lr, momentum=momentum, weight_decay=wd, nesterov=nesterov, **frozen)
+            loss_hist[n_it:n_it + 1].copy_(loss_dev.to(loss_hist.dtype))
+            n_it += 1
+        if world > 1:
+            torch.distributed.all_reduce(loss_hist)                           # the ranks' shares add up to the batch mean
+        if writer is not None:
+            for i, v in enumerate(loss_hist[:n_it].tolist()):
+                writer.add_scalar('training/loss', v, iteration + i + 1)
+                writer.add_scalar('lr/group_0', lr, iteration + i + 1)
+        iteration += n_it
         validate(epoch)
         if hyperparams.get('early_stopping', False) and epoch - best_epoch >= hyperparams.get('patience', 10):
             break
+    if writer is not None:
+        writer.close()
     return history

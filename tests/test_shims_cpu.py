@@ -457,3 +457,35 @@ def test_pretrained_runs_freeze_everything_but_the_head_for_two_epochs(tmp_path,
     b, e = net.head_range()
     assert e == net.flat.numel() and e - b == 1024 * 1108 + 1108
     assert net.flat.data[b:b + 5].tolist() == net.view("classifier.weight").reshape(-1)[:5].tolist()
+
+
+def test_train_writes_the_references_tensorboard_scalars(tmp_path, monkeypatch):
+    """board/<id> holds 'training/loss' and 'lr/group_0' per iteration and 'validation/accuracy' / 'validation/loss'
+    per epoch (train.py:114-135), with the cosine learning rate of each epoch."""
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from test_parallel_cpu import _FeatureDS, _LinearNet
+    from recursion_cellular_image_classification_b200.cell_classifier import train as T
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+
+    def softmax_ce(logits, target, grad_scale=None):
+        lp = torch.log_softmax(logits.double(), dim=1)
+        return -lp[torch.arange(len(target)), target], None
+
+    monkeypatch.setattr(ops, "softmax_ce", softmax_ce)
+    net = _LinearNet()
+    opt = torch.optim.SGD([net.flat], lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-5)
+    hp = {"bs": 4, "nb_epochs": 3, "scheduler": True, "lr": 0.05, "early_stopping": False, "patience": 10,
+          "pretrained": False}
+    hist = T.train("tb", _FeatureDS(8, 1), _FeatureDS(8, 1), net, opt, hp, num_workers=0, device="cpu", debug=True)
+    acc = EventAccumulator(str(tmp_path / "board" / "tb"))
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    assert tags == {"training/loss", "lr/group_0", "validation/accuracy", "validation/loss"}
+    tl = acc.Scalars("training/loss")
+    assert [e.step for e in tl] == [1, 2, 3, 4, 5, 6] and tl[-1].value < tl[0].value          # 2 iterations x 3 epochs
+    lrs = [e.value for e in acc.Scalars("lr/group_0")]
+    np.testing.assert_allclose(lrs, [T.cosine_lr(0.05, e, 3) for e in (0, 0, 1, 1, 2, 2)], rtol=1e-6)
+    vl = acc.Scalars("validation/loss")
+    assert [e.step for e in vl] == [0, 1, 2, 3]
+    np.testing.assert_allclose([e.value for e in vl], [h["val_loss"] for h in hist], rtol=1e-6)
