@@ -489,3 +489,31 @@ def test_train_writes_the_references_tensorboard_scalars(tmp_path, monkeypatch):
     vl = acc.Scalars("validation/loss")
     assert [e.step for e in vl] == [0, 1, 2, 3]
     np.testing.assert_allclose([e.value for e in vl], [h["val_loss"] for h in hist], rtol=1e-6)
+
+
+def test_train_early_stopping_and_best_checkpoint(tmp_path, monkeypatch):
+    """train.py:74-80,88-96: with early_stopping the run ends `patience` epochs after the last improvement of the
+    validation accuracy; the checkpoint on disk is the best epoch's, not the last one's."""
+    from test_parallel_cpu import _FeatureDS, _LinearNet
+    from recursion_cellular_image_classification_b200.cell_classifier import train as T
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    accs = iter([0.10, 0.30, 0.20, 0.25, 0.30, 0.90, 0.95])           # epochs 0..: best at epoch 1, then no improvement
+    monkeypatch.setattr(T, "evaluate", lambda model, ds, bs, nw, dev: (next(accs), 1.0))
+    net = _LinearNet()
+    snapshots = []
+    real_step = net.sgd_step
+
+    def sgd_step(*a, **k):
+        real_step(*a, **k)
+        snapshots.append(net.flat.data.clone())
+
+    net.sgd_step = sgd_step
+    opt = torch.optim.SGD([net.flat], lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-5)
+    hp = {"bs": 8, "nb_epochs": 10, "scheduler": False, "lr": 0.05, "early_stopping": True, "patience": 3,
+          "pretrained": False, "tensorboard": False}
+    hist = T.train("es", _FeatureDS(8, 1), _FeatureDS(8, 1), net, opt, hp, num_workers=0, device="cpu", debug=True)
+    assert [h["epoch"] for h in hist] == [0, 1, 2, 3, 4]              # stopped 3 epochs after the best (epoch 1)
+    assert not (tmp_path / "board").exists()
+    sd = torch.load("models/best_model_es.pth")
+    assert torch.equal(sd["module.flat"], snapshots[0])               # weights as they were after epoch 1
