@@ -89,6 +89,12 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     def validate(epoch):
         nonlocal best_acc, best_epoch
         acc, loss = evaluate(model, ds_val, bs, num_workers, device)
+        if world > 1:
+            # every rank evaluates, but validation items draw a random site per image (dataloader.py:159-173), so the
+            # ranks' numbers differ slightly: rank 0's decide (best checkpoint, early stopping) for everybody
+            m = torch.tensor([acc, loss], dtype=torch.float64, device=dev)
+            torch.distributed.broadcast(m, src=0)
+            acc, loss = float(m[0]), float(m[1])
         history.append({"epoch": epoch, "val_acc": acc, "val_loss": loss})
         if writer is not None:
             writer.add_scalar('validation/accuracy', acc, epoch)

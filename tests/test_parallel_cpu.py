@@ -303,3 +303,38 @@ def test_train_loop_two_ranks_equals_one_rank(tmp_path):
     assert out[1][3][-1] < out[1][3][0]                                          # it learns (validation set = training set)
     sd = torch.load(str(tmp_path / "models" / "best_model_w2.pth"))
     assert all(k.startswith("module.") for k in sd)
+
+
+def _early_stop_worker(rank, world, port, root, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    os.chdir(root)
+    from recursion_cellular_image_classification_b200.cell_classifier import train as T
+    parallel.init_from_env(backend="gloo")
+    # validation items draw random sites, so ranks measure slightly different accuracies: here rank 1 keeps "improving"
+    accs = iter([0.10, 0.30, 0.20, 0.25, 0.30, 0.9, 0.95] if rank == 0 else [0.10, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7])
+    T.evaluate = lambda model, ds, bs, nw, dev: (next(accs), 1.0 + rank)
+    net = _LinearNet()
+    opt = torch.optim.SGD([net.flat], lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-5)
+    hp = {"bs": 8, "nb_epochs": 10, "scheduler": False, "lr": 0.05, "early_stopping": True, "patience": 3,
+          "pretrained": False, "tensorboard": False}
+    hist = T.train("es2", _FeatureDS(8, 1), _FeatureDS(8, 1), net, opt, hp, num_workers=0, device="cpu", debug=True)
+    q.put((rank, [(h["epoch"], h["val_acc"], h["val_loss"]) for h in hist], net.steps))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_ranks_take_the_same_early_stopping_decision(tmp_path):
+    """Rank 0's validation numbers decide for every rank: without that, a rank whose own accuracy kept improving would
+    carry on into an all-reduce its peers never enter."""
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_early_stop_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=200) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] and [e for e, _, _ in got[0][1]] == [0, 1, 2, 3, 4]
+    assert got[0][2] == got[1][2] == 4 and got[0][1][1][1:] == (0.30, 1.0)
