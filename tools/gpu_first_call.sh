@@ -22,3 +22,8 @@ timeout 60 python tools/corpus_sweep.py --experiments 5 > "$out/corpus_sweep.jso
 # ncu: the all-lanes JPEG kernel (round 1 captured only the affine loader)
 timeout 60 ncu --set full --clock-control none --import-source on -k regex:jpeg_decode_par_kernel -s 2 -c 1 \
   -o "$out/prof_jpeg_par" python tools/widen_check.py --no-tests > "$out/ncu_jpeg.json" 2> "$out/ncu_jpeg.log"; echo "ncu rc=$?"
+# train() itself on two ranks (needs `gpurun --gpus 2`; skipped on a one-GPU box)
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+    tools/train_two_ranks.py > "$out/train_two_ranks.json" 2> "$out/train_two_ranks.err"; echo "train ranks rc=$?"; cat "$out/train_two_ranks.json"
+fi
