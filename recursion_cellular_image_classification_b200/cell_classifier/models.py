@@ -7,9 +7,13 @@ tensor in torchvision's named_parameters() order; `state_dict()` / `load_state_d
 names so checkpoints interchange with `torchvision.models.densenet121`.
 
 `TwoSitesNN` keeps the reference's constructor and call signature (models.py:8-12, 41):
-x[B, G, 6, H, W] -> [B, nb_classes]; the G images of a sample are averaged in feature space (models.py:46-50),
-which for DenseNet's linear classifier equals averaging the logits.  `DummyClassifier` is the reference's
-fake backend (models.py:60-68).
+x[B, G, 6, H, W] -> [B, nb_classes].  The reference splits the G images of a sample into thirds — the sample's own
+sites, the negative control's, the positive control's (models.py:46-49) — averages each third in feature space and
+concatenates the three means into its MLP (:50-55).  DenseNet-121 has a single-image trunk with ONE linear classifier,
+so only the first third (the sample's own sites) can reach it: `sample_group(G)` says how many leading images that
+is, their features are averaged (= averaging their logits, the head being linear), and the control thirds are
+neither decoded, copied nor run (dataloader.raw_item(controls=False)).  train(), evaluate() and test() all use this
+one rule.  `DummyClassifier` is the reference's fake backend (models.py:60-68).
 """
 import ctypes
 import math
@@ -53,6 +57,12 @@ def densenet121_param_specs(nb_classes=1108):
     specs.append(("classifier.weight", (nb_classes, c)))
     specs.append(("classifier.bias", (nb_classes,)))
     return specs, bufs
+
+
+def sample_group(G):
+    """How many of the G images of an item are the sample's own sites: the first third when the item carries the
+    reference's image / negative-control / positive-control thirds (models.py:45-49: shape = int(G/3)), else all."""
+    return G // 3 if G >= 3 and G % 3 == 0 else G
 
 
 def to_s2d32(x_nchw):
@@ -186,6 +196,10 @@ class DenseNet121(torch.nn.Module):
             return self._plans[key]
         _lib.require_gpu()
         lib = load()
+        # one live plan per mode: a plan owns a full workspace (12.8 GB at B=128, 512x512), so the odd last batch of
+        # an epoch or another evaluation batch size replaces the previous plan of that mode instead of piling up
+        for old in [k for k in self._plans if k[3] == bool(training)]:
+            lib.rxb_dn121_destroy(self._plans.pop(old)["handle"])
         cfg = Dn121Config(B, H, W, self.nb_classes, self.bn_eps, self.bn_momentum)
         assert lib.rxb_dn121_param_count(ctypes.byref(cfg)) == self.flat.numel()
         assert lib.rxb_dn121_buffer_count(ctypes.byref(cfg)) == self.bn_buffers.numel()
@@ -222,11 +236,12 @@ class DenseNet121(torch.nn.Module):
         return to_s2d32(x.to(self.flat.device))
 
     def forward(self, x):
-        """x: bf16 S2D32 [B,H/2,W/2,32] (fused-loader output) or float [B,6,H,W] / [B,G,6,H,W]."""
+        """x: bf16 S2D32 [B,H/2,W/2,32] (fused-loader output) or float [B,6,H,W] / [B,G,6,H,W] (the reference's item
+        layout: only the sample's own sites, the first third of G, are run and averaged — see the module docstring)."""
         groups = None
         if x.dim() == 5:
-            groups = x.shape[1]
-            x = x.reshape(-1, *x.shape[2:])
+            groups = sample_group(x.shape[1])
+            x = x[:, :groups].reshape(-1, *x.shape[2:])
         xs = self._as_s2d(x)
         B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
         plan = self._plan(B, H, W, False)

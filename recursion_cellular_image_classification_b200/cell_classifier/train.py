@@ -38,12 +38,12 @@ def evaluate(model, ds, bs, num_workers, device):
     net = _unwrap(model)
     was_training = net.training
     net.eval()
-    loader = torch.utils.data.DataLoader(RawView(ds), batch_size=bs, shuffle=False, num_workers=num_workers,
-                                         collate_fn=collate_raw)
+    loader = torch.utils.data.DataLoader(RawView(ds, controls=False), batch_size=bs, shuffle=False,
+                                         num_workers=num_workers, collate_fn=collate_raw)
     correct, total, loss_sum = 0, 0, 0.0
     dev = torch.device(device)
     for batch in loader:
-        xs = ds.device_batch(batch, dev, first_only=True)
+        xs = ds.device_batch(batch, dev)                              # one image per sample (its own site, no controls)
         y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
         logits = net(xs)
         loss_rows, _ = ops.softmax_ce(logits, y)
@@ -69,8 +69,12 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     sampler = None
     if world > 1:
         sampler = torch.utils.data.distributed.DistributedSampler(ds_train, num_replicas=world, rank=rank, shuffle=True)
-    loader = torch.utils.data.DataLoader(RawView(ds_train), batch_size=bs, shuffle=sampler is None, sampler=sampler,
-                                         num_workers=num_workers, collate_fn=collate_raw, drop_last=world > 1)
+    # items carry the sample's own image only (controls=False): the control wells cannot reach DenseNet's single
+    # linear classifier (see cell_classifier/models.py), so they are neither decoded nor copied — train, validation
+    # and test() all follow this one rule
+    loader = torch.utils.data.DataLoader(RawView(ds_train, controls=False), batch_size=bs, shuffle=sampler is None,
+                                         sampler=sampler, num_workers=num_workers, collate_fn=collate_raw,
+                                         drop_last=world > 1)
     net.train()
     # TensorBoard scalars under board/<id> like train.py:114-138 (tags 'training/loss' and 'lr/group_0' per iteration,
     # 'validation/accuracy' and 'validation/loss' per epoch); gradient histograms (:136-138) are not written.
@@ -121,7 +125,7 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
         loss_hist = torch.zeros(max(len(loader), 1), device=dev)             # per-iteration losses, read back once per epoch
         n_it = 0
         for batch in loader:
-            xs = ds_train.device_batch(batch, dev, first_only=True)
+            xs = ds_train.device_batch(batch, dev)
             y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
             B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
             if n_phases is None:

@@ -44,10 +44,20 @@ def world_size():
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
-def scaled_hyperparams(per_gpu_bs, n_ranks, lr=None):
-    """main.py:67,71: the global batch is 16 x nGPU and lr = 0.0005 x global batch unless given."""
-    gbs = per_gpu_bs * n_ranks
-    return gbs, (0.0005 * gbs if lr is None else lr)
+def rank_world():
+    """(rank, world size) of the initialised process group — (0, 1) in a single process."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def max_int(value, device):
+    """Largest `value` over the ranks (an agreement step for sizes only some ranks know)."""
+    if world_size() == 1:
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
 
 
 def shard_range(n_items, rank, world):

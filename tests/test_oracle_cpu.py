@@ -311,6 +311,14 @@ def test_stem_recipe_and_site_averaging_match_reference_golden(golden_dir):
         x = torch.from_numpy(g["x%d" % G])
         feats = (x.reshape(-1, 6, 8, 8).mean(dim=(2, 3)) * torch.arange(1, 7, dtype=x.dtype))   # the golden's stub trunk
         np.testing.assert_array_equal(O.two_sites_features(feats, x.shape[0]).numpy(), g["y%d" % G])
+        # the product's grouping rule (models.sample_group): the sample's own sites are the FIRST third of the item,
+        # and their feature mean is the first block of what the reference's forward concatenates (models.py:46-50)
+        from recursion_cellular_image_classification_b200.cell_classifier.models import sample_group
+        own = sample_group(G)
+        assert own == G // 3
+        F = feats.shape[1]
+        np.testing.assert_array_equal(feats.reshape(x.shape[0], G, F)[:, :own].mean(1).numpy(), g["y%d" % G][:, :F])
+    assert [sample_group(G) for G in (1, 2, 3, 6, 4)] == [1, 2, 1, 2, 4]     # items without controls: every image is a site
 
 
 # ---------------------------------------------------------------- product host helpers (no GPU needed)

@@ -80,11 +80,6 @@ def test_shard_range_covers_everything_without_overlap():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_batch_and_lr_scaling_follow_main_py():
-    assert parallel.scaled_hyperparams(16, 8) == (128, 0.0005 * 128)      # main.py:67,71
-    assert parallel.scaled_hyperparams(16, 1, lr=0.1) == (16, 0.1)
-
-
 def test_cosine_schedule_matches_torch():
     p = torch.nn.Parameter(torch.zeros(1))
     opt = torch.optim.SGD([p], lr=0.008)
@@ -242,7 +237,7 @@ class _FeatureDS:
     def __len__(self):
         return len(self.y)
 
-    def raw_item(self, i):
+    def raw_item(self, i, controls=True):
         return {"planes": self.x[i][None], "codes": torch.zeros(1, dtype=torch.uint8),
                 "crops": torch.zeros(1, 2, dtype=torch.int32), "exp": 0, "out": 0, "label": int(self.y[i])}
 
@@ -338,3 +333,69 @@ def test_ranks_take_the_same_early_stopping_decision(tmp_path):
         assert p.exitcode == 0
     assert got[0][1] == got[1][1] and [e for e, _, _ in got[0][1]] == [0, 1, 2, 3, 4]
     assert got[0][2] == got[1][2] == 4 and got[0][1][1][1:] == (0.30, 1.0)
+
+
+# ---------------------------------------------------------------- test(): wells sharded over ranks, logits all-gathered
+def _test_shard_worker(rank, world, port, golden, n_wells, views, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import pandas as pd
+    from oracle import oracle_np as O
+    from recursion_cellular_image_classification_b200 import ops
+    from recursion_cellular_image_classification_b200.cell_classifier import test as shim
+
+    def tta_softmax_avg_mask(logits, plate=None, group_col=None):
+        probs = np.mean([O.softmax(v) for v in logits.numpy()], axis=0).astype(np.float32)
+        return torch.from_numpy(O.mask_rescale(probs, group_col.numpy(), plate.numpy()))
+
+    ops.tta_softmax_avg_mask = tta_softmax_avg_mask
+    ops.greedy_assign = lambda p: torch.from_numpy(O.greedy_assign(p.numpy()).astype(np.int32))
+    if world > 1:
+        parallel.init_from_env(backend="gloo")
+    g = np.load(golden)
+    logits = g["logits64"][:n_wells]
+    seen = []
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return n_wells
+
+        def __getitem__(self, i):
+            seen.append(i)
+            return torch.tensor([float(i)]), "id%d" % i
+
+    res = shim.test(pd.DataFrame({"plate": g["plates64"][:n_wells]}), DS(), g["pg64"], int(g["et64"]),
+                    lambda x: torch.from_numpy(logits[x[:, 0].long().numpy()]), bs=5, num_workers=0, device="cpu",
+                    tta_views=views)
+    q.put((rank, res.tolist(), sorted(set(seen))))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("n_wells,views", [(64, 1), (7, 2), (1, 1)])
+def test_test_shim_shards_wells_and_gathers_logits(golden_dir, n_wells, views):
+    """test() under two gloo ranks: each rank runs the model on its contiguous shard of wells only, the
+    [V, N, C] logits are all-gathered and BOTH ranks return the one-rank answer — the reference's own output for the
+    64-well golden case.  One well on two ranks leaves rank 1 with an empty shard that still joins the gather."""
+    golden = os.path.join(golden_dir, "assign_golden.npz")
+    ctx = mp.get_context("spawn")
+    out = {}
+    for world in (1, 2):
+        q, port = ctx.Queue(), _free_port()
+        procs = [ctx.Process(target=_test_shard_worker, args=(r, world, port, golden, n_wells, views, q))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        got = sorted(q.get(timeout=200) for _ in range(world))
+        for p in procs:
+            p.join(timeout=30)
+            assert p.exitcode == 0
+        out[world] = got
+    one = out[1][0][1]
+    if n_wells == 64 and views == 1:
+        np.testing.assert_array_equal(one, np.load(golden)["res64"])
+    for rank, res, seen in out[2]:
+        assert res == one
+        b, e = parallel.shard_range(n_wells, rank, 2)
+        assert seen == list(range(b, e))                     # a rank touches its own wells only

@@ -210,6 +210,24 @@ def test_images_ds_host_logic(tmp_path, fake_loader, decode):
                     ref = np.ascontiguousarray(np.moveaxis(O.normalize(w, stats[exp]["mean"], stats[exp]["std"]), 2, 0))
                 assert np.array_equal(got[bi, g_].view(np.uint32), ref.view(np.uint32))
             assert np.array_equal(first[bi], got[bi, 0])
+    # the fast path of train() / evaluate() / test(): items without the control wells (what DenseNet's single linear
+    # head can use) — one random site in train/val, both sites in test, same transforms
+    import random as _random
+    for mode, G in (("val", 1), ("test", 2)):
+        ds = dl.ImagesDS(df, dfc, stats, str(tmp_path), mode, crop=20, **kw)
+        _random.seed(5)
+        item = ds.raw_item(4, controls=False)
+        assert item["codes"].shape == (G,) and item["crops"].shape == (G, 2)
+        x = ds.device_batch(dl.collate_raw([item]), torch.device("cpu"), out_format=ops.OUT_F32_NCHW)
+        exp, well = df.iloc[4].experiment, df.iloc[4].well
+        split = "train" if mode == "val" else "test"
+        t = dict(crop_yx=(6, 6), out_hw=(20, 20)) if mode == "val" else {}
+        assert x.shape[0] == G
+        if mode == "val":
+            assert is_one_of(x[0], [expect(split, exp, well, s, **t) for s in (1, 2)])
+        else:
+            for s in (1, 2):
+                assert is_one_of(x[s - 1], [expect(split, exp, well, s)])
 
 
 def test_test_shim_host_logic_matches_reference_golden(golden_dir, monkeypatch):
@@ -243,9 +261,10 @@ def test_test_shim_host_logic_matches_reference_golden(golden_dir, monkeypatch):
 
 
 def test_test_shim_with_dataset_and_eight_d4_views(tmp_path, fake_loader, monkeypatch):
-    """test() over an ImagesDS with tta_views=8 (BASELINE config 4: 2 sites x 8 D4 views, controls included): every
-    view re-normalises and re-augments all six images of a well, logits are averaged over the images, probabilities
-    over the views, then mask + rescale + greedy assignment — against the same computation spelled out with the oracle."""
+    """test() over an ImagesDS with tta_views=8 (BASELINE config 4: 2 sites x 8 D4 views): every view re-normalises
+    and re-augments the well's OWN two sites (the first third of the reference's item, models.py:46-49 — control wells
+    never reach a single-image linear head and are not loaded), logits are averaged over the sites, probabilities over
+    the views, then mask + rescale + greedy assignment — against the same computation spelled out with the oracle."""
     from recursion_cellular_image_classification_b200.cell_classifier import dataloader as dl
     from recursion_cellular_image_classification_b200.cell_classifier import test as shim
     df, dfc, planes = _tree(tmp_path)
@@ -283,7 +302,7 @@ def test_test_shim_with_dataset_and_eight_d4_views(tmp_path, fake_loader, monkey
         rows = []
         for i in range(len(df)):
             exp, well = df.iloc[i].experiment, df.iloc[i].well
-            imgs = [planes[("test", exp, w, s)] for w in (well, "B02", "C03") for s in (1, 2)]
+            imgs = [planes[("test", exp, well, s)] for s in (1, 2)]
             x = np.stack([O.transform(im, stats[exp]["mean"], stats[exp]["std"], vflip=bool(c & 1), hflip=bool(c & 2),
                                       k=(c >> 2) & 3) for im in imgs])
             rows.append(model(torch.from_numpy(x)).mean(0).numpy())
@@ -517,3 +536,23 @@ def test_train_early_stopping_and_best_checkpoint(tmp_path, monkeypatch):
     assert not (tmp_path / "board").exists()
     sd = torch.load("models/best_model_es.pth")
     assert torch.equal(sd["module.flat"], snapshots[0])               # weights as they were after epoch 1
+
+
+def test_config4_case_is_well_separated(tmp_path):
+    """The seeded config-4 case the GPU parity test runs (tests/c4_case.py), oracle side only: the expected
+    assignment (two collisions resolved by the greedy loop) does not move under logit noise three times the 2e-2
+    tolerance, so a GPU/oracle disagreement there is an error, not a tie."""
+    import c4_case as C
+    from recursion_cellular_image_classification_b200.synth import synth_plate_groups
+    pg = synth_plate_groups(3)
+    df, dfc, planes = C.write_tree(str(tmp_path))
+    net, classes = C.build_oracle_model(planes, pg)
+    L = C.oracle_logits(net, planes, 8)
+    _, res = C.oracle_assign(L, pg, df.plate.values)
+    assert list(res.astype(int)) == classes
+    assert len(set(classes)) == 6 and all(pg[c, C.EXPERIMENT_TYPE] == p for c, p in zip(classes, C.PLATES))
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        noise = rng.standard_normal(L.shape).astype(np.float32)
+        noise *= 0.06 * np.linalg.norm(L) / np.linalg.norm(noise)
+        np.testing.assert_array_equal(C.oracle_assign(L + noise, pg, df.plate.values)[1], res)
