@@ -102,19 +102,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference path on the host CPUs: oracle normalise+augment (numpy/OpenCV restatement of
-    dataloader.py:128-139) + torchvision DenseNet-121 (6-ch stem) fp32 forward/backward + SGD (main.py:89-93),
-    all host threads, on a bounded sample of the same workload (batch `--ref-batch` of 6x512x512)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# ---------------------------------------------------------------------------------------------- CPU arms
+def cpu_threads():
+    """Use every host core: under torchrun OMP_NUM_THREADS defaults to 1, which made round 1's N>1 reference lines
+    a one-core number.  Returns the thread count torch will really use."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_port_step_rate(B, max_steps, warmup, seconds_budget=None):
+    """THE CPU baseline of both arms (one definition): the reference path on the host — oracle normalise + D4 augment
+    (numpy/OpenCV restatement of dataloader.py:128-139) + torchvision DenseNet-121 with the reference's 6-channel stem,
+    fp32 forward / CrossEntropy / backward + nesterov SGD (main.py:89-93) — on a bounded sample of the workload:
+    batch B of 6x512x512, `warmup` untimed steps, then up to `max_steps` timed steps (or until the budget runs out)."""
     from oracle import oracle_np as O
     from recursion_cellular_image_classification_b200.synth import synth_planes
+    cores = cpu_threads()
     torch.manual_seed(0)
-    cores = torch.get_num_threads()
-    B = args.ref_batch
     net = O.densenet121_6ch(NUM_CLASSES, seed=0)
     net.train()
     opt = O.sgd_reference(net.parameters(), lr=0.0005 * B)
@@ -135,60 +144,146 @@ def run_reference(args):
         opt.step()
         return loss.item()
 
-    steps, warmup = min(args.steps, args.ref_max_steps), min(args.warmup, 1)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    n = 0
+    while n < max_steps and (n < 1 or seconds_budget is None or time.perf_counter() - t0 < seconds_budget):
         step()
+        n += 1
     dt = time.perf_counter() - t0
-    val = B * steps / dt
-    sample = "batch %d x 6x512x512, %d timed steps after %d warm-up, torch fp32 CPU + numpy loader" % (B, steps, warmup)
+    sample = ("batch %d x 6x512x512, %d timed steps after %d warm-up: numpy/OpenCV normalise+D4 loader + torchvision "
+              "densenet121 (6-ch stem) fp32 fwd+CE+bwd+nesterov SGD, %d threads" % (B, n, warmup, cores))
+    return {"value": B * n / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}, n, dt
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU baseline above as its own JSON line (rank 0 only; other ranks exit without work)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    steps, warmup = min(args.steps, args.ref_max_steps), min(args.warmup, 1)
+    cpu, steps, dt = cpu_port_step_rate(B, steps, warmup)
+    val = cpu["value"]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "DenseNet-121 6-channel 512x512 training step: normalise+D4 loader, fwd, CE, bwd, "
                                    "nesterov SGD (the same step as the default arm; fp32 CPU port, bounded sample)",
                        "batch_per_gpu": B, "global_batch": B, "num_classes": NUM_CLASSES, "parallelism": "cpu",
-                       "lr": 0.0005 * B},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "lr": 0.0005 * B, "host_threads": cpu["cores"], "os_cpu_count": os.cpu_count()},
+            "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
 def cpu_baseline(seconds_budget=25.0):
-    """Oracle port of the same train step on the host cores: bounded sample (batch 2, as many steps as fit)."""
-    from oracle import oracle_np as O
-    torch.manual_seed(0)
-    B = 2
-    net = O.densenet121_6ch(NUM_CLASSES, seed=0)
-    net.train()
-    opt = O.sgd_reference(net.parameters(), lr=0.001)
-    lossf = torch.nn.CrossEntropyLoss()
-    x = torch.randn(B, 6, IMG, IMG)
-    y = torch.randint(0, NUM_CLASSES, (B,))
-
-    def step():
-        opt.zero_grad()
-        lossf(net(x), y).backward()
-        opt.step()
-
-    step()
-    t0 = time.perf_counter()
-    n = 0
-    while n < 1 or (time.perf_counter() - t0 < seconds_budget and n < 8):
-        step()
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": B * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "torchvision densenet121 (6-ch stem) fp32 fwd+bwd+SGD, batch %d x 6x512x512, %d steps after 1 "
-                      "warm-up (model only, no loader)" % (B, n)}
+    """The same CPU port as `--impl reference` (batch 4), bounded to ~25 s."""
+    return cpu_port_step_rate(4, 8, 1, seconds_budget)[0]
 
 
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of each representative conv kernel at batch
-# 128, from the committed `ncu --set full` capture profiles/r01_conv_kernels_b128_ncu_raw.csv (tools/bench_conv.py prof).
-NCU_TRAFFIC_B128 = {"fwd_3x3": 657641176, "fwd_1x1": 1577551888, "dgrad_3x3_bn": 1171553048, "dgrad_1x1_bn_accum": 3577494384, "wgrad_3x3": 686420504, "wgrad_1x1": 1615986728}
+def library_gpu_baseline(dev, B=64, steps=6):
+    """INFORMATIONAL, NOT THE REFERENCE ARM: the stock library path on the same box — torchvision densenet121 with the
+    6-channel stem, bf16 autocast, channels_last, eager cuDNN (cudnn.benchmark like main.py:68), fwd + CE + bwd + SGD
+    on a resident batch (BASELINE.md 1 names this as the bar on the box).  Kept small (batch 64) so it cannot run the
+    box out of memory."""
+    try:
+        import torchvision
+        torch.backends.cudnn.benchmark = True
+        torch.manual_seed(0)
+        net = torchvision.models.densenet121(weights=None, num_classes=NUM_CLASSES)
+        net.features.conv0 = torch.nn.Conv2d(6, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        net = net.to(dev).to(memory_format=torch.channels_last).train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.0005 * B, momentum=0.9, nesterov=True, weight_decay=3e-5)
+        x = torch.randn(B, 6, IMG, IMG, device=dev).to(memory_format=torch.channels_last)
+        y = torch.randint(0, NUM_CLASSES, (B,), device=dev)
+        lossf = torch.nn.CrossEntropyLoss()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = lossf(net(x).float(), y)
+            loss.backward()
+            opt.step()
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b_.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b_) / steps
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        del net, opt, x, y
+        torch.cuda.empty_cache()
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps,
+                "peak_mem_gb": peak_gb,
+                "what": "NOT the reference arm: torchvision densenet121 (6-ch stem), bf16 autocast, channels_last, "
+                        "eager cuDNN/cuBLAS, model step only (no loader), same box"}
+    except Exception as e:
+        torch.cuda.empty_cache()
+        return {"error": repr(e)}
+
+
+def step_traffic_model(B):
+    """ALGORITHMIC HBM bytes of one training step under the CURRENT data flow (bf16 NHWC activations,
+    one concat buffer per block, lazy BatchNorm backward), per kernel family — every operand read once, every result
+    written once, the running concat gradient read AND written.  Keys match kernel_breakdown_fine."""
+    px = lambda h: B * h * h
+    blocks, C, H = (6, 12, 24, 16), 64, IMG // 4
+    t = {k: 0.0 for k in ("conv_fwd_1x1", "conv_fwd_3x3", "conv_wgrad_3x3", "conv_dgrad_3x3", "bn_bwd_apply",
+                          "conv_wgrad_1x1", "conv_dgrad_1x1", "grad_fixup", "conv_other", "wgrad_other",
+                          "elementwise_other", "loader")}
+    Ms = px(IMG // 2)
+    # stem: conv (S2D input 32 ch -> 64), BN+ReLU+maxpool (+indices), pool backward, BN backward apply, weight gradient
+    t["conv_other"] += 2.0 * Ms * (32 + 64)
+    t["elementwise_other"] += 2.0 * Ms * 64 + px(H) * (2.0 * 64 + 64)
+    t["elementwise_other"] += px(H) * (2.0 * 64 + 64) + 2.0 * Ms * 64 * 2
+    t["bn_bwd_apply"] += 2.0 * Ms * 64 * 3
+    t["wgrad_other"] += 2.0 * Ms * (64 + 32)
+    for b, n_layers in enumerate(blocks):
+        M, C0 = px(H), C
+        for i in range(n_layers):
+            cin = C + 32 * i
+            t["conv_fwd_1x1"] += 2.0 * M * (cin + 128)
+            t["conv_fwd_3x3"] += 2.0 * M * (128 + 32)
+            t["grad_fixup"] += 2.0 * M * 32 * 3
+            t["conv_wgrad_3x3"] += 2.0 * M * (128 + 32)
+            t["conv_dgrad_3x3"] += 2.0 * M * (32 + 128 + 128)
+            t["bn_bwd_apply"] += 2.0 * M * 128 * 3
+            t["conv_wgrad_1x1"] += 2.0 * M * (cin + 128)
+            t["conv_dgrad_1x1"] += 2.0 * M * (128 + 3 * cin)
+        C += 32 * n_layers
+        t["grad_fixup"] += 2.0 * M * C0 * 3                         # exact gradient of the block input
+        if b < 3:
+            Mq = M / 4
+            t["elementwise_other"] += 2.0 * (M * C + Mq * C)         # BN+ReLU+avgpool
+            t["conv_other"] += 2.0 * Mq * (C + C // 2)               # transition conv (after the pool)
+            t["wgrad_other"] += 2.0 * Mq * (C + C // 2)
+            t["conv_other"] += 2.0 * Mq * (C // 2 + C)               # its data gradient
+            t["elementwise_other"] += 2.0 * (Mq * C + 2 * M * C)     # pool/ReLU/BN backward into G
+            C //= 2
+            H //= 2
+        else:
+            t["elementwise_other"] += 2.0 * M * C + 2.0 * 2 * M * C  # norm5+ReLU+GAP forward; backward into G
+    t["loader"] = float(LOADER_BYTES_PER_IMG) * B
+    return t
+
+
+def ncu_traffic(B):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of each representative kernel, read from
+    the committed summary of the `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py
+    from the raw CSV of the same commands) — null when no capture exists for this batch size."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return {}
+    d = json.load(open(path))
+    return d.get("batch_%d" % B, {}).get("kernels", {})
 
 
 def conv_kernel_rooflines(B, dev, peaks):
@@ -212,11 +307,12 @@ def conv_kernel_rooflines(B, dev, peaks):
     H = W = IMG // 4
     M = B * H * W
     out = {}
+    traffic_tab = ncu_traffic(B)
 
     def entry(name, ms, bytes_, flops, what):
         gbs = bytes_ / (ms * 1e-3) / 1e9
         tf = flops / (ms * 1e-3) / 1e12
-        tr = NCU_TRAFFIC_B128.get(name) if B == 128 else None
+        tr = traffic_tab.get(name)
         out[name] = {"what": what, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy", "ms": ms,
                      "algorithmic_bytes": bytes_, "tflops": tf, "tensor_frac": tf / peaks["bf16_tflops_sustained"],
@@ -489,8 +585,9 @@ def run_ours(args):
 
     # ---- kernel-family breakdown (event-bracketed launches, separate untimed pass) and HBM kernels
     breakdown, roofline, hbm_kernels, roofline_tensor, conv_kernels, widen_kernels = None, None, None, None, None, None
+    fine, step_roofline = None, None
     # every rank runs the profiled steps (they contain the gradient all-reduces); only rank 0 reports
-    ncat = 9
+    ncat = 17
     msb = (ctypes.c_float * ncat)()
     cnt = (ctypes.c_int64 * ncat)()
     prof_steps = 2
@@ -503,9 +600,25 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     if rank == 0:
-        names = ["stats", "loader", "conv_fwd", "conv_dgrad", "conv_wgrad", "elementwise", "head", "optimizer", "tta"]
-        breakdown = {nme: {"ms_per_step": msb[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps}
-                     for i, nme in enumerate(names)}
+        fine_names = ["stats", "loader", "conv_fwd_1x1", "conv_dgrad_1x1", "conv_wgrad_1x1", "elementwise_other", "head",
+                      "optimizer", "tta", "conv_fwd_3x3", "conv_dgrad_3x3", "conv_wgrad_3x3", "conv_other", "wgrad_other",
+                      "bn_bwd_apply", "grad_fixup", "bn_bwd_finalize"]
+        model = step_traffic_model(B)
+        fine = {}
+        for i, nme in enumerate(fine_names):
+            e = {"ms_per_step": msb[i] / prof_steps, "launches_per_step": cnt[i] / prof_steps}
+            if nme in model and e["ms_per_step"] > 0:
+                e["algorithmic_gb_per_step"] = model[nme] / 1e9
+                e["hbm_frac"] = model[nme] / (e["ms_per_step"] * 1e-3) / 1e9 / peaks["hbm_gbs"]
+            fine[nme] = e
+        fam = {"stats": ["stats"], "loader": ["loader"], "conv_fwd": ["conv_fwd_1x1", "conv_fwd_3x3", "conv_other"],
+               "conv_dgrad": ["conv_dgrad_1x1", "conv_dgrad_3x3"],
+               "conv_wgrad": ["conv_wgrad_1x1", "conv_wgrad_3x3", "wgrad_other"],
+               "elementwise": ["elementwise_other", "bn_bwd_apply", "grad_fixup", "bn_bwd_finalize"], "head": ["head"],
+               "optimizer": ["optimizer"], "tta": ["tta"]}
+        breakdown = {k: {"ms_per_step": sum(fine[n]["ms_per_step"] for n in v),
+                         "launches_per_step": sum(fine[n]["launches_per_step"] for n in v)} for k, v in fam.items()}
+        prof_total_ms = max(sum(v["ms_per_step"] for v in fine.values()), 1e-9)
         conv_ms = sum(breakdown[k]["ms_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
         conv_launches = sum(breakdown[k]["launches_per_step"] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad"))
         achieved_tf = FLOP_FWD_BWD_PER_IMG * B / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -518,12 +631,52 @@ def run_ours(args):
                            "note": "the stride-1 DenseNet convs at bf16 have 43-230 FLOP/B arithmetic intensity, at or "
                                    "below the B200 ridge (~217 FLOP/B): they are HBM-bound, see DESIGN.md section 5"}
         conv_kernels = conv_kernel_rooflines(B, dev, peaks)
-        # the dominant kernel of the step (largest share of the launch list, profiles/): the 1x1 data-gradient
-        # with the fused ReLU/BatchNorm-backward epilogue, on its true bound
-        roofline = dict(conv_kernels["dgrad_1x1_bn_accum"])
-        roofline["kernel"] = "conv_gemm_kernel<64,false> EPI_DGRAD_BN (dense-layer 1x1 data gradient + ReLU/BN backward)"
-        roofline["share_of_step"] = breakdown["conv_dgrad"]["ms_per_step"] / max(sum(
-            v["ms_per_step"] for v in breakdown.values()), 1e-9)
+        # Whole-step position: against the tensor roofline SURVEY 8d names for the convolutions, and against the HBM
+        # traffic the current data flow moves (the bound the step can reach without moving fewer bytes).
+        step_ms = ms / args.steps
+        traffic_bytes = sum(model.values())
+        step_roofline = {"tensor_frac_step": FLOP_FWD_BWD_PER_IMG * B / (step_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                         "tflops_step": FLOP_FWD_BWD_PER_IMG * B / (step_ms * 1e-3) / 1e12,
+                         "algorithmic_hbm_gb_per_step": traffic_bytes / 1e9,
+                         "hbm_traffic_bound_ms": traffic_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3,
+                         "hbm_frac_step": traffic_bytes / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "ms_per_step": step_ms}
+        # `roofline`: the kernel SYMBOL with the largest share of the step (launch list in profiles/), its bytes and
+        # time summed over ALL its launches of the step (event-bracketed), with the tensor number beside the HBM one.
+        symbols = {
+            "conv_wgrad_kernel": (["conv_wgrad_1x1", "conv_wgrad_3x3", "wgrad_other"], "wgrad_1x1",
+                                  "conv_wgrad_kernel (weight gradients: dense-layer 1x1 and 3x3, transitions, stem)"),
+            "conv_gemm_kernel<64,false,2>": (["conv_dgrad_1x1"], "dgrad_1x1_bn_accum",
+                                             "conv_gemm_kernel<64,false,2> (dense-layer 1x1 data gradient + ReLU/BN backward, "
+                                             "L2 reduce-add into the concat gradient)"),
+            "conv_gemm_kernel<64,true,0>": (["conv_fwd_1x1"], "fwd_1x1", "conv_gemm_kernel<64,true,0> (dense-layer 1x1 forward)"),
+            "conv_gemm_kernel<64,true,1>": (["conv_fwd_3x3"], "fwd_3x3", "conv_gemm_kernel<64,true,1> (dense-layer 3x3 forward)"),
+            "conv_gemm_kernel<32,false,2>": (["conv_dgrad_3x3"], "dgrad_3x3_bn", "conv_gemm_kernel<32,false,2> (3x3 data gradient)"),
+        }
+        share = {k: sum(fine[n]["ms_per_step"] for n in v[0]) / prof_total_ms for k, v in symbols.items()}
+        top = max(share, key=share.get)
+        cats, rep, label = symbols[top]
+        t_ms = sum(fine[n]["ms_per_step"] for n in cats)
+        n_l = sum(fine[n]["launches_per_step"] for n in cats)
+        alg = sum(model[n] for n in cats)
+        # algorithmic FLOPs per image of each symbol's launches (dense 1x1 12.17, dense 3x3 12.98 GFLOP
+        # forward; a weight gradient exists for every conv: 30.84)
+        flops_share = {"conv_wgrad_kernel": 30.84e9, "conv_gemm_kernel<64,false,2>": 12.17e9,
+                       "conv_gemm_kernel<64,true,0>": 12.17e9, "conv_gemm_kernel<64,true,1>": 12.98e9,
+                       "conv_gemm_kernel<32,false,2>": 12.98e9}[top] * B
+        ach = alg / (t_ms * 1e-3) / 1e9
+        roofline = {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy",
+                    "launches_per_step": n_l, "avg_launch_ms": t_ms / max(n_l, 1), "ms_per_step": t_ms,
+                    "algorithmic_bytes_per_step": alg, "algorithmic_bytes_per_launch": alg / max(n_l, 1),
+                    "share_of_step": share[top], "share_of_step_by_symbol": share,
+                    "traffic": conv_kernels[rep]["traffic"], "traffic_launch": rep,
+                    "representative_launch": conv_kernels[rep],
+                    "tensor": {"achieved": flops_share / (t_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                               "unit": "TFLOP/s", "frac": flops_share / (t_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                               "note": "SURVEY 8d names the tensor roofline for convolutions; at bf16 these kernels sit "
+                                       "below the ridge, so the HBM figure is the binding one and both are given"},
+                    "step": step_roofline}
         # HBM-bound families, timed alone on >L2 inputs
         def time_kernel(fn, reps=10):
             for _ in range(3):
@@ -601,6 +754,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
+        lib_gpu = library_gpu_baseline(dev) if world == 1 and not args.no_library_baseline else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -614,8 +768,10 @@ def run_ours(args):
                 "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
                 "clocks": clocks,
                 "roofline": roofline, "roofline_tensor_conv_family": roofline_tensor, "conv_kernels": conv_kernels,
+                "step_roofline": step_roofline,
                 "hbm_kernels": hbm_kernels, "widen_kernels": widen_kernels, "kernel_breakdown": breakdown,
-                "cpu_baseline": cpu,
+                "kernel_breakdown_fine": fine,
+                "cpu_baseline": cpu, "library_gpu_baseline": lib_gpu,
                 "loss": {"after_warmup": loss_first, "last": loss_last}}
         if graph_result is not None:
             line["cuda_graph_experiment"] = graph_result
@@ -634,6 +790,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--ref-max-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
                     help="development: also time the step replayed from one CUDA graph (N=1; reported separately)")
     ap.add_argument("--quick", action="store_true",

@@ -33,9 +33,11 @@ enum rxb_status {
   RXB_ERR_INVALID = -1,   /* bad argument */
   RXB_ERR_CUDA = -2,      /* CUDA runtime / driver error */
   RXB_ERR_UNSUPPORTED = -3,
-  RXB_ERR_NO_DEVICE = -4, /* no sm_100 device: there is no fallback */
-  RXB_ERR_NCCL = -5
+  RXB_ERR_NO_DEVICE = -4  /* no sm_100 device: there is no fallback */
 };
+/* Collectives are not part of this library: the gradient all-reduce, the statistics all-reduce and the test-time
+ * all-gather are issued by the host side through torch.distributed (NCCL) between the phases the executor exposes
+ * (rxb_dn121_train_step's `phase`), see recursion_cellular_image_classification_b200/parallel.py. */
 
 int rxb_version(void);
 const char* rxb_last_error(void);
@@ -46,14 +48,14 @@ int rxb_check_device(void);
  * Family 1a — per-experiment channel statistics.
  * Replaces the hot loop of compute_mean_std(), compute_stats_experiments.py:13-20 (count / sum(x) /
  * sum(x^2) per channel of x = u8/255), with exact integer accumulation.
- *   imgs    u8, layout RXB_LAYOUT_NCHW: [n, C, H, W] planar   (what dataloader.py:141-146 decodes)
- *               layout RXB_LAYOUT_NHWC: [n, H, W, C] interleaved (what dataloader.py:129 moves to)
+ *   imgs    u8 [n, C, H, W] planar — what dataloader.py:141-146 decodes and compute_stats_experiments.py:15 reads
+ *           (one file per channel).  `layout` must be RXB_LAYOUT_NCHW; any other value is RXB_ERR_UNSUPPORTED.
  *   exp_id  i32[n], experiment slot of every image, 0 <= exp_id < n_exp
  *   sum, sumsq, count  u64[n_exp, C], ACCUMULATED into (caller zeroes them once); count is in pixels
  *               (compute_stats_experiments.py:21 multiplies the image count by 512*512).
  * H*W must be a multiple of 16.
  */
-enum rxb_layout { RXB_LAYOUT_NCHW = 0, RXB_LAYOUT_NHWC = 1 };
+enum rxb_layout { RXB_LAYOUT_NCHW = 0 };
 int rxb_stats_accumulate(const uint8_t* imgs, const int32_t* exp_id, int64_t n, int H, int W, int C,
                          int layout, int n_exp, unsigned long long* sum, unsigned long long* sumsq,
                          unsigned long long* count, rxb_stream_t stream);
@@ -192,6 +194,14 @@ int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16 
 int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
                       int ldX, const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16,
                       float* sum_dy, rxb_stream_t stream);
+/* The same launch with the BatchNorm's own weight and bias (f32[Cout]) given: channels with |gamma| < 1e-3 or
+ * |gamma| < 0.05*|beta| ("degenerate": the W.dW identity below divides by gamma*rstd and cancels catastrophically
+ * there) get sum_dy AND sum_dyx[k] += sum_p dy*X reduced directly in the epilogue, in fp32 from the unrounded dy;
+ * sum_dyx is left untouched for every other channel.  This is what the executor calls. */
+int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
+                         int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
+                         const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
+                         rxb_stream_t stream);
 /* sum_dyx[c] = sum_p dy[p,c]*X[p,c] for the BatchNorm in front of a convolution, from that convolution's weights and
  * finished weight gradient (fp32 OIHW [Cout][Cin][taps]):  with z = bn_scale*x + bn_shift,
  *   sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap]   (both equal sum_p dL/dA' * A', A' = relu(z)),
@@ -250,8 +260,11 @@ int64_t rxb_launch_count(void);
 void rxb_launch_count_reset(void);
 /* Per-kernel-family timing for bench.py: while enabled every launch is bracketed by CUDA events on its
  * stream.  rxb_profile_collect synchronises, writes milliseconds and launch counts per category
- * (0 stats, 1 loader, 2 conv fwd, 3 conv dgrad, 4 conv wgrad, 5 elementwise, 6 head, 7 optimizer+repack,
- * 8 TTA/assignment; ncat >= 9) and clears the record. */
+ * and clears the record.  Categories (ncat >= 17): 0 stats, 1 loader, 2 dense-layer 1x1 forward, 3 dense-layer 1x1
+ * data gradient, 4 dense-layer 1x1 weight gradient, 5 elementwise (other than 14-16), 6 head, 7 optimizer+repack,
+ * 8 TTA/assignment, 9 dense-layer 3x3 forward, 10 3x3 data gradient, 11 3x3 weight gradient, 12 other forward-style
+ * GEMMs (stem, transitions and their data gradient), 13 other weight gradients (stem, transitions),
+ * 14 bn_bwd_apply, 15 grad_fixup, 16 bn_bwd_finalize. */
 void rxb_profile_enable(int on);
 int rxb_profile_collect(float* ms, long long* launches, int ncat);
 

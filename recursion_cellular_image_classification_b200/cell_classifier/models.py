@@ -293,13 +293,39 @@ class DenseNet121(torch.nn.Module):
             p["synced"] = p is plan
 
 
+def _pretrained_densenet121_state():
+    """ImageNet weights for the trunk, or None: a state_dict file named by RXB_PRETRAINED_DENSENET121 (torchvision
+    densenet121 key names), else torchvision's own download/cache (needs network or a warm cache)."""
+    import os
+    path = os.environ.get("RXB_PRETRAINED_DENSENET121")
+    if path:
+        return torch.load(path, map_location="cpu")
+    try:
+        import torchvision
+        return torchvision.models.densenet121(weights="IMAGENET1K_V1").state_dict()
+    except Exception:
+        return None
+
+
 class TwoSitesNN(DenseNet121):
-    """Reference constructor signature (models.py:8-12); DenseNet-121 trunk per the north star."""
+    """Reference constructor signature (models.py:8-12); DenseNet-121 trunk per the north star.
+    pretrained=True (main.py:43 sets it whenever CUDA is available) loads torchvision's ImageNet densenet121 through
+    the reference's stem surgery (3-channel stem -> channel mean replicated 6x, models.py:24-26; the 1000-class head is
+    dropped); when the weights cannot be found (no network, no RXB_PRETRAINED_DENSENET121 file) it warns and keeps the
+    random initialisation instead of failing, so an unchanged main.py still runs."""
 
     def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None):
-        if pretrained:
-            raise _lib.RxbError("pretrained ImageNet weights need network access; load a state_dict instead")
         super().__init__(nb_classes=nb_classes, device=device)
+        self.pretrained_loaded = False
+        if pretrained:
+            sd = _pretrained_densenet121_state()
+            if sd is None:
+                import warnings
+                warnings.warn("TwoSitesNN(pretrained=True): ImageNet densenet121 weights are not available (no network "
+                              "and RXB_PRETRAINED_DENSENET121 is not set) - continuing from random initialisation")
+            else:
+                self.load_state_dict(sd, strict=False)
+                self.pretrained_loaded = True
 
 
 class DummyClassifier():

@@ -44,9 +44,19 @@ int rxb_conv_fwd(const rxb_conv_desc* d, const void* A_bf16, const void* W_bf16,
 int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16, int ldX,
                       const float* bn_scale, const float* bn_shift, int out_mode, void* out_bf16, float* sum_dy,
                       rxb_stream_t stream) {
+  return rxb_conv_dgrad_bn_ex(d, dOut_bf16, Wt_bf16, X_bf16, ldX, bn_scale, bn_shift, nullptr, nullptr, out_mode,
+                              out_bf16, sum_dy, nullptr, stream);
+}
+
+int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
+                         int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
+                         const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
+                         rxb_stream_t stream) {
   using namespace rxb;
   RXB_CHECK_ARG(d && dOut_bf16 && Wt_bf16 && X_bf16 && bn_scale && bn_shift && out_bf16 && sum_dy,
                 "rxb_conv_dgrad_bn: null pointer");
+  RXB_CHECK_ARG((bn_gamma == nullptr) == (bn_beta == nullptr) && (bn_gamma == nullptr || sum_dyx != nullptr),
+                "rxb_conv_dgrad_bn_ex: bn_gamma, bn_beta and sum_dyx come together");
   RXB_CHECK_ARG(d->Cin > 0 && d->Cin % 8 == 0 && d->ldA >= d->Cin && d->ldA % 8 == 0, "rxb_conv_dgrad_bn: bad Cin/ldA");
   RXB_CHECK_ARG(d->Cout >= 64 && d->Cout % 32 == 0 && d->ldC >= d->Cout && ldX >= d->Cout, "rxb_conv_dgrad_bn: bad Cout");
   RXB_CHECK_ARG(out_mode >= OUT_DY && out_mode <= OUT_G_ACCUM, "rxb_conv_dgrad_bn: bad out_mode");
@@ -61,9 +71,11 @@ int rxb_conv_dgrad_bn(const rxb_conv_desc* d, const void* dOut_bf16, const void*
   p.out_mode = out_mode;
   p.do_stats = 1;
   p.ch_sum = sum_dy;
-  p.ch_sumsq = nullptr;
+  p.ch_sumsq = sum_dyx;
   p.e_scale = bn_scale;
   p.e_shift = bn_shift;
+  p.e_gamma = bn_gamma;
+  p.e_beta = bn_beta;
   return launch_conv_gemm(p, dOut_bf16, d->ldA, Wt_bf16, out_bf16, d->ldC, 0, X_bf16, ldX, d->Cin <= 32 ? 32 : 64, false,
                           as_stream(stream));
 }

@@ -42,7 +42,10 @@ extern long long g_launches;  // kernels enqueued since the last reset (gpu_laun
 // Optional per-launch timing (bench.py's kernel-family breakdown): when enabled, every launcher brackets its
 // kernel with CUDA events on the launching stream; rxb_profile_collect sums them per category.
 enum ProfCat { PROF_STATS = 0, PROF_LOADER, PROF_CONV_FWD, PROF_CONV_DGRAD, PROF_CONV_WGRAD, PROF_ELEMENTWISE,
-               PROF_HEAD, PROF_OPTIM, PROF_TTA, PROF_NCAT };
+               PROF_HEAD, PROF_OPTIM, PROF_TTA,
+               // finer split (rxb.h): 2/3/4 are the dense layers' 1x1 kernels, 5 the remaining elementwise kernels
+               PROF_CONV_FWD_3X3, PROF_CONV_DGRAD_3X3, PROF_CONV_WGRAD_3X3, PROF_CONV_OTHER, PROF_WGRAD_OTHER,
+               PROF_EW_BN_APPLY, PROF_EW_FIXUP, PROF_EW_FINALIZE, PROF_NCAT };
 extern bool g_prof_on;
 struct ProfScope {
   cudaStream_t st;
@@ -60,6 +63,7 @@ inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStre
 // pdl_sync() is the point after which they may touch global memory (the predecessor has completed and flushed).
 // EVERY kernel launched through launch_k must call pdl_sync() before its first global read or write.
 extern bool g_dbg_sync;
+extern bool g_fold_fp32;   // RXB_FOLD_FP32=1: the conv prologues apply the BatchNorm fold in fp32 (default: one packed bf16 FMA)
 extern bool g_pdl;   // RXB_PDL=1 enables the attribute (default off: kernels serialise as usual and pdl_sync() is a no-op)
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -128,6 +132,16 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float bf16_round(float v) {
   return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+// BatchNorm channels whose backward cannot use the W.dW identity (it recovers sum(dy*x) as (W.dW - shift*sum dy)/scale,
+// which cancels catastrophically when |gamma| is small against |beta| and is undefined for gamma == 0): for these the
+// data-gradient epilogue reduces sum(dy) and sum(dy*x) directly.  Freshly initialised networks (gamma = 1, beta = 0)
+// have none; trained / weight-decayed checkpoints do.  One predicate shared by the kernel that reduces and the kernel
+// that consumes.
+__host__ __device__ inline bool bn_degenerate(float gamma, float beta) {
+  const float g = gamma < 0.f ? -gamma : gamma, b = beta < 0.f ? -beta : beta;
+  return g < 1e-3f || g < 0.05f * b;
 }
 
 }  // namespace rxb

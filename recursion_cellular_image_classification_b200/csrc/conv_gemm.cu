@@ -47,12 +47,13 @@ constexpr int kMaxPrologueC = 1024;
 constexpr int kMaxBN = 128;
 
 struct __align__(16) GemmAux {
-  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
-  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
+  float s_scale[kMaxPrologueC + 64];   // prologue fold (fp32; packed to bf16 pairs per thread in the default mode)
+  float s_shift[kMaxPrologueC + 64];
   float e_scale[kMaxBN];
   float e_shift[kMaxBN];
   uint32_t e_thr2[kMaxBN / 2];   // dgrad ReLU mask as a packed-bf16 threshold test: (x ^ sgn) > thr, two columns per word
   uint32_t e_sgn2[kMaxBN / 2];
+  uint32_t e_flag16[kMaxBN / 16];   // dgrad: bit j of word c/16 = column c+j takes direct sum(dy) / sum(dy*x) reductions
   float s_stat[2][kMaxBN];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
@@ -121,7 +122,8 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
 // Rows whose pixel lies outside the image keep the zeros TMA wrote (conv zero padding); boxes entirely
 // inside the image take the path without per-row coordinate arithmetic.
 // relu(x*s + h) on two packed bf16 lanes in ONE instruction (single rounding of the exact fused result; the
-// BatchNorm scale/shift are rounded to bf16 like every other GEMM operand).
+// BatchNorm scale/shift are rounded to bf16 like every other GEMM operand).  RXB_FOLD_FP32=1 selects the fp32
+// variant below instead (fp32 scale/shift, one rounding of the result) - five instructions per pair instead of one.
 __device__ __forceinline__ uint32_t fma_relu_bf16x2(uint32_t x, uint32_t s, uint32_t h) {
   uint32_t d;
   asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
@@ -136,21 +138,45 @@ __device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4]
   v.w = fma_relu_bf16x2(v.w, s[3], h[3]);
   *p = v;
 }
+// fp32 variant: relu(x*s + h) with fp32 scale/shift, ONE rounding to bf16 (cvt.rn.relu.bf16x2.f32 packs two results)
+__device__ __forceinline__ uint32_t fma_relu_f32_pack(uint32_t x, float s0, float h0, float s1, float h1) {
+  const float lo = fmaf(__uint_as_float(x << 16), s0, h0), hi = fmaf(__uint_as_float(x & 0xffff0000u), s1, h1);
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void transform_chunk32(uint4* p, const float (&s)[8], const float (&h)[8]) {
+  uint4 v = *p;
+  v.x = fma_relu_f32_pack(v.x, s[0], h[0], s[1], h[1]);
+  v.y = fma_relu_f32_pack(v.y, s[2], h[2], s[3], h[3]);
+  v.z = fma_relu_f32_pack(v.z, s[4], h[4], s[5], h[5]);
+  v.w = fma_relu_f32_pack(v.w, s[6], h[6], s[7], h[7]);
+  *p = v;
+}
 
-__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const __nv_bfloat16* sc,
-                                                    const __nv_bfloat16* sh, int t, const PixelTiling& til, int box_w,
-                                                    int box_h, int bx, int by, int bb) {
+template <bool FOLD32>
+__device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
+                                                      const PixelTiling& til, int box_w, int box_h, int bx, int by,
+                                                      int bb) {
   const int j = t & 7;
-  // the 8 channels of this thread's chunk: one 16-byte load each for scale and shift (already bf16 pairs)
-  const uint4 s4 = *reinterpret_cast<const uint4*>(sc + j * 8), h4 = *reinterpret_cast<const uint4*>(sh + j * 8);
-  const uint32_t s[4] = {s4.x, s4.y, s4.z, s4.w}, h[4] = {h4.x, h4.y, h4.z, h4.w};
+  // the 8 channels of this thread's chunk: fp32 fold values from shared memory, packed to bf16 pairs in the default mode
+  const float4 sa = *reinterpret_cast<const float4*>(sc + j * 8), sb = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
+  const float4 ha = *reinterpret_cast<const float4*>(sh + j * 8), hb = *reinterpret_cast<const float4*>(sh + j * 8 + 4);
+  const float s32[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+  const float h32[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  const uint32_t s[4] = {pack_bf16x2(s32[0], s32[1]), pack_bf16x2(s32[2], s32[3]), pack_bf16x2(s32[4], s32[5]),
+                         pack_bf16x2(s32[6], s32[7])};
+  const uint32_t h[4] = {pack_bf16x2(h32[0], h32[1]), pack_bf16x2(h32[2], h32[3]), pack_bf16x2(h32[4], h32[5]),
+                         pack_bf16x2(h32[6], h32[7])};
   const int tb = 1 << til.tb_log2;
   const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
   if (interior) {
 #pragma unroll 4
-    for (int row = t >> 3; row < rows; row += kRowsPerIter)
-      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
+    for (int row = t >> 3; row < rows; row += kRowsPerIter) {
+      uint4* ptr = reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4));
+      if (FOLD32) transform_chunk32(ptr, s32, h32); else transform_chunk(ptr, s, h);
+    }
   } else {
     for (int row = t >> 3; row < rows; row += kRowsPerIter) {
       const int r2 = row / box_w;
@@ -159,9 +185,16 @@ __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, con
       const int yi = r2 - bi * box_h;
       const int x = bx + xi, y = by + yi, b = bb + bi;
       if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
-      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
+      uint4* ptr = reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4));
+      if (FOLD32) transform_chunk32(ptr, s32, h32); else transform_chunk(ptr, s, h);
     }
   }
+}
+__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
+                                                    const PixelTiling& til, int box_w, int box_h, int bx, int by, int bb,
+                                                    int fold_fp32) {
+  if (fold_fp32) transform_box_sw128_t<true>(tile, rows, sc, sh, t, til, box_w, box_h, bx, by, bb);
+  else transform_box_sw128_t<false>(tile, rows, sc, sh, t, til, box_w, box_h, bx, by, bb);
 }
 
 // Column sums over the 32 rows held by a warp for 32 columns: lane L ends with the total of column L.
@@ -333,13 +366,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        aux->s_scale[c] = __float2bfloat16_rn(sc);
-        aux->s_shift[c] = __float2bfloat16_rn(sh);
+        aux->s_scale[c] = sc;
+        aux->s_shift[c] = sh;
       }
     } else {
       for (int c = threadIdx.x; c < padded; c += kConvThreads) {
-        aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
-        aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
+        aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
+        aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
       }
     }
   }
@@ -363,6 +396,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       aux->e_thr2[c2] = thr;
       aux->e_sgn2[c2] = sg;
+    }
+    for (int w16 = threadIdx.x; w16 < kMaxBN / 16; w16 += kConvThreads) {
+      uint32_t fl = 0;
+      if (p.e_gamma != nullptr)
+        for (int j = 0; j < 16; ++j) {
+          const int c = n0 + w16 * 16 + j;
+          if (c < p.n_total && bn_degenerate(p.e_gamma[c], p.e_beta[c])) fl |= 1u << j;
+        }
+      aux->e_flag16[w16] = fl;
     }
   }
   ptx::tcgen05_fence_before();
@@ -633,6 +675,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (cc >> 1));
             const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + cc);
             ptx::tmem_ld_wait();
+            const uint32_t fl16 = aux->e_flag16[cc >> 4];
+            if (fl16 != 0) {
+              // degenerate BatchNorm channels (rare, warp-uniform): sum(dy) and sum(dy*x) of the UNSCALED fp32 dy,
+              // reduced over the warp's 32 pixel rows and added to the CTA's shared totals
+#pragma unroll
+              for (int jc = 0; jc < 16; ++jc) {    // unrolled: register arrays are indexed by constants only
+                if (!((fl16 >> jc) & 1u)) continue;
+                const uint32_t thw = aux->e_thr2[(cc + jc) >> 1], sgw = aux->e_sgn2[(cc + jc) >> 1];
+                bool m0, m1;
+                gt_bf16x2(xin[jc >> 1] ^ sgw, thw, m0, m1);
+                const bool m = (jc & 1) ? m1 : m0;
+                const float xv = (jc & 1) ? bf16_hi(xin[jc >> 1]) : bf16_lo(xin[jc >> 1]);
+                const float d = (m && row_valid) ? __uint_as_float(r16[jc]) : 0.f;
+                const float s1 = warp_sum(d), s2 = warp_sum(d * xv);
+                if (lane == 0) {
+                  atomicAdd(&aux->s_stat[0][cc + jc], s1);
+                  atomicAdd(&aux->s_stat[1][cc + jc], s2);
+                }
+              }
+            }
             uint32_t pk[8];
 #pragma unroll
             for (int i4 = 0; i4 < 2; ++i4) {
@@ -727,6 +789,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (!narrow && p.do_stats && p.mma_stats) {
+      if (dgrad) asm volatile("bar.sync 3, %0;" ::"r"((uint32_t)n_epi_threads) : "memory");   // s_stat of both groups
       // per-channel totals of this CTA from TMEM: lane = channel; Gram diagonal and the sums column
       if (g2 == 0 && grp == 0 && my_tiles > 0) {
         ptx::mbar_wait(&aux->stats_done, 0, 12);
@@ -737,7 +800,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tmem_ld_wait();
         float total = __uint_as_float(s16[0]);
         if (dgrad) {
-          if (p.out_mode != OUT_DY) {  // the staged value was es*dy
+          if ((aux->e_flag16[row >> 4] >> (row & 15)) & 1u) {
+            // degenerate channel: the direct fp32 reductions replace the tensor-pipe sum of the (scaled) staged tile
+            total = aux->s_stat[0][row];
+            const float dyx = aux->s_stat[1][row];
+            if (ch < p.n_total && dyx != 0.f) atomicAdd(p.ch_sumsq + ch, dyx);
+          } else if (p.out_mode != OUT_DY) {  // the staged value was es*dy
             const float es = aux->e_scale[row];
             total = es != 0.f ? total / es : 0.f;
           }
@@ -774,7 +842,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
             transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
-                                t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
+                                t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0, p.fold_fp32);
             ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
             __syncwarp();
             if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&aux->xform[stage]);
@@ -797,8 +865,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 // Weight gradient
 struct __align__(16) WgradAux {
-  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
-  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
+  float s_scale[kMaxPrologueC + 64];   // prologue fold (fp32; packed to bf16 pairs per thread in the default mode)
+  float s_shift[kMaxPrologueC + 64];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -864,8 +932,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.prologue) {
     const int padded = p.boxes_per_tap * p.bkc;
     for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
-      aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
-      aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
+      aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
+      aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
     }
   }
   ptx::tcgen05_fence_before();
@@ -1147,7 +1215,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ay += ty - p.pad_y;
             }
             transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale + c0,
-                                aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0);
+                                aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0, p.fold_fp32);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -1199,6 +1267,9 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
   // dgrad, and stores of >= 128 channels with statistics, run 128-wide N tiles whose column sums come from the
   // tensor pipe (columns past n_total are zero weights / clipped stores)
+  p.fold_fp32 = g_fold_fp32 ? 1 : 0;
+  if (p.e_gamma != nullptr && (p.e_beta == nullptr || p.ch_sumsq == nullptr))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: e_gamma needs e_beta and ch_sumsq");
   p.bn = (dgrad || p.n_total >= kMaxBN) ? kMaxBN : p.n_total;
   p.mma_stats = (dgrad || (p.do_stats && p.bn == kMaxBN)) ? 1 : 0;
   static const int dbg_dgrad = getenv("RXB_DBG_DGRAD") ? atoi(getenv("RXB_DBG_DGRAD")) : 0;   // timing experiments only
@@ -1331,7 +1402,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     p.dbg = tl_dev;
   }
 
-  RXB_PROF(stream, p.epi_mode == EPI_STORE ? PROF_CONV_FWD : PROF_CONV_DGRAD);
+  RXB_PROF(stream, dgrad ? (taps > 1 ? PROF_CONV_DGRAD_3X3 : PROF_CONV_DGRAD)
+                         : !prologue ? PROF_CONV_OTHER : (taps > 1 ? PROF_CONV_FWD_3X3 : PROF_CONV_FWD));
 #define RXB_LAUNCH_GEMM(BK_, PRO_, EPI_)                                                                        \
   do {                                                                                                          \
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1377,6 +1449,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   if (!(p.n == 32 || (p.n % 64 == 0 && p.n >= 64 && p.n <= 256)))
     return set_error(RXB_ERR_INVALID, "conv_wgrad: n=%d must be 32 or a multiple of 64 up to 256", p.n);
   const int taps = p.taps_x * p.taps_y;
+  p.fold_fp32 = g_fold_fp32 ? 1 : 0;
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
   p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;
@@ -1474,7 +1547,7 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
     }
   }
   RXB_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RXB_PROF(stream, PROF_CONV_WGRAD);
+  RXB_PROF(stream, !p.prologue ? PROF_WGRAD_OTHER : (taps > 1 ? PROF_CONV_WGRAD_3X3 : PROF_CONV_WGRAD));
   static const int dbg_tl = getenv("RXB_DBG_TIMELINE") ? atoi(getenv("RXB_DBG_TIMELINE")) : 0;
   static unsigned long long* tl_dev = nullptr;
   p.dbg = nullptr;

@@ -47,8 +47,8 @@ struct GemmParams {
   int out_mode;
   int do_stats;
   float* ch_sum;    // [n_total] (EPI_STORE: of the channel range being written; DGRAD: sum dy)
-  float* ch_sumsq;  // [n_total] (EPI_STORE: sum of squares; DGRAD: unused - sum(dy*x) follows from W.dW, see
-                    //  bn_bwd_finalize)
+  float* ch_sumsq;  // [n_total] (EPI_STORE: sum of squares; DGRAD: sum(dy*x), written ONLY for the channels
+                    //  bn_degenerate(e_gamma, e_beta) flags - for all others it follows from W.dW, see bn_bwd_finalize)
   // prologue (A := relu(A*scale + shift)), indexed by A channel
   const float* scale;
   const float* shift;
@@ -56,7 +56,10 @@ struct GemmParams {
   // EPI_DGRAD_BN: folded BatchNorm of the consumer, per N channel
   const float* e_scale;
   const float* e_shift;
+  const float* e_gamma;   // optional (with e_beta and ch_sumsq): BatchNorm weight / bias per N channel; channels that
+  const float* e_beta;    // bn_degenerate() flags get direct sum(dy) / sum(dy*x) reductions in the epilogue
   // ---- filled by launch_conv_gemm
+  int fold_fp32;    // prologue arithmetic: 0 = one packed bf16 fma.relu per channel pair, 1 = fp32 FMA, one rounding
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;
   int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
@@ -102,6 +105,7 @@ struct WgradParams {
   unsigned long long* dbg;  // development timeline of CTA (0,0) (RXB_DBG_TIMELINE), else nullptr
   int bulk_out;         // 1: result staged in shared memory and added to dW by cp.reduce.async.bulk (else fp32 atomics)
   int bulk_bufs;        // staging buffers for the 1x1 bulk path (1 or 2)
+  int fold_fp32;        // prologue arithmetic, as GemmParams::fold_fp32 (filled by the launcher)
 };
 // A: bf16 [B,H,W,ldA]; dOut: bf16 [B,H,W,ldD].
 int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* dOut, long long ldD,

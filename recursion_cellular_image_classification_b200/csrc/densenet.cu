@@ -297,6 +297,7 @@ static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfl
   p.do_stats = 1;
   p.ch_sum = bn.dsum; p.ch_sumsq = bn.dsq;
   p.e_scale = bn.fold.scale; p.e_shift = bn.fold.shift;
+  p.e_gamma = n.params + bn.gamma_off; p.e_beta = n.params + bn.beta_off;   // degenerate channels: direct reductions
   return launch_conv_gemm(p, dOut, ldD, n.arena + cv.dgrad_off, out, ldc, 0, X, ldx, cout <= 32 ? 32 : 64, false, st);
 }
 
@@ -411,7 +412,7 @@ static int backward_head(rxb_dn121& n, cudaStream_t st) {
   RXB_TRY(bn_relu_bwd_to_G(1, n.dfeat, b3.X, b3.Ctot, c.B, b3.H, b3.W, b3.Ctot, n.bn5.fold, b3.G, n.bn5.dsum,
                            n.bn5.dsq, st));
   RXB_TRY(bn_bwd_finalize(0, nullptr, nullptr, 0, 0, n.bn5.dsum, n.bn5.dsq, n.bn5.fold, (float)b3.M, b3.Ctot,
-                          n.grads + n.bn5.gamma_off, n.grads + n.bn5.beta_off, b3.corrA, b3.corrB, st));
+                          n.grads + n.bn5.gamma_off, n.grads + n.bn5.beta_off, b3.corrA, b3.corrB, nullptr, nullptr, st));
   return RXB_OK;
 }
 
@@ -431,7 +432,8 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
                           n.dy2, kBott, st));
     RXB_TRY(bn_bwd_finalize(1, n.params + L.c2.w_off, n.grads + L.c2.w_off, kGrowth, 9, L.bn2.dsum, L.bn2.dsq,
                             L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
-                            n.grads + L.bn2.beta_off, nullptr, nullptr, st));
+                            n.grads + L.bn2.beta_off, nullptr, nullptr, n.params + L.bn2.gamma_off,
+                            n.params + L.bn2.beta_off, st));
     RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st));  // dy2 := dY
     // 1x1 conv
     RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, 1, 0, &L.bn1.fold, n.dy2, kBott, kBott,
@@ -440,7 +442,8 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
                           OUT_G_ACCUM, blk.G, blk.Ctot, st));
     RXB_TRY(bn_bwd_finalize(0, n.params + L.c1.w_off, n.grads + L.c1.w_off, kBott, 1, L.bn1.dsum, L.bn1.dsq,
                             L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
-                            n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, st));
+                            n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, n.params + L.bn1.gamma_off,
+                            n.params + L.bn1.beta_off, st));
   }
   // exact gradient of the block's input channels
   RXB_TRY(grad_fixup(blk.G, blk.X, blk.Ctot, blk.M, 0, blk.C0, closing.fold.mean, closing.fold.rstd, blk.corrA,
@@ -462,13 +465,13 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
     RXB_TRY(bn_relu_bwd_to_G(0, n.dP, pb.X, pb.Ctot, c.B, pb.H, pb.W, pb.Ctot, t.bn.fold, pb.G, t.bn.dsum, t.bn.dsq, st));
     RXB_TRY(bn_bwd_finalize(0, nullptr, nullptr, 0, 0, t.bn.dsum, t.bn.dsq, t.bn.fold, (float)pb.M, pb.Ctot,
                             n.grads + t.bn.gamma_off,
-                            n.grads + t.bn.beta_off, pb.corrA, pb.corrB, st));
+                            n.grads + t.bn.beta_off, pb.corrA, pb.corrB, nullptr, nullptr, st));
   } else {
     RXB_TRY(stem_pool_bwd(n.dX0, n.pool_idx, n.S0, c.B, n.Hs, n.Ws, n.bn0.fold, n.dy0, n.bn0.dsum, n.bn0.dsq, st));
     const float cnt = (float)((long long)c.B * n.Hs * n.Ws);
     RXB_TRY(bn_bwd_finalize(1, nullptr, nullptr, 0, 0, n.bn0.dsum, n.bn0.dsq, n.bn0.fold, cnt, 64,
                             n.grads + n.bn0.gamma_off,
-                            n.grads + n.bn0.beta_off, nullptr, nullptr, st));
+                            n.grads + n.bn0.beta_off, nullptr, nullptr, nullptr, nullptr, st));
     RXB_TRY(bn_bwd_apply(n.dy0, n.S0, (long long)c.B * n.Hs * n.Ws, 64, n.bn0.fold, n.bn0.dsum, n.bn0.dsq, st));
     RXB_TRY(conv_wgrad_any(c.B, n.Hs, n.Ws, static_cast<const __nv_bfloat16*>(input), 32, 32, 4, 2, nullptr, n.dy0, 64,
                            64, n.grads + n.conv0.w_off, 1, st));

@@ -314,30 +314,35 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
 }
 
 // ------------------------------------------------------------------------------------------------ BN bwd finalize
-// sum_p dy*x of input channel c from the finished weight gradient of the conv that consumed relu(scale*x+shift):
-// sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap] with z = scale*x+shift, so sum dy*x = (W.dW - shift*sum dy)/scale.
+// sum_p dy*x of input channel c from the finished weight gradient of the conv that consumed A' = relu(scale*x+shift):
+// sum_p dy*A' = sum_{k,tap} W[k][c][tap]*dW[k][c][tap] (both sides equal sum_p dL/dA' * A'), and on the ReLU's support
+// A' = scale*x + shift, so sum dy*x = (W.dW - shift*sum dy)/scale.  The identity is evaluated with the operands the
+// kernels really used: W rounded to bf16 (the GEMM operand), scale/shift rounded to bf16 unless the prologues fold in
+// fp32 (fold_fp32) - otherwise the 2^-9 operand mismatch is amplified by 1/scale.
 // One warp per channel (the K*taps products are strided through the OIHW tensors); every lane returns the result.
 __device__ __forceinline__ float sum_dyx_from_wdw(const float* __restrict__ W, const float* __restrict__ dW, int K, int C,
-                                                  int taps, int c, float es, float eh, float sum_dy, int lane) {
+                                                  int taps, int c, float es, float eh, float sum_dy, int lane,
+                                                  int fold_fp32) {
   float t = 0.f;
   const int n = K * taps;
   for (int i = lane; i < n; i += 32) {
     const int k = i / taps, tp = i - k * taps;
     const long long at = ((long long)k * C + c) * taps + tp;
-    t = fmaf(__ldg(W + at), __ldg(dW + at), t);
+    t = fmaf(bf16_round(__ldg(W + at)), __ldg(dW + at), t);
   }
   t = warp_sum(t);
+  if (!fold_fp32) { es = bf16_round(es); eh = bf16_round(eh); }
   return es != 0.f ? (t - eh * sum_dy) / es : 0.f;
 }
 
 __global__ void __launch_bounds__(256)
 sum_dyx_from_wdw_kernel(const float* __restrict__ W, const float* __restrict__ dW, int K, int C, int taps,
                         const float* __restrict__ scale, const float* __restrict__ shift,
-                        const float* __restrict__ sum_dy, float* __restrict__ out) {
+                        const float* __restrict__ sum_dy, float* __restrict__ out, int fold_fp32) {
   pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
-  const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane);
+  const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane, fold_fp32);
   if (lane == 0) out[c] = r;
 }
 
@@ -346,14 +351,17 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __restrict__ dW, int K, int taps,
                        float* __restrict__ dsum, float* __restrict__ dsq, BnFold f, float count, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ corrA,
-                       float* __restrict__ corrB) {
+                       float* __restrict__ corrB, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       int fold_fp32) {
   pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   const float s = dsum[c];
   float q;
   if (W) {
-    const float raw = sum_dyx_from_wdw(W, dW, K, C, taps, c, f.scale[c], f.shift[c], s, lane);
+    // degenerate channels: the data-gradient epilogue reduced sum dy*x directly into dsq (conv_gemm.cu)
+    const bool direct = gamma != nullptr && bn_degenerate(gamma[c], beta[c]);
+    const float raw = direct ? dsq[c] : sum_dyx_from_wdw(W, dW, K, C, taps, c, f.scale[c], f.shift[c], s, lane, fold_fp32);
     q = f.rstd[c] * (raw - f.mean[c] * s);                       // sum dy*xhat
   } else {
     q = dsq[c];
@@ -372,10 +380,11 @@ bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __res
 }
 
 int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, float* dsum, float* dsq, BnFold f,
-                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, cudaStream_t st) {
-  RXB_PROF(st, PROF_ELEMENTWISE);
+                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, const float* gamma,
+                    const float* beta, cudaStream_t st) {
+  RXB_PROF(st, PROF_EW_FINALIZE);
   RXB_CUDA(launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, mode, W, dW, K, taps, dsum, dsq, f, count, C, dgamma, dbeta,
-                                                        corrA, corrB));
+                                                        corrA, corrB, gamma, beta, g_fold_fp32 ? 1 : 0));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -436,7 +445,7 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
                  const float* m2, cudaStream_t st) {
   if (C % 8 || kEwThreads % (C / 8)) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must divide into the block", C);
-  RXB_PROF(st, PROF_ELEMENTWISE);
+  RXB_PROF(st, PROF_EW_BN_APPLY);
   const int rows_per_block = kEwThreads / (C / 8);
   RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2));
   RXB_LAUNCH_OK();
@@ -472,7 +481,7 @@ grad_fixup_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __re
 int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long M, int c0, int nch,
                const float* mean, const float* rstd, const float* corrA, const float* corrB, __nv_bfloat16* dst,
                cudaStream_t st) {
-  RXB_PROF(st, PROF_ELEMENTWISE);
+  RXB_PROF(st, PROF_EW_FIXUP);
   RXB_CUDA(launch_k(grad_fixup_kernel, dim3(ew_grid(M * (nch / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st, G, X, ld, M, c0, nch, mean, rstd,
                                                                                  corrA, corrB, dst));
   RXB_LAUNCH_OK();
@@ -718,7 +727,8 @@ int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* j
 int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
                             const float* shift, const float* sum_dy, float* out, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  RXB_CUDA(launch_k(sum_dyx_from_wdw_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, W, dW, K, C, taps, scale, shift, sum_dy, out));
+  RXB_CUDA(launch_k(sum_dyx_from_wdw_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, W, dW, K, C, taps, scale, shift, sum_dy, out,
+                    g_fold_fp32 ? 1 : 0));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

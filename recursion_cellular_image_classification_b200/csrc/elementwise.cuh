@@ -47,9 +47,11 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
 // When W/dW are given (the conv that consumed relu(bn(x)), fp32 OIHW [K][C][taps] weights and their finished
 // gradient), dsq is not read: with z = scale*x+shift and dz = dy,  sum_p dy*z = sum_{k,tap} W*dW  per input
 // channel (both sides equal sum_p dL/dA' * A'), hence sum dy*x = (W.dW - shift*sum dy)/scale.  The dgrad kernel
-// therefore only reduces sum dy.
+// therefore only reduces sum dy - except for the channels bn_degenerate(gamma, beta) flags (gamma/beta: the
+// BatchNorm's own weight and bias, may be null), whose sum dy*x the dgrad epilogue reduced directly into dsq.
 int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, float* dsum, float* dsq, BnFold f,
-                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, cudaStream_t st);
+                    float count, int C, float* dgamma, float* dbeta, float* corrA, float* corrB, const float* gamma,
+                    const float* beta, cudaStream_t st);
 
 // out[c] = sum_p dy*x per input channel from W.dW (see above); the standalone form behind rxb_bn_sum_dyx_from_wdw.
 int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,

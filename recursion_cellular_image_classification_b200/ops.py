@@ -303,12 +303,15 @@ def conv_wgrad(A, dOut, Cin, Cout, taps=(1, 1), pad=(0, 0), scale=None, shift=No
 OUT_DY, OUT_G_WRITE, OUT_G_ACCUM = 0, 1, 2
 
 
-def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=None, Cin=None, pad=(0, 0)):
+def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=None, Cin=None, pad=(0, 0),
+                  bn_gamma=None, bn_beta=None):
     """Data gradient fused with the ReLU/BatchNorm backward of the layer that produced the conv input.
     dOut bf16 [B,H,W,ldD]; Wt bf16 [ty,tx,Cout,Cin] = the dgrad operand (tap-flipped, transposed weights);
     X bf16 [B,H,W,ldX] raw activation whose relu(bn(.)) fed the conv (channels 0..Cout).
     Returns (out bf16 [B,H,W,ldC], sum_dy f32 [Cout]); the second BatchNorm-backward reduction comes from
-    bn_sum_dyx_from_wdw."""
+    bn_sum_dyx_from_wdw.  With bn_gamma / bn_beta (the BatchNorm's weight and bias, f32 [Cout]) the channels the
+    library flags as degenerate get direct reductions and a third value is returned: sum_dyx f32 [Cout] (zero for
+    the channels that were not flagged)."""
     require_gpu()
     dOut = _cuda(dOut, torch.bfloat16)
     Wt = _cuda(Wt, torch.bfloat16)
@@ -321,6 +324,12 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     ldC = out.shape[-1]
     s1 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
     d = _desc(B, H, W, Cin, ldD, Cout, ldC, 0, (ty, tx), pad, False, True)
+    if bn_gamma is not None:
+        s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
+        check(load().rxb_conv_dgrad_bn_ex(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1],
+                                          ptr(_cuda(bn_scale)), ptr(_cuda(bn_shift)), ptr(_cuda(bn_gamma)),
+                                          ptr(_cuda(bn_beta)), out_mode, ptr(out), ptr(s1), ptr(s2), stream_ptr()))
+        return out, s1, s2
     check(load().rxb_conv_dgrad_bn(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1], ptr(_cuda(bn_scale)),
                                    ptr(_cuda(bn_shift)), out_mode, ptr(out), ptr(s1), stream_ptr()))
     return out, s1

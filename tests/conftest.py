@@ -23,4 +23,9 @@ def cuda():
     import torch
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device is visible (there is no CPU fallback)")
+    # the torch oracle on the device must be genuine fp32: cuDNN / cuBLAS default to TF32 (10-bit mantissa) for
+    # float32 convolutions and matmuls, which is bf16-grade noise in the thing we measure against
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
     return torch.device("cuda:0")

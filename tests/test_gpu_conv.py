@@ -45,6 +45,10 @@ CASES = [
     (1, 24, 72, 128, 128, 32, 3, True),      # x-merged tiles clipped in x (72 = 5*14 + 2) with three tile rows
     (2, 20, 60, 128, 128, 32, 3, False),     # x-merged, H not a multiple of the 8-row tile
     (1, 40, 72, 32, 32, 64, 4, False),       # stem geometry with a full-halo box clipped on every side
+    # the benchmark's regime: many tiles per persistent CTA (2048 tiles / 148 CTAs ~ 14), so the pipeline stages, the
+    # two accumulator stages and both staging buffers wrap several times
+    (16, 128, 128, 224, 256, 128, 1, True),  # last dense layer of block 1
+    (16, 128, 128, 128, 128, 32, 3, True),   # x-merged 3x3, 2960 tiles / 148 CTAs = 20 per CTA
 ]
 
 
@@ -93,6 +97,8 @@ WG_CASES = [
     (2, 64, 64, 128, 128, 32, 3, True),      # full-halo dOut box, a filter row's taps as one N = 96 MMA
     (1, 20, 28, 128, 128, 32, 3, True),      # ... image not a multiple of the 8x16 tile
     (2, 32, 32, 1024, 1024, 128, 1, True),   # 8 channel chunks: dOut tile shared by the chunks of a CTA
+    (16, 128, 128, 224, 256, 128, 1, True),  # benchmark regime: ~14 pixel tiles per CTA, pipeline wraps
+    (16, 128, 128, 128, 128, 32, 3, True),
 ]
 
 
@@ -130,6 +136,11 @@ DG_CASES = [
     (3, 8, 8, 128, 224, 256, 1, 1),
     (2, 64, 64, 32, 128, 128, 3, 0),
     (1, 128, 128, 128, 160, 256, 1, 2),
+    # benchmark regime: ~14 tiles per CTA, so every in-place activation/staging buffer (four for 1x1, two for 3x3) is
+    # reused several times by each epilogue group
+    (16, 128, 128, 128, 224, 256, 1, 2),
+    (16, 128, 128, 32, 128, 128, 3, 0),
+    (16, 128, 128, 128, 224, 256, 1, 0),
 ]
 
 
@@ -202,3 +213,72 @@ def test_bn_backward_sums_from_wdw(cuda, k, Cin, Cout):
     np.testing.assert_allclose(s1.cpu().numpy(), ref_s1.numpy(), rtol=4e-3, atol=4e-3 * scale1)
     scale2 = (dy * x.detach()).abs().sum((0, 2, 3)).max().item()
     np.testing.assert_allclose(s2.cpu().numpy(), ref_s2.numpy(), rtol=1e-2, atol=1e-2 * scale2)
+
+
+@pytest.mark.parametrize("kind,nx", [("1x1", None), ("1x1", "3"), ("3x3", None), ("3x3", "3")])
+def test_dgrad_repeat_launch_stress(cuda, kind, nx):
+    """200 identical launches of the fused data-gradient kernel at ~14 tiles per CTA: bit-identical output every time
+    (tools/stress_dgrad.py), for the shipped buffer count and for the odd count (RXB_DBG_NX=3, per-group barriers)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if nx is not None:
+        env["RXB_DBG_NX"] = nx
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_dgrad.py"), "--iters", "200", "--kind", kind],
+                       capture_output=True, text=True, env=env, timeout=300)
+    print(p.stdout.strip())
+    assert p.returncode == 0, p.stdout + p.stderr
+    res = json.loads(p.stdout.strip().splitlines()[-1])
+    assert res["mismatching_launches"] == 0 and res["tiles_per_cta"] > 10
+
+
+@pytest.mark.parametrize("k,out_mode", [(1, 2), (3, 0)])
+def test_dgrad_direct_reductions_for_degenerate_channels(cuda, k, out_mode):
+    """Channels whose BatchNorm weight is tiny, zero or small against its bias get sum(dy) and sum(dy*x) reduced
+    directly in the epilogue (fp32, unscaled dy) — exact even where scale = gamma*rstd is 0 and the staged value
+    scale*dy carries no information; every other channel keeps the tensor-pipe sum and leaves sum_dyx untouched."""
+    B, H, W = 3, 24, 20
+    Cd, Cx = (128, 160) if k == 1 else (32, 128)
+    gen = torch.Generator().manual_seed(41 + k)
+    dOut = _rand_bf16((B, H, W, Cd), gen)
+    Wt = _rand_bf16((Cx, Cd, k, k), gen, scale=(Cd * k * k) ** -0.5)
+    X = _rand_bf16((B, H, W, Cx), gen)
+    gamma = torch.rand(Cx, generator=gen) + 0.5
+    beta = torch.randn(Cx, generator=gen) * 0.3
+    gamma[3], gamma[17], gamma[64], gamma[100] = 0.0, 1e-4, -2e-4, 0.01
+    beta[100] = 0.9                                     # |gamma| < 0.05 |beta|
+    beta[3] = 0.25                                      # gamma = 0, positive shift: the ReLU passes every pixel
+    flagged = [3, 17, 64, 100]
+    rstd = torch.rand(Cx, generator=gen) + 0.5
+    mean = torch.randn(Cx, generator=gen) * 0.1
+    s = gamma * rstd
+    h = beta - mean * s
+    G0 = _rand_bf16((B, H, W, Cx), gen)
+    pad = k // 2
+    acc = _ref_conv(dOut, Wt, pad)
+    xv = X.float()
+    dy = acc * ((xv * s + h) > 0)
+    ref = dy if out_mode == 0 else G0.float() + s * dy
+    out = G0.clone().to(cuda)
+    out, s1, s2 = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
+                                    out_mode=out_mode, out=out, pad=(pad, pad), bn_gamma=gamma.to(cuda),
+                                    bn_beta=beta.to(cuda))
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item()
+    d64 = dy.double().reshape(-1, Cx)
+    x64 = xv.double().reshape(-1, Cx)
+    tol1 = 4e-3 * d64.abs().sum(0).max().item()
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=4e-3, atol=tol1)
+    want2 = (d64 * x64).sum(0).numpy()
+    got2 = s2.cpu().numpy()
+    others = [c for c in range(Cx) if c not in flagged]
+    assert (got2[others] == 0).all()
+    # direct fp32 reductions: far tighter than the bf16-staged sums
+    np.testing.assert_allclose(s1.cpu().numpy()[flagged], d64.sum(0).numpy()[flagged], rtol=1e-4,
+                               atol=1e-5 * d64.abs().sum(0).max().item())
+    np.testing.assert_allclose(got2[flagged], want2[flagged], rtol=1e-4, atol=1e-5 * (d64 * x64).abs().sum(0).max().item())
+    assert abs(d64.sum(0)[3].item()) > 0                  # the gamma = 0 channel really has a non-zero sum(dy)

@@ -345,8 +345,33 @@ def test_densenet_parameter_layout_is_torchvisions(tmp_path):
     assert torch.equal(net2.flat.data, net.flat.data) and torch.equal(net2.bn_buffers, net.bn_buffers)
     with pytest.raises(KeyError):
         net2.load_state_dict({k: v for k, v in sd.items() if k != "classifier.bias"})
-    with pytest.raises(_lib.RxbError):
-        TwoSitesNN(pretrained=True, nb_classes=1108, device="cpu")
+    # pretrained=True (what main.py:43 asks for on a GPU box): weights from the file RXB_PRETRAINED_DENSENET121 names go
+    # through the stem surgery and keep our 1108-way head; without any source it warns and stays at random init
+    import torchvision
+    tv = torchvision.models.densenet121(weights=None)
+    ckpt = str(tmp_path / "densenet121_imagenet_like.pth")
+    torch.save(tv.state_dict(), ckpt)
+    import os
+    os.environ["RXB_PRETRAINED_DENSENET121"] = ckpt
+    try:
+        net3 = TwoSitesNN(pretrained=True, nb_classes=1108, device="cpu")
+    finally:
+        del os.environ["RXB_PRETRAINED_DENSENET121"]
+    assert net3.pretrained_loaded
+    assert torch.equal(net3.view("features.conv0.weight"),
+                       torch.stack([tv.features.conv0.weight.detach().mean(1)] * 6, dim=1))
+    assert torch.equal(net3.view("features.denseblock3.denselayer7.conv2.weight"),
+                       tv.features.denseblock3.denselayer7.conv2.weight.detach())
+    assert tuple(net3.view("classifier.weight").shape) == (1108, 1024)
+    from recursion_cellular_image_classification_b200.cell_classifier import models as M
+    real = M._pretrained_densenet121_state
+    M._pretrained_densenet121_state = lambda: None                  # "no network, no file"
+    try:
+        with pytest.warns(UserWarning, match="not available"):
+            net4 = TwoSitesNN(pretrained=True, nb_classes=1108, device="cpu")
+    finally:
+        M._pretrained_densenet121_state = real
+    assert not net4.pretrained_loaded
     # torch.optim.SGD as main.py:89-93 builds it sees one flat parameter
     assert [p.numel() for p in net.parameters()] == [8098964]
     if not torch.cuda.is_available():
