@@ -62,6 +62,11 @@ def run_dgrad(B, H, W, Cd, Cx, ldX, k, out_mode):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "one":
+        # one shape, e.g. for RXB_DBG_TIMELINE=1:  bench_conv.py one fwd|wgrad|dgrad <args of run / run_wgrad / run_dgrad>
+        kind, a = sys.argv[2], [int(v) for v in sys.argv[3:]]
+        {"fwd": run, "wgrad": run_wgrad, "dgrad": run_dgrad}[kind](*a)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prof":
         # one launch of each representative block-1 shape (for ncu); optional batch as argv[2]
         B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
