@@ -46,20 +46,30 @@ constexpr int kSumCol = 384;      // TMEM columns [384,400): running column sums
 constexpr int kMaxPrologueC = 1024;
 constexpr int kMaxBN = 128;
 
+// Prologue fold in shared memory: bf16 pairs (the operands of fma.rn.relu.bf16x2, default) or fp32 (fold_fp32); one
+// array sized for fp32 serves both, the transform reads it in the mode's own type.
+struct FoldArray {
+  float v[kMaxPrologueC + 64];
+  __device__ __forceinline__ void set(int c, float x, int fold_fp32) {
+    if (fold_fp32) v[c] = x; else reinterpret_cast<__nv_bfloat16*>(v)[c] = __float2bfloat16_rn(x);
+  }
+};
+
 struct __align__(16) GemmAux {
-  float s_scale[kMaxPrologueC + 64];   // prologue fold (fp32; packed to bf16 pairs per thread in the default mode)
-  float s_shift[kMaxPrologueC + 64];
+  FoldArray s_scale;
+  FoldArray s_shift;
   float e_scale[kMaxBN];
   float e_shift[kMaxBN];
   uint32_t e_thr2[kMaxBN / 2];   // dgrad ReLU mask as a packed-bf16 threshold test: (x ^ sgn) > thr, two columns per word
   uint32_t e_sgn2[kMaxBN / 2];
   uint32_t e_flag16[kMaxBN / 16];   // dgrad: bit j of word c/16 = column c+j takes direct sum(dy) / sum(dy*x) reductions
+  uint32_t e_flag_any4[4];          // OR of e_flag16 per 32 columns (all 0 for every freshly initialised network)
   float s_stat[2][kMaxBN];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[4];    // per TMEM accumulator stage (p.n_acc = 2, or 4 for the narrow store epilogue)
+  uint64_t tmem_empty[4];
   uint64_t epi_in_full[4][2];   // [buffer][epilogue group that will consume the tile]: each barrier has ONE waiting
                                 // group that observes every one of its phases (a parity wait tells only adjacent
                                 // phases apart, so two groups must not alternate on one barrier)
@@ -154,20 +164,27 @@ __device__ __forceinline__ void transform_chunk32(uint4* p, const float (&s)[8],
   *p = v;
 }
 
+// `c0` = first channel of the k-block inside the fold arrays.
 template <bool FOLD32>
-__device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
-                                                      const PixelTiling& til, int box_w, int box_h, int bx, int by,
-                                                      int bb) {
+__device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, const FoldArray& sc, const FoldArray& sh,
+                                                      int c0, int t, const PixelTiling& til, int box_w, int box_h, int bx,
+                                                      int by, int bb) {
   const int j = t & 7;
-  // the 8 channels of this thread's chunk: fp32 fold values from shared memory, packed to bf16 pairs in the default mode
-  const float4 sa = *reinterpret_cast<const float4*>(sc + j * 8), sb = *reinterpret_cast<const float4*>(sc + j * 8 + 4);
-  const float4 ha = *reinterpret_cast<const float4*>(sh + j * 8), hb = *reinterpret_cast<const float4*>(sh + j * 8 + 4);
-  const float s32[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-  const float h32[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
-  const uint32_t s[4] = {pack_bf16x2(s32[0], s32[1]), pack_bf16x2(s32[2], s32[3]), pack_bf16x2(s32[4], s32[5]),
-                         pack_bf16x2(s32[6], s32[7])};
-  const uint32_t h[4] = {pack_bf16x2(h32[0], h32[1]), pack_bf16x2(h32[2], h32[3]), pack_bf16x2(h32[4], h32[5]),
-                         pack_bf16x2(h32[6], h32[7])};
+  // the 8 channels of this thread's chunk
+  float s32[8], h32[8];
+  uint32_t s[4], h[4];
+  if (FOLD32) {
+    const float4 sa = *reinterpret_cast<const float4*>(sc.v + c0 + j * 8), sb = *reinterpret_cast<const float4*>(sc.v + c0 + j * 8 + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(sh.v + c0 + j * 8), hb = *reinterpret_cast<const float4*>(sh.v + c0 + j * 8 + 4);
+    s32[0] = sa.x; s32[1] = sa.y; s32[2] = sa.z; s32[3] = sa.w; s32[4] = sb.x; s32[5] = sb.y; s32[6] = sb.z; s32[7] = sb.w;
+    h32[0] = ha.x; h32[1] = ha.y; h32[2] = ha.z; h32[3] = ha.w; h32[4] = hb.x; h32[5] = hb.y; h32[6] = hb.z; h32[7] = hb.w;
+  } else {
+    // one 16-byte load each for scale and shift (already bf16 pairs)
+    const uint4 s4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(sc.v) + c0 + j * 8);
+    const uint4 h4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(sh.v) + c0 + j * 8);
+    s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
+    h[0] = h4.x; h[1] = h4.y; h[2] = h4.z; h[3] = h4.w;
+  }
   const int tb = 1 << til.tb_log2;
   const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
@@ -190,11 +207,11 @@ __device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, c
     }
   }
 }
-__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const float* sc, const float* sh, int t,
-                                                    const PixelTiling& til, int box_w, int box_h, int bx, int by, int bb,
-                                                    int fold_fp32) {
-  if (fold_fp32) transform_box_sw128_t<true>(tile, rows, sc, sh, t, til, box_w, box_h, bx, by, bb);
-  else transform_box_sw128_t<false>(tile, rows, sc, sh, t, til, box_w, box_h, bx, by, bb);
+__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const FoldArray& sc, const FoldArray& sh,
+                                                    int c0, int t, const PixelTiling& til, int box_w, int box_h, int bx,
+                                                    int by, int bb, int fold_fp32) {
+  if (fold_fp32) transform_box_sw128_t<true>(tile, rows, sc, sh, c0, t, til, box_w, box_h, bx, by, bb);
+  else transform_box_sw128_t<false>(tile, rows, sc, sh, c0, t, til, box_w, box_h, bx, by, bb);
 }
 
 // Column sums over the 32 rows held by a warp for 32 columns: lane L ends with the total of column L.
@@ -245,6 +262,34 @@ __device__ __forceinline__ uint32_t relu_threshold_bits(float es, float eh, uint
   if (es > 0.f) return bf16_round_down_bits(-eh / es);             // x > -eh/es
   if (es < 0.f) { sgn = 0x8000u; return bf16_round_down_bits(eh / es); }   // x < -eh/es  <=>  -x > eh/es
   return eh > 0.f ? 0xff80u : 0x7f80u;                              // constant mask: thr = -inf (always) / +inf (never)
+}
+
+// Direct BatchNorm-backward reductions for the degenerate channels of one 16-column chunk (rare; see bn_degenerate):
+// sum(dy) and sum(dy*x) of the UNSCALED fp32 dy over the warp's 32 pixel rows, added to the CTA's shared totals.
+// Out of line on purpose, and self-contained: it re-reads the accumulators from TMEM and the activation chunk from
+// shared memory (not yet overwritten), so the hot epilogue only tests the chunk's flag word and shares no registers.
+__device__ __noinline__ void dgrad_direct_sums(uint32_t fl16, uint32_t taddr, const uint4* xc0, const uint4* xc1,
+                                               const uint32_t* thr2, const uint32_t* sgn2, bool row_valid, float* s_dy,
+                                               float* s_dyx, int lane) {
+  uint32_t r16[16];
+  ptx::tmem_ld_32x32b_x16(taddr, r16);
+  const uint4 xa = *xc0, xb = *xc1;
+  const uint32_t xin[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int jc = 0; jc < 16; ++jc) {
+    if (!((fl16 >> jc) & 1u)) continue;
+    bool m0, m1;
+    gt_bf16x2(xin[jc >> 1] ^ sgn2[jc >> 1], thr2[jc >> 1], m0, m1);
+    const bool m = (jc & 1) ? m1 : m0;
+    const float xv = (jc & 1) ? bf16_hi(xin[jc >> 1]) : bf16_lo(xin[jc >> 1]);
+    const float d = (m && row_valid) ? __uint_as_float(r16[jc]) : 0.f;
+    const float s1 = warp_sum(d), s2 = warp_sum(d * xv);
+    if (lane == 0) {
+      atomicAdd(s_dy + jc, s1);
+      atomicAdd(s_dyx + jc, s2);
+    }
+  }
 }
 
 // development timeline: role r (0 producer, 1 mma, 2 epilogue leader), tile it < 16, event ev < 8
@@ -313,7 +358,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&aux->xform[s], kXformThreads / 32);   // one arrival per transform warp
       ptx::mbar_init(&aux->empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
       ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 64);  // one arrival per warp of the stage's epilogue group
     }
@@ -366,13 +411,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        aux->s_scale[c] = sc;
-        aux->s_shift[c] = sh;
+        aux->s_scale.set(c, sc, p.fold_fp32);
+        aux->s_shift.set(c, sh, p.fold_fp32);
       }
     } else {
       for (int c = threadIdx.x; c < padded; c += kConvThreads) {
-        aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
-        aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+        aux->s_scale.set(c, c < p.cin ? p.scale[c] : 0.f, p.fold_fp32);
+        aux->s_shift.set(c, c < p.cin ? p.shift[c] : 0.f, p.fold_fp32);
       }
     }
   }
@@ -397,14 +442,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       aux->e_thr2[c2] = thr;
       aux->e_sgn2[c2] = sg;
     }
-    for (int w16 = threadIdx.x; w16 < kMaxBN / 16; w16 += kConvThreads) {
-      uint32_t fl = 0;
-      if (p.e_gamma != nullptr)
-        for (int j = 0; j < 16; ++j) {
-          const int c = n0 + w16 * 16 + j;
-          if (c < p.n_total && bn_degenerate(p.e_gamma[c], p.e_beta[c])) fl |= 1u << j;
-        }
-      aux->e_flag16[w16] = fl;
+    if (threadIdx.x < kMaxBN) {   // warps 0-3: one column per lane, the warp's ballot is two flag words
+      const int c = n0 + (int)threadIdx.x;
+      const bool f = p.e_gamma != nullptr && c < p.n_total && bn_degenerate(p.e_gamma[c], p.e_beta[c]);
+      const uint32_t b = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) {
+        aux->e_flag16[2 * warp] = b & 0xffffu;
+        aux->e_flag16[2 * warp + 1] = b >> 16;
+        aux->e_flag_any4[warp] = b;
+      }
     }
   }
   ptx::tcgen05_fence_before();
@@ -509,10 +555,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
       int it = 0;
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
+        // accumulator stage it % n_acc, used (it / n_acc) times before: the MMA warp runs up to n_acc tiles ahead of
+        // the epilogue groups (each group holds a stage for the whole of its TMEM reads)
+        const int acc = it % p.n_acc;
+        const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
         ptx::mbar_wait(&aux->tmem_empty[acc], acc_phase ^ 1, 2);
         ptx::tcgen05_fence_after();
         if (lane == 0) RXB_TL(1, it, 0);
@@ -569,8 +617,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ptx::elect_one()) ptx::umma_commit(&aux->tmem_full[acc]);
         __syncwarp();
         if (lane == 0) RXB_TL(1, it, 2);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
         if (p.mma_stats && it > 0) issue_stats(it - 1);   // the previous tile's epilogue ran under this tile's main loop
       }
       if (p.mma_stats) {
@@ -623,9 +669,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = et == 0;
     const uint32_t bar_threads = (uint32_t)group_threads;
     const uint32_t bar_id = 1 + g2;
-    const int acc = g2;
-    uint32_t acc_phase = 0;
     for (int it = g2; it < my_tiles; it += 2) {
+      const int acc = it % p.n_acc;                              // n_acc is even: a stage always belongs to one group
+      const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
       const int m_tile = blockIdx.x + it * gridDim.x;
       int x0, y0, b0;
       tile_origin(p.t, m_tile, x0, y0, b0);
@@ -655,6 +701,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(&aux->tmem_full[acc], acc_phase, 4);
       ptx::tcgen05_fence_after();
       if (leader) RXB_TL(2, it, 4);
+      if constexpr (dgrad) {
+        // degenerate BatchNorm channels (kernel-uniform test, rare): a separate pass over the flagged 16-column chunks
+        // BEFORE the activation tile is overwritten, so the main loop below carries no trace of it
+        const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
+        if ((any4.x | any4.y | any4.z | any4.w) != 0) {
+          for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
+            for (int hc = 0; hc < 32; hc += 16) {
+              const int cc = c + hc;
+              const uint32_t fl16 = aux->e_flag16[cc >> 4];
+              if (fl16 != 0)
+                dgrad_direct_sums(fl16, tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + cc,
+                                  staging_chunk(so, cw, row, cc), staging_chunk(so, cw, row, cc + 8),
+                                  aux->e_thr2 + (cc >> 1), aux->e_sgn2 + (cc >> 1), row_valid, &aux->s_stat[0][cc],
+                                  &aux->s_stat[1][cc], lane);
+            }
+          }
+        }
+      }
       for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
         if (n0 + c >= p.n_total) break;
         if constexpr (dgrad) {
@@ -675,26 +739,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (cc >> 1));
             const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + cc);
             ptx::tmem_ld_wait();
-            const uint32_t fl16 = aux->e_flag16[cc >> 4];
-            if (fl16 != 0) {
-              // degenerate BatchNorm channels (rare, warp-uniform): sum(dy) and sum(dy*x) of the UNSCALED fp32 dy,
-              // reduced over the warp's 32 pixel rows and added to the CTA's shared totals
-#pragma unroll
-              for (int jc = 0; jc < 16; ++jc) {    // unrolled: register arrays are indexed by constants only
-                if (!((fl16 >> jc) & 1u)) continue;
-                const uint32_t thw = aux->e_thr2[(cc + jc) >> 1], sgw = aux->e_sgn2[(cc + jc) >> 1];
-                bool m0, m1;
-                gt_bf16x2(xin[jc >> 1] ^ sgw, thw, m0, m1);
-                const bool m = (jc & 1) ? m1 : m0;
-                const float xv = (jc & 1) ? bf16_hi(xin[jc >> 1]) : bf16_lo(xin[jc >> 1]);
-                const float d = (m && row_valid) ? __uint_as_float(r16[jc]) : 0.f;
-                const float s1 = warp_sum(d), s2 = warp_sum(d * xv);
-                if (lane == 0) {
-                  atomicAdd(&aux->s_stat[0][cc + jc], s1);
-                  atomicAdd(&aux->s_stat[1][cc + jc], s2);
-                }
-              }
-            }
             uint32_t pk[8];
 #pragma unroll
             for (int i4 = 0; i4 < 2; ++i4) {
@@ -779,7 +823,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
-      acc_phase ^= 1;
       // hand the staged tile to the store warp (and to the MMA warp for the column statistics)
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
@@ -841,7 +884,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
-            transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
+            transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale, aux->s_shift, kb * BK,
                                 t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0, p.fold_fp32);
             ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
             __syncwarp();
@@ -865,8 +908,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 // Weight gradient
 struct __align__(16) WgradAux {
-  float s_scale[kMaxPrologueC + 64];   // prologue fold (fp32; packed to bf16 pairs per thread in the default mode)
-  float s_shift[kMaxPrologueC + 64];
+  FoldArray s_scale;
+  FoldArray s_shift;
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -932,8 +975,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.prologue) {
     const int padded = p.boxes_per_tap * p.bkc;
     for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
-      aux->s_scale[c] = c < p.cin ? p.scale[c] : 0.f;
-      aux->s_shift[c] = c < p.cin ? p.shift[c] : 0.f;
+      aux->s_scale.set(c, c < p.cin ? p.scale[c] : 0.f, p.fold_fp32);
+      aux->s_shift.set(c, c < p.cin ? p.shift[c] : 0.f, p.fold_fp32);
     }
   }
   ptx::tcgen05_fence_before();
@@ -1214,8 +1257,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ax += tx - p.pad_x;
               ay += ty - p.pad_y;
             }
-            transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale + c0,
-                                aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0, p.fold_fp32);
+            transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale,
+                                aux->s_shift, c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0, p.fold_fp32);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -1275,6 +1318,11 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   static const int dbg_dgrad = getenv("RXB_DBG_DGRAD") ? atoi(getenv("RXB_DBG_DGRAD")) : 0;   // timing experiments only
   if (dgrad && (dbg_dgrad & 1)) { p.mma_stats = 0; p.do_stats = 0; }
   if (dgrad && (dbg_dgrad & 2) && p.out_mode == OUT_G_ACCUM) p.out_mode = OUT_G_WRITE;
+  // TMEM accumulator stages: the narrow store epilogue (shuffle statistics, no Gram / sum columns in TMEM) has all 512
+  // columns for accumulators - four stages let the MMA warp run ahead of the x-merge epilogue, which holds a stage for
+  // ~4k cycles per tile (profiles/r02_timelines.log)
+  static const int dbg_nacc = getenv("RXB_DBG_NACC") ? atoi(getenv("RXB_DBG_NACC")) : 4;
+  p.n_acc = (!dgrad && p.bn < kMaxBN && !p.mma_stats && dbg_nacc == 4) ? 4 : 2;
   p.n_tiles = ceil_div(p.n_total, p.bn);
   p.kb_per_tap = ceil_div(p.cin, bk);
   if (prologue && p.kb_per_tap * bk > kMaxPrologueC + 64) return set_error(RXB_ERR_INVALID, "conv_gemm: cin too large");

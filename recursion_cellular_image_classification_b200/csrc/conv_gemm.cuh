@@ -70,6 +70,7 @@ struct GemmParams {
   int stages;       // A (and streamed B) pipeline depth
   int n_stg;        // output staging buffers (stores: 1 or 2; dgrad: 2..4 activation-tile buffers staged in place)
   int b_resident;   // 1: the whole [taps][k-blocks] weight panel of the N tile is loaded once per CTA
+  int n_acc;        // TMEM accumulator stages of kAccStride columns: 2, or 4 for the narrow store epilogue
   int mma_stats;    // 1: per-channel sums of the stored tile are accumulated by tcgen05.mma over the staging buffer
   unsigned long long* dbg;  // development: per-role clock64 timeline of CTA (0,0) (RXB_DBG_TIMELINE=1), else nullptr
 };
