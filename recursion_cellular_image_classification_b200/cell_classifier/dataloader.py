@@ -147,9 +147,10 @@ class ImagesDS(torch.utils.data.Dataset):
             self._norm_dev = (torch.from_numpy(self.norm_m).to(dev), torch.from_numpy(self.norm_d).to(dev))
         return self._norm_dev
 
-    def device_batch(self, batch, dev, out_format=ops.OUT_BF16_S2D32, first_only=False):
+    def device_batch(self, batch, dev, out_format=ops.OUT_BF16_S2D32, first_only=False, out=None):
         """collate_raw output -> normalised/augmented device tensor via the fused loader.
-        Returns [B*G, ...] in `out_format` (G images per sample, or only the first when first_only)."""
+        Returns [B*G, ...] in `out_format` (G images per sample, or only the first when first_only); `out` makes the
+        loader write into a caller-owned tensor of that shape (the executor's fixed-address step buffer)."""
         if "jpeg_blob" in batch:
             B, G, S = batch["codes"].shape[0], batch["codes"].shape[1], batch["size"]
             select = None
@@ -169,14 +170,14 @@ class ImagesDS(torch.utils.data.Dataset):
         planes = planes.reshape(B * G, *planes.shape[2:]).contiguous()
         exp = batch["exp"].to(dev).to(torch.int32).repeat_interleave(G)
         norm_m, norm_d = self._norm(dev)
-        out = batch["out"]
+        hw = batch["out"]
         if mats is not None:
             return ops.load_norm_affine(planes, torch.arange(B * G, dtype=torch.int32, device=dev), exp,
                                         codes.reshape(-1).contiguous(), mats.reshape(-1, 2, 3).contiguous(),
-                                        crops.reshape(-1, 2).contiguous(), norm_m, norm_d, (out, out), out_format)
+                                        crops.reshape(-1, 2).contiguous(), norm_m, norm_d, (hw, hw), out_format, out=out)
         return ops.load_norm_aug(planes, torch.arange(B * G, dtype=torch.int32, device=dev), exp,
                                  codes.reshape(-1).contiguous(), crops.reshape(-1, 2).contiguous(), norm_m, norm_d,
-                                 (out, out), out_format)
+                                 (hw, hw), out_format, out=out)
 
     # ------------------------------------------------------------ reference-compatible item (dataloader.py:148-209)
     def __getitem__(self, index):

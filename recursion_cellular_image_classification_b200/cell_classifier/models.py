@@ -92,6 +92,7 @@ class DenseNet121(torch.nn.Module):
         self.register_buffer("momentum_buf", torch.zeros(n, dtype=torch.float32, device=dev))
         self.register_buffer("bn_buffers", torch.zeros(nb, dtype=torch.float32, device=dev))
         self._plans = {}
+        self.graph_launches = 0
         self._views = OrderedDict()
         off = 0
         for name, shape in self.specs:
@@ -208,9 +209,21 @@ class DenseNet121(torch.nn.Module):
         handle = ctypes.c_void_p()
         check(lib.rxb_dn121_create(ctypes.byref(cfg), ptr(self.flat.data), ptr(self.flat.grad), ptr(self.momentum_buf),
                                    ptr(self.bn_buffers), ptr(ws), nbytes, 1 if training else 0, ctypes.byref(handle)))
-        plan = {"handle": handle, "ws": ws, "cfg": cfg, "synced": False}
+        plan = {"handle": handle, "ws": ws, "cfg": cfg, "synced": False, "graphs": {}, "static": None}
         self._plans[key] = plan
         return plan
+
+    def static_buffers(self, B, H, W):
+        """The training plan's fixed-address step buffers — (xs bf16 [B,H/2,W/2,32], target int64 [B], loss f32 [1]).
+        Steps whose inputs live here can be replayed from CUDA graphs (`train_step(..., graph=True)`): have the fused
+        loader write `xs` directly (ops.load_norm_aug(..., out=xs)) and copy the labels into `target`."""
+        plan = self._plan(B, H, W, True)
+        if plan["static"] is None:
+            dev = self.flat.device
+            plan["static"] = (torch.empty(B, H // 2, W // 2, 32, dtype=torch.bfloat16, device=dev),
+                              torch.zeros(B, dtype=torch.int64, device=dev),
+                              torch.zeros(1, dtype=torch.float32, device=dev))
+        return plan["static"]
 
     def _sync(self, plan):
         if self._weights_dirty:
@@ -252,18 +265,49 @@ class DenseNet121(torch.nn.Module):
             logits = logits.view(-1, groups, self.nb_classes).mean(1)
         return logits
 
-    def train_step(self, xs, target, global_batch=None, phase=-1, loss_out=None):
+    def train_step(self, xs, target, global_batch=None, phase=-1, loss_out=None, graph=False):
         """forward + CrossEntropy(mean over global_batch) + backward into self.flat.grad.  Returns the
-        device scalar holding this rank's share of the loss."""
+        device scalar holding this rank's share of the loss.
+        graph=True replays the phase from a CUDA graph: the executor enqueues ~620 kernels per step with no host
+        synchronisation, so a phase is captured once per (buffers, phase, global batch) — on its second use, the first
+        one runs eagerly and loads every kernel — and replayed afterwards (about 4 % of the step at batch 128).  The
+        inputs must then sit at fixed addresses: use `static_buffers()`; other tensors are copied into them."""
         xs = self._as_s2d(xs)
         B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
         plan = self._plan(B, H, W, True)
         self._sync(plan)
-        if loss_out is None:
-            loss_out = torch.empty(1, dtype=torch.float32, device=xs.device)
-        check(load().rxb_dn121_train_step(plan["handle"], ptr(xs), ptr(target.contiguous()), global_batch or B,
-                                          ptr(loss_out), phase, stream_ptr()))
-        return loss_out
+        if not graph:
+            if loss_out is None:
+                loss_out = torch.empty(1, dtype=torch.float32, device=xs.device)
+            check(load().rxb_dn121_train_step(plan["handle"], ptr(xs), ptr(target.contiguous()), global_batch or B,
+                                              ptr(loss_out), phase, stream_ptr()))
+            return loss_out
+        sx, sy, sl = self.static_buffers(B, H, W)
+        if xs.data_ptr() != sx.data_ptr() and phase in (-1, 0):
+            sx.copy_(xs)
+        if target.data_ptr() != sy.data_ptr() and phase in (-1, 0):
+            sy.copy_(target)
+        key = (phase, global_batch or B)
+        entry = plan["graphs"].get(key)
+        lib = load()
+        if entry is None:                                  # first use: eager (doubles as the warm-up a capture needs)
+            check(lib.rxb_dn121_train_step(plan["handle"], ptr(sx), ptr(sy), global_batch or B, ptr(sl), phase, stream_ptr()))
+            plan["graphs"][key] = "warm"
+        else:
+            if entry == "warm":
+                torch.cuda.synchronize(self.flat.device)
+                g = torch.cuda.CUDAGraph()
+                n0 = lib.rxb_launch_count()
+                with torch.cuda.graph(g):
+                    check(lib.rxb_dn121_train_step(plan["handle"], ptr(sx), ptr(sy), global_batch or B, ptr(sl), phase,
+                                                   stream_ptr()))
+                entry = plan["graphs"][key] = (g, lib.rxb_launch_count() - n0)
+            entry[0].replay()
+            self.graph_launches += entry[1]               # kernels replayed (rxb_launch_count only sees enqueues)
+        if loss_out is not None and loss_out.data_ptr() != sl.data_ptr() and phase in (-1, 0):
+            loss_out.copy_(sl)
+            return loss_out
+        return sl
 
     def phase_grad_range(self, B, H, W, phase):
         plan = self._plan(B, H, W, True)

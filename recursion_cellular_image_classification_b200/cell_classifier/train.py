@@ -90,6 +90,11 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     best_acc, best_epoch, history = -1.0, 0, []
     loss_dev = torch.zeros(1, device=dev)
     n_phases = None
+    # CUDA-graph replay of the executor's phases (models.DenseNet121.train_step): on by default on the device;
+    # hyperparams['cuda_graph'] = False or RXB_NO_GRAPH=1 keeps plain stream launches
+    use_graph = bool(hyperparams.get('cuda_graph', True)) and dev.type == "cuda" and hasattr(net, "static_buffers") \
+        and os.environ.get("RXB_NO_GRAPH", "0") != "1"
+    graph_kw = {"graph": True} if use_graph else {}
 
     def validate(epoch):
         nonlocal best_acc, best_epoch
@@ -129,8 +134,17 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
             torch.cuda.synchronize(dev)
         t_epoch = time.perf_counter()
         for batch in loader:
-            xs = ds_train.device_batch(batch, dev)
             y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
+            if use_graph:
+                # the loader writes straight into the executor's fixed-address step buffer, the labels are copied
+                # beside it, and every backward phase is replayed from a CUDA graph (captured on its second use)
+                B, H, W = len(batch["label"]), batch["out"], batch["out"]
+                xs_static, y_static, _ = net.static_buffers(B, H, W)
+                xs = ds_train.device_batch(batch, dev, out=xs_static)
+                y_static.copy_(y)
+                y = y_static
+            else:
+                xs = ds_train.device_batch(batch, dev)
             B, H, W = xs.shape[0], xs.shape[1] * 2, xs.shape[2] * 2
             if n_phases is None:
                 from .._lib import load
@@ -138,7 +152,7 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
             ranges = [net.phase_grad_range(B, H, W, p) for p in range(n_phases)]
             ar = parallel.PhasedGradAllReduce(net.flat.grad, ranges)
             for p in range(n_phases):
-                net.train_step(xs, y, global_batch=B * world, phase=p, loss_out=loss_dev)
+                net.train_step(xs, y, global_batch=B * world, phase=p, loss_out=loss_dev, **graph_kw)
                 ar.after_phase(p)
             ar.wait()
             net.sgd_step(B, H, W, lr=lr, momentum=momentum, weight_decay=wd, nesterov=nesterov, **frozen)

@@ -20,7 +20,6 @@ int set_error(int code, const char* fmt, ...) {
 
 bool g_prof_on = false;
 bool g_dbg_sync = getenv("RXB_DBG_SYNC") && atoi(getenv("RXB_DBG_SYNC")) != 0;
-bool g_fold_fp32 = getenv("RXB_FOLD_FP32") && atoi(getenv("RXB_FOLD_FP32")) != 0;
 bool g_pdl = getenv("RXB_PDL") && atoi(getenv("RXB_PDL")) != 0;   // measured: no gain on the DenseNet step
 namespace {
 struct ProfRec { cudaEvent_t a, b; int cat; };

@@ -63,7 +63,6 @@ inline cudaStream_t as_stream(rxb_stream_t s) { return reinterpret_cast<cudaStre
 // pdl_sync() is the point after which they may touch global memory (the predecessor has completed and flushed).
 // EVERY kernel launched through launch_k must call pdl_sync() before its first global read or write.
 extern bool g_dbg_sync;
-extern bool g_fold_fp32;   // RXB_FOLD_FP32=1: the conv prologues apply the BatchNorm fold in fp32 (default: one packed bf16 FMA)
 extern bool g_pdl;   // RXB_PDL=1 enables the attribute (default off: kernels serialise as usual and pdl_sync() is a no-op)
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

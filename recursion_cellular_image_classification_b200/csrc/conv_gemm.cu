@@ -46,18 +46,9 @@ constexpr int kSumCol = 384;      // TMEM columns [384,400): running column sums
 constexpr int kMaxPrologueC = 1024;
 constexpr int kMaxBN = 128;
 
-// Prologue fold in shared memory: bf16 pairs (the operands of fma.rn.relu.bf16x2, default) or fp32 (fold_fp32); one
-// array sized for fp32 serves both, the transform reads it in the mode's own type.
-struct FoldArray {
-  float v[kMaxPrologueC + 64];
-  __device__ __forceinline__ void set(int c, float x, int fold_fp32) {
-    if (fold_fp32) v[c] = x; else reinterpret_cast<__nv_bfloat16*>(v)[c] = __float2bfloat16_rn(x);
-  }
-};
-
 struct __align__(16) GemmAux {
-  FoldArray s_scale;
-  FoldArray s_shift;
+  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
+  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
   float e_scale[kMaxBN];
   float e_shift[kMaxBN];
   uint32_t e_thr2[kMaxBN / 2];   // dgrad ReLU mask as a packed-bf16 threshold test: (x ^ sgn) > thr, two columns per word
@@ -132,8 +123,9 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
 // Rows whose pixel lies outside the image keep the zeros TMA wrote (conv zero padding); boxes entirely
 // inside the image take the path without per-row coordinate arithmetic.
 // relu(x*s + h) on two packed bf16 lanes in ONE instruction (single rounding of the exact fused result; the
-// BatchNorm scale/shift are rounded to bf16 like every other GEMM operand).  RXB_FOLD_FP32=1 selects the fp32
-// variant below instead (fp32 scale/shift, one rounding of the result) - five instructions per pair instead of one.
+// BatchNorm scale/shift are rounded to bf16 like every other GEMM operand).  Measured alternative (round 2, removed
+// again): fp32 scale/shift with cvt.rn.relu.bf16x2.f32, five instructions per pair - training-mode logits 0.0127
+// instead of 0.0144 relative at 512x512 B=16 (both under the 2e-2 bar), step time +3.5 %; see DESIGN.md 5.3.
 __device__ __forceinline__ uint32_t fma_relu_bf16x2(uint32_t x, uint32_t s, uint32_t h) {
   uint32_t d;
   asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
@@ -148,52 +140,20 @@ __device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4]
   v.w = fma_relu_bf16x2(v.w, s[3], h[3]);
   *p = v;
 }
-// fp32 variant: relu(x*s + h) with fp32 scale/shift, ONE rounding to bf16 (cvt.rn.relu.bf16x2.f32 packs two results)
-__device__ __forceinline__ uint32_t fma_relu_f32_pack(uint32_t x, float s0, float h0, float s1, float h1) {
-  const float lo = fmaf(__uint_as_float(x << 16), s0, h0), hi = fmaf(__uint_as_float(x & 0xffff0000u), s1, h1);
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ void transform_chunk32(uint4* p, const float (&s)[8], const float (&h)[8]) {
-  uint4 v = *p;
-  v.x = fma_relu_f32_pack(v.x, s[0], h[0], s[1], h[1]);
-  v.y = fma_relu_f32_pack(v.y, s[2], h[2], s[3], h[3]);
-  v.z = fma_relu_f32_pack(v.z, s[4], h[4], s[5], h[5]);
-  v.w = fma_relu_f32_pack(v.w, s[6], h[6], s[7], h[7]);
-  *p = v;
-}
-
-// `c0` = first channel of the k-block inside the fold arrays.
-template <bool FOLD32>
-__device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, const FoldArray& sc, const FoldArray& sh,
-                                                      int c0, int t, const PixelTiling& til, int box_w, int box_h, int bx,
-                                                      int by, int bb) {
+__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const __nv_bfloat16* sc,
+                                                    const __nv_bfloat16* sh, int t, const PixelTiling& til, int box_w,
+                                                    int box_h, int bx, int by, int bb) {
   const int j = t & 7;
-  // the 8 channels of this thread's chunk
-  float s32[8], h32[8];
-  uint32_t s[4], h[4];
-  if (FOLD32) {
-    const float4 sa = *reinterpret_cast<const float4*>(sc.v + c0 + j * 8), sb = *reinterpret_cast<const float4*>(sc.v + c0 + j * 8 + 4);
-    const float4 ha = *reinterpret_cast<const float4*>(sh.v + c0 + j * 8), hb = *reinterpret_cast<const float4*>(sh.v + c0 + j * 8 + 4);
-    s32[0] = sa.x; s32[1] = sa.y; s32[2] = sa.z; s32[3] = sa.w; s32[4] = sb.x; s32[5] = sb.y; s32[6] = sb.z; s32[7] = sb.w;
-    h32[0] = ha.x; h32[1] = ha.y; h32[2] = ha.z; h32[3] = ha.w; h32[4] = hb.x; h32[5] = hb.y; h32[6] = hb.z; h32[7] = hb.w;
-  } else {
-    // one 16-byte load each for scale and shift (already bf16 pairs)
-    const uint4 s4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(sc.v) + c0 + j * 8);
-    const uint4 h4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(sh.v) + c0 + j * 8);
-    s[0] = s4.x; s[1] = s4.y; s[2] = s4.z; s[3] = s4.w;
-    h[0] = h4.x; h[1] = h4.y; h[2] = h4.z; h[3] = h4.w;
-  }
+  // the 8 channels of this thread's chunk: one 16-byte load each for scale and shift (already bf16 pairs)
+  const uint4 s4 = *reinterpret_cast<const uint4*>(sc + j * 8), h4 = *reinterpret_cast<const uint4*>(sh + j * 8);
+  const uint32_t s[4] = {s4.x, s4.y, s4.z, s4.w}, h[4] = {h4.x, h4.y, h4.z, h4.w};
   const int tb = 1 << til.tb_log2;
   const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
   constexpr int kRowsPerIter = kXformThreads / 8;
   if (interior) {
 #pragma unroll 4
-    for (int row = t >> 3; row < rows; row += kRowsPerIter) {
-      uint4* ptr = reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4));
-      if (FOLD32) transform_chunk32(ptr, s32, h32); else transform_chunk(ptr, s, h);
-    }
+    for (int row = t >> 3; row < rows; row += kRowsPerIter)
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
   } else {
     for (int row = t >> 3; row < rows; row += kRowsPerIter) {
       const int r2 = row / box_w;
@@ -202,16 +162,9 @@ __device__ __forceinline__ void transform_box_sw128_t(uint8_t* tile, int rows, c
       const int yi = r2 - bi * box_h;
       const int x = bx + xi, y = by + yi, b = bb + bi;
       if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
-      uint4* ptr = reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4));
-      if (FOLD32) transform_chunk32(ptr, s32, h32); else transform_chunk(ptr, s, h);
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
     }
   }
-}
-__device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const FoldArray& sc, const FoldArray& sh,
-                                                    int c0, int t, const PixelTiling& til, int box_w, int box_h, int bx,
-                                                    int by, int bb, int fold_fp32) {
-  if (fold_fp32) transform_box_sw128_t<true>(tile, rows, sc, sh, c0, t, til, box_w, box_h, bx, by, bb);
-  else transform_box_sw128_t<false>(tile, rows, sc, sh, c0, t, til, box_w, box_h, bx, by, bb);
 }
 
 // Column sums over the 32 rows held by a warp for 32 columns: lane L ends with the total of column L.
@@ -411,13 +364,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        aux->s_scale.set(c, sc, p.fold_fp32);
-        aux->s_shift.set(c, sh, p.fold_fp32);
+        aux->s_scale[c] = __float2bfloat16_rn(sc);
+        aux->s_shift[c] = __float2bfloat16_rn(sh);
       }
     } else {
       for (int c = threadIdx.x; c < padded; c += kConvThreads) {
-        aux->s_scale.set(c, c < p.cin ? p.scale[c] : 0.f, p.fold_fp32);
-        aux->s_shift.set(c, c < p.cin ? p.shift[c] : 0.f, p.fold_fp32);
+        aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
+        aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
       }
     }
   }
@@ -884,8 +837,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->full[stage], phase, 5);
-            transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale, aux->s_shift, kb * BK,
-                                t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0, p.fold_fp32);
+            transform_box_sw128(smA + (size_t)stage * a_stage, p.rows_a, aux->s_scale + kb * BK, aux->s_shift + kb * BK,
+                                t, p.t, box_w, box_h, x0 + gx - p.pad_x, y0 + gy - p.pad_y, b0);
             ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
             __syncwarp();
             if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&aux->xform[stage]);
@@ -908,8 +861,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ================================================================================================
 // Weight gradient
 struct __align__(16) WgradAux {
-  FoldArray s_scale;
-  FoldArray s_shift;
+  __nv_bfloat16 s_scale[kMaxPrologueC + 64];   // prologue fold as bf16 pairs: the operands of fma.rn.relu.bf16x2
+  __nv_bfloat16 s_shift[kMaxPrologueC + 64];
   uint64_t full[kMaxStages];
   uint64_t xform[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -975,8 +928,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (p.prologue) {
     const int padded = p.boxes_per_tap * p.bkc;
     for (int c = threadIdx.x; c < padded; c += kGemmThreads) {
-      aux->s_scale.set(c, c < p.cin ? p.scale[c] : 0.f, p.fold_fp32);
-      aux->s_shift.set(c, c < p.cin ? p.shift[c] : 0.f, p.fold_fp32);
+      aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
+      aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
     }
   }
   ptx::tcgen05_fence_before();
@@ -1257,8 +1210,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ax += tx - p.pad_x;
               ay += ty - p.pad_y;
             }
-            transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale,
-                                aux->s_shift, c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0, p.fold_fp32);
+            transform_box_sw128(smA + (size_t)stage * kWgA_BYTES + (size_t)i * a_box_bytes, 128, aux->s_scale + c0,
+                                aux->s_shift + c0, t, p.t, 1 << p.t.tw_log2, th, ax, ay, b0);
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -1310,7 +1263,6 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
   // dgrad, and stores of >= 128 channels with statistics, run 128-wide N tiles whose column sums come from the
   // tensor pipe (columns past n_total are zero weights / clipped stores)
-  p.fold_fp32 = g_fold_fp32 ? 1 : 0;
   if (p.e_gamma != nullptr && (p.e_beta == nullptr || p.ch_sumsq == nullptr))
     return set_error(RXB_ERR_INVALID, "conv_gemm: e_gamma needs e_beta and ch_sumsq");
   p.bn = (dgrad || p.n_total >= kMaxBN) ? kMaxBN : p.n_total;
@@ -1420,7 +1372,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     // An EVEN number of buffers, so that a buffer always belongs to the same epilogue group (the groups take alternate
     // tiles): with three buffers shared by both groups the kernel faulted intermittently in 4-GPU runs (never at N<=2);
     // two or four buffers ran clean.  RXB_DBG_NX=3 restores the odd count for investigation.
-    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 4;   // 3: odd count, per-group barriers
+    static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 3;   // 3: odd count, per-group barriers
     p.n_stg = 2;
     if (dbg_nx == 3) {
       if ((avail - stage_tile) / per_stage >= 3) { p.n_stg = 3; avail -= stage_tile; }
@@ -1497,7 +1449,6 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   if (!(p.n == 32 || (p.n % 64 == 0 && p.n >= 64 && p.n <= 256)))
     return set_error(RXB_ERR_INVALID, "conv_wgrad: n=%d must be 32 or a multiple of 64 up to 256", p.n);
   const int taps = p.taps_x * p.taps_y;
-  p.fold_fp32 = g_fold_fp32 ? 1 : 0;
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
   p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;

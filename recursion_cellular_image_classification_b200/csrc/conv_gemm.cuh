@@ -59,7 +59,6 @@ struct GemmParams {
   const float* e_gamma;   // optional (with e_beta and ch_sumsq): BatchNorm weight / bias per N channel; channels that
   const float* e_beta;    // bn_degenerate() flags get direct sum(dy) / sum(dy*x) reductions in the epilogue
   // ---- filled by launch_conv_gemm
-  int fold_fp32;    // prologue arithmetic: 0 = one packed bf16 fma.relu per channel pair, 1 = fp32 FMA, one rounding
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;
   int halo;         // 1: an A stage holds th+taps_y-1 image rows; row taps are descriptor offsets into it
@@ -106,7 +105,6 @@ struct WgradParams {
   unsigned long long* dbg;  // development timeline of CTA (0,0) (RXB_DBG_TIMELINE), else nullptr
   int bulk_out;         // 1: result staged in shared memory and added to dW by cp.reduce.async.bulk (else fp32 atomics)
   int bulk_bufs;        // staging buffers for the 1x1 bulk path (1 or 2)
-  int fold_fp32;        // prologue arithmetic, as GemmParams::fold_fp32 (filled by the launcher)
 };
 // A: bf16 [B,H,W,ldA]; dOut: bf16 [B,H,W,ldD].
 int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* dOut, long long ldD,

@@ -317,12 +317,11 @@ int bn_relu_bwd_to_G(int mode, const void* upstream, const __nv_bfloat16* X, int
 // sum_p dy*x of input channel c from the finished weight gradient of the conv that consumed A' = relu(scale*x+shift):
 // sum_p dy*A' = sum_{k,tap} W[k][c][tap]*dW[k][c][tap] (both sides equal sum_p dL/dA' * A'), and on the ReLU's support
 // A' = scale*x + shift, so sum dy*x = (W.dW - shift*sum dy)/scale.  The identity is evaluated with the operands the
-// kernels really used: W rounded to bf16 (the GEMM operand), scale/shift rounded to bf16 unless the prologues fold in
-// fp32 (fold_fp32) - otherwise the 2^-9 operand mismatch is amplified by 1/scale.
+// kernels really used: W rounded to bf16 (the GEMM operand), scale/shift rounded to bf16 (the prologue's fold operands)
+// - otherwise the 2^-9 operand mismatch is amplified by 1/scale.
 // One warp per channel (the K*taps products are strided through the OIHW tensors); every lane returns the result.
 __device__ __forceinline__ float sum_dyx_from_wdw(const float* __restrict__ W, const float* __restrict__ dW, int K, int C,
-                                                  int taps, int c, float es, float eh, float sum_dy, int lane,
-                                                  int fold_fp32) {
+                                                  int taps, int c, float es, float eh, float sum_dy, int lane) {
   float t = 0.f;
   const int n = K * taps;
   for (int i = lane; i < n; i += 32) {
@@ -331,18 +330,19 @@ __device__ __forceinline__ float sum_dyx_from_wdw(const float* __restrict__ W, c
     t = fmaf(bf16_round(__ldg(W + at)), __ldg(dW + at), t);
   }
   t = warp_sum(t);
-  if (!fold_fp32) { es = bf16_round(es); eh = bf16_round(eh); }
+  es = bf16_round(es);
+  eh = bf16_round(eh);
   return es != 0.f ? (t - eh * sum_dy) / es : 0.f;
 }
 
 __global__ void __launch_bounds__(256)
 sum_dyx_from_wdw_kernel(const float* __restrict__ W, const float* __restrict__ dW, int K, int C, int taps,
                         const float* __restrict__ scale, const float* __restrict__ shift,
-                        const float* __restrict__ sum_dy, float* __restrict__ out, int fold_fp32) {
+                        const float* __restrict__ sum_dy, float* __restrict__ out) {
   pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
-  const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane, fold_fp32);
+  const float r = sum_dyx_from_wdw(W, dW, K, C, taps, c, scale[c], shift[c], sum_dy[c], lane);
   if (lane == 0) out[c] = r;
 }
 
@@ -351,8 +351,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __restrict__ dW, int K, int taps,
                        float* __restrict__ dsum, float* __restrict__ dsq, BnFold f, float count, int C,
                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ corrA,
-                       float* __restrict__ corrB, const float* __restrict__ gamma, const float* __restrict__ beta,
-                       int fold_fp32) {
+                       float* __restrict__ corrB, const float* __restrict__ gamma, const float* __restrict__ beta) {
   pdl_sync();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -361,7 +360,7 @@ bn_bwd_finalize_kernel(int mode, const float* __restrict__ W, const float* __res
   if (W) {
     // degenerate channels: the data-gradient epilogue reduced sum dy*x directly into dsq (conv_gemm.cu)
     const bool direct = gamma != nullptr && bn_degenerate(gamma[c], beta[c]);
-    const float raw = direct ? dsq[c] : sum_dyx_from_wdw(W, dW, K, C, taps, c, f.scale[c], f.shift[c], s, lane, fold_fp32);
+    const float raw = direct ? dsq[c] : sum_dyx_from_wdw(W, dW, K, C, taps, c, f.scale[c], f.shift[c], s, lane);
     q = f.rstd[c] * (raw - f.mean[c] * s);                       // sum dy*xhat
   } else {
     q = dsq[c];
@@ -384,7 +383,7 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
                     const float* beta, cudaStream_t st) {
   RXB_PROF(st, PROF_EW_FINALIZE);
   RXB_CUDA(launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, mode, W, dW, K, taps, dsum, dsq, f, count, C, dgamma, dbeta,
-                                                        corrA, corrB, gamma, beta, g_fold_fp32 ? 1 : 0));
+                                                        corrA, corrB, gamma, beta));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -727,8 +726,7 @@ int repack_weights(const float* params, __nv_bfloat16* arena, const RepackJob* j
 int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
                             const float* shift, const float* sum_dy, float* out, cudaStream_t st) {
   RXB_PROF(st, PROF_ELEMENTWISE);
-  RXB_CUDA(launch_k(sum_dyx_from_wdw_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, W, dW, K, C, taps, scale, shift, sum_dy, out,
-                    g_fold_fp32 ? 1 : 0));
+  RXB_CUDA(launch_k(sum_dyx_from_wdw_kernel, dim3(ceil_div(C, 8)), dim3(256), (size_t)(0), st, W, dW, K, C, taps, scale, shift, sum_dy, out));
   RXB_LAUNCH_OK();
   return RXB_OK;
 }

@@ -6,7 +6,7 @@ out=gpurun_out/r02b
 mkdir -p "$out"
 ( time timeout 900 python -m pytest tests -m gpu -q -s ) > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -5 "$out/pytest_gpu.log"
 RXB_FOLD_FP32=1 timeout 200 python -m pytest tests/test_gpu_aa_regime.py tests/test_gpu_densenet.py -m gpu -q -s > "$out/regime_fold_fp32.log" 2>&1; echo "fold32 rc=$?"; grep -E "512x512|deviation|logits rel|passed|failed" "$out/regime_fold_fp32.log"
-for v in "default:" "nx3:RXB_DBG_NX=3" "nacc2:RXB_DBG_NACC=2" "fold32:RXB_FOLD_FP32=1" "nx3_b256:RXB_DBG_NX=3"; do
+for v in "default:" "nx4:RXB_DBG_NX=4" "nograph:RXB_NO_GRAPH=1"; do
   name=${v%%:*}; envs=${v#*:}; extra=""; [ "$name" = "nx3_b256" ] && extra="--batch 256"
   env $envs timeout 90 python bench.py --quick --steps 8 --warmup 3 $extra > "$out/bench_quick_$name.json" 2>/dev/null; echo "$name $(cat $out/bench_quick_$name.json | python -c 'import json,sys; d=json.load(sys.stdin); print(d["ms_per_step"], d["value"])')"
 done
