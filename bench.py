@@ -569,11 +569,13 @@ def run_ours(args):
     cnt = (ctypes.c_int64 * ncat)()
     prof_steps = 2
     torch.cuda.synchronize()
+    graph_was_on, use_graph["on"] = use_graph["on"], False      # event brackets need real launches, not graph replays
     lib.rxb_profile_enable(1)
     for _ in range(prof_steps):
         step(False)
     _lib.check(lib.rxb_profile_collect(msb, cnt, ncat))
     lib.rxb_profile_enable(0)
+    use_graph["on"] = graph_was_on
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -708,6 +710,7 @@ def run_ours(args):
                     d_blob, d_offs = torch.empty_like(blob, device=dev), torch.empty_like(offs, device=dev)
 
                     def jpeg_step():
+                        # (stream launches: the input buffer here is not the executor's static one)
                         d_blob.copy_(h_blob, non_blocking=True)
                         d_offs.copy_(h_offs, non_blocking=True)
                         ops.jpeg_decode_gray(d_blob, d_offs, (IMG, IMG), out=planes_dev, check_status=False)
