@@ -255,6 +255,39 @@ int rxb_dn121_train_step(rxb_dn121* net, const void* input_s2d, const int64_t* t
 /* p -= lr * nesterov(grad*grad_scale + wd*p) on the flat buffers, then refresh the bf16 operands. */
 int rxb_dn121_sgd(rxb_dn121* net, float lr, float mu, float wd, int nesterov, float grad_scale,
                   rxb_stream_t stream);
+/* ------------------------------------------------------------------------------------------------
+ * The reference's real model, evaluation mode: TwoSitesNN = torchvision ResNet-50 trunk with the
+ * 6-channel stem, fc -> Identity (models.py:16-29), per-sample feature means of the image / negative-control /
+ * positive-control thirds concatenated (models.py:44-53), and the BatchNorm1d -> Dropout -> Linear(6144,
+ * size_features) -> ReLU -> BatchNorm1d -> Dropout -> Linear(size_features, num_classes) head (models.py:31-39).
+ * Replaces TwoSitesNN.forward as test.py:23-27 calls it (model.eval(): running statistics, Dropout = identity), so a
+ * checkpoint trained with the reference (main.py:147) can be served natively.  Convolutions are the tcgen05
+ * implicit GEMMs above (stride-2 3x3 as a 2x2-tap convolution over a space-to-depth pass, see csrc/resnet.cu).
+ */
+typedef struct rxb_rn50 rxb_rn50; /* opaque */
+typedef struct rxb_rn50_config {
+  int B;             /* samples per call */
+  int G;             /* images per sample: 3 (train/val item) or 6 (test item); a multiple of 3 */
+  int H, W;          /* image size, multiples of 4 (364 in the reference's training, 512 at test time) */
+  int num_classes;   /* 1108 */
+  int size_features; /* 1024 (models.py:11) */
+  float bn_eps;      /* 1e-5 */
+} rxb_rn50_config;
+/* fp32 parameters in the reference model's named_parameters() order (base_nn.conv1.weight, base_nn.bn1.weight, ...,
+ * mlp.6.bias; conv weights OIHW) and fp32 buffers (running_mean, running_var per BatchNorm in module order; the
+ * int64 num_batches_tracked entries are not part of it). */
+int64_t rxb_rn50_param_count(const rxb_rn50_config* cfg);
+int64_t rxb_rn50_buffer_count(const rxb_rn50_config* cfg);
+size_t rxb_rn50_workspace_bytes(const rxb_rn50_config* cfg);
+int rxb_rn50_create(const rxb_rn50_config* cfg, float* params, float* buffers, void* workspace, size_t workspace_bytes,
+                    rxb_rn50** out);
+void rxb_rn50_destroy(rxb_rn50* net);
+/* Re-derive the bf16 GEMM operand copies from the fp32 parameters (after loading a checkpoint). */
+int rxb_rn50_sync_weights(rxb_rn50* net, rxb_stream_t stream);
+/* input: bf16 S2D32 [B*G, H/2, W/2, 32] from rxb_load_norm_aug (sample-major: the G images of a sample are
+ * consecutive, thirds in the reference's order).  logits_out f32 [B, num_classes]. */
+int rxb_rn50_forward(rxb_rn50* net, const void* input_s2d, float* logits_out, rxb_stream_t stream);
+
 /* number of kernels the last forward/train_step/sgd call enqueued (bench.py's gpu_launches). */
 int64_t rxb_launch_count(void);
 void rxb_launch_count_reset(void);

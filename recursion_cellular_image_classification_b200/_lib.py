@@ -35,6 +35,12 @@ class Dn121Config(ctypes.Structure):
                 ("bn_eps", c_float), ("bn_momentum", c_float)]
 
 
+class Rn50Config(ctypes.Structure):
+    """struct rxb_rn50_config (include/rxb.h)."""
+    _fields_ = [("B", c_int), ("G", c_int), ("H", c_int), ("W", c_int), ("num_classes", c_int),
+                ("size_features", c_int), ("bn_eps", c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/rxb.h declares
 SIGNATURES = {
     "rxb_version": (c_int, []),
@@ -80,6 +86,14 @@ SIGNATURES = {
     "rxb_dn121_phase_grad_range": (c_int, [c_void_p, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
     "rxb_dn121_train_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "rxb_dn121_sgd": (c_int, [c_void_p, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+    "rxb_rn50_param_count": (c_int64, [ctypes.POINTER(Rn50Config)]),
+    "rxb_rn50_buffer_count": (c_int64, [ctypes.POINTER(Rn50Config)]),
+    "rxb_rn50_workspace_bytes": (c_size_t, [ctypes.POINTER(Rn50Config)]),
+    "rxb_rn50_create": (c_int, [ctypes.POINTER(Rn50Config), c_void_p, c_void_p, c_void_p, c_size_t,
+                                ctypes.POINTER(c_void_p)]),
+    "rxb_rn50_destroy": (None, [c_void_p]),
+    "rxb_rn50_sync_weights": (c_int, [c_void_p, c_void_p]),
+    "rxb_rn50_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "rxb_launch_count": (c_int64, []),
     "rxb_launch_count_reset": (None, []),
     "rxb_profile_enable": (None, [c_int]),

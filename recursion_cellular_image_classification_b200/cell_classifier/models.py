@@ -22,7 +22,7 @@ from collections import OrderedDict
 import torch
 
 from .. import _lib, ops
-from .._lib import Dn121Config, check, load, ptr, stream_ptr
+from .._lib import Dn121Config, Rn50Config, check, load, ptr, stream_ptr
 
 _BLOCKS = (6, 12, 24, 16)
 
@@ -76,6 +76,8 @@ def to_s2d32(x_nchw):
 
 
 class DenseNet121(torch.nn.Module):
+    wants_controls = False         # a single-image trunk: test() feeds it the sample's own sites only
+
     def __init__(self, nb_classes=1108, device=None, bn_eps=1e-5, bn_momentum=0.1, seed=None):
         super().__init__()
         if device is None:       # buffers live where compute will run; without a GPU only the host-side surface works
@@ -351,14 +353,235 @@ def _pretrained_densenet121_state():
         return None
 
 
+_RN_LAYERS, _RN_WIDTHS = (3, 4, 6, 3), (64, 128, 256, 512)
+
+
+def two_sites_resnet50_param_specs(nb_classes=1108, size_features=1024):
+    """[(name, shape)] of the reference TwoSitesNN (models.py:8-39) in named_parameters() order, and its BatchNorm
+    buffers in module order (a Bottleneck registers bn1, bn2, bn3 and then downsample; running_mean / running_var only,
+    the int64 num_batches_tracked entries are host bookkeeping)."""
+    specs, bufs = [], []
+
+    def bn_p(prefix, c):
+        specs.append((prefix + ".weight", (c,)))
+        specs.append((prefix + ".bias", (c,)))
+
+    def bn_b(prefix, c):
+        bufs.append((prefix + ".running_mean", (c,)))
+        bufs.append((prefix + ".running_var", (c,)))
+
+    specs.append(("base_nn.conv1.weight", (64, 6, 7, 7)))
+    bn_p("base_nn.bn1", 64)
+    bn_b("base_nn.bn1", 64)
+    cin = 64
+    for l, (n_blocks, w) in enumerate(zip(_RN_LAYERS, _RN_WIDTHS), 1):
+        for i in range(n_blocks):
+            p = "base_nn.layer%d.%d" % (l, i)
+            specs.append((p + ".conv1.weight", (w, cin, 1, 1)))
+            bn_p(p + ".bn1", w)
+            specs.append((p + ".conv2.weight", (w, w, 3, 3)))
+            bn_p(p + ".bn2", w)
+            specs.append((p + ".conv3.weight", (4 * w, w, 1, 1)))
+            bn_p(p + ".bn3", 4 * w)
+            bn_b(p + ".bn1", w)
+            bn_b(p + ".bn2", w)
+            bn_b(p + ".bn3", 4 * w)
+            if i == 0:
+                specs.append((p + ".downsample.0.weight", (4 * w, cin, 1, 1)))
+                bn_p(p + ".downsample.1", 4 * w)
+                bn_b(p + ".downsample.1", 4 * w)
+            cin = 4 * w
+    bn_p("mlp.0", 3 * cin)
+    bn_b("mlp.0", 3 * cin)
+    specs.append(("mlp.2.weight", (size_features, 3 * cin)))
+    specs.append(("mlp.2.bias", (size_features,)))
+    bn_p("mlp.4", size_features)
+    bn_b("mlp.4", size_features)
+    specs.append(("mlp.6.weight", (nb_classes, size_features)))
+    specs.append(("mlp.6.bias", (nb_classes,)))
+    return specs, bufs
+
+
+def _reference_two_sites_init(pretrained, nb_classes, size_features, dropout, seed):
+    """Initial values exactly as the reference constructor produces them (models.py:14-39): torchvision resnet50, the
+    6-channel stem from the channel mean of its 3-channel kernel, then the MLP — host-side torch modules used for
+    their initialisers only (and, with pretrained=True, for torchvision's ImageNet weights when they can be had)."""
+    import torchvision
+    if seed is not None:
+        torch.manual_seed(seed)
+    base, loaded = None, False
+    if pretrained:
+        try:
+            base = torchvision.models.resnet50(weights="IMAGENET1K_V1")
+            loaded = True
+        except Exception:
+            import warnings
+            warnings.warn("TwoSitesNN(pretrained=True, trunk='resnet50'): ImageNet resnet50 weights are not available "
+                          "(no network / cache) - continuing from random initialisation")
+    if base is None:
+        base = torchvision.models.resnet50(weights=None)
+    kernel = base.conv1.weight.detach()
+    torch.nn.Conv2d(6, 64, kernel_size=7, stride=2, padding=3, bias=False)              # models.py:18-23 draws its own
+    stem = torch.stack([torch.mean(kernel, 1)] * 6, dim=1)                              # init first; then :24-26
+    n_feat = 3 * base.fc.in_features
+    mlp = torch.nn.Sequential(torch.nn.BatchNorm1d(n_feat), torch.nn.Dropout(dropout), torch.nn.Linear(n_feat, size_features),
+                              torch.nn.ReLU(), torch.nn.BatchNorm1d(size_features), torch.nn.Dropout(dropout),
+                              torch.nn.Linear(size_features, nb_classes))
+    sd = {"base_nn." + k: v for k, v in base.state_dict().items() if not k.startswith("fc.")}
+    sd["base_nn.conv1.weight"] = stem
+    sd.update({"mlp." + k: v for k, v in mlp.state_dict().items()})
+    return sd, loaded
+
+
+class TwoSitesResNet50(torch.nn.Module):
+    """The reference's real model (models.py:7-57) on the device, evaluation mode: ResNet-50 trunk, feature means of
+    the image / negative-control / positive-control thirds of an item concatenated, BatchNorm1d/Dropout/Linear MLP
+    head — executed by librxb's rxb_rn50 executor (csrc/resnet.cu, tcgen05 implicit-GEMM convolutions).  state_dict()
+    / load_state_dict() speak the reference's own names (`base_nn.*`, `mlp.*`, optionally `module.`-prefixed), so a
+    checkpoint written by the reference's train() loads unchanged.  Training this trunk natively is not implemented:
+    forward() in training mode raises (no silent fallback to PyTorch)."""
+
+    wants_controls = True          # test() must hand it the full reference item (image + control thirds)
+
+    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None, seed=None,
+                 bn_eps=1e-5):
+        super().__init__()
+        if device is None:
+            from ..parallel import default_device
+            device = default_device()
+        self.nb_classes, self.size_features, self.dropout, self.bn_eps = nb_classes, size_features, dropout, bn_eps
+        self.specs, self.buf_specs = two_sites_resnet50_param_specs(nb_classes, size_features)
+        n = sum(math.prod(sh) for _, sh in self.specs)
+        nb = sum(math.prod(sh) for _, sh in self.buf_specs)
+        dev = torch.device(device)
+        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32, device=dev), requires_grad=False)
+        self.register_buffer("bn_buffers", torch.zeros(nb, dtype=torch.float32, device=dev))
+        self._views, self._bviews, off = OrderedDict(), OrderedDict(), 0
+        for name, shape in self.specs:
+            k = math.prod(shape)
+            self._views[name] = (off, k, shape)
+            off += k
+        off = 0
+        for name, shape in self.buf_specs:
+            k = math.prod(shape)
+            self._bviews[name] = (off, k, shape)
+            off += k
+        self._plans = {}
+        self._weights_dirty = True
+        sd, self.pretrained_loaded = _reference_two_sites_init(pretrained, nb_classes, size_features, dropout, seed)
+        self.load_state_dict(sd)
+        self.eval()
+
+    def view(self, name):
+        off, k, shape = self._views[name]
+        return self.flat.data[off:off + k].view(shape)
+
+    def buffer_view(self, name):
+        off, k, shape = self._bviews[name]
+        return self.bn_buffers[off:off + k].view(shape)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        if args:
+            destination, prefix, keep_vars = (list(args) + [prefix, keep_vars])[:3] if len(args) < 3 else args[:3]
+        sd = OrderedDict() if destination is None else destination
+        for name in self._views:
+            sd[prefix + name] = self.view(name).clone()
+        for name in self._bviews:
+            sd[prefix + name] = self.buffer_view(name).clone()
+        return sd
+
+    def _copy_from(self, sd, prefix, strict, missing):
+        with torch.no_grad():
+            for table, getter in ((self._views, self.view), (self._bviews, self.buffer_view)):
+                for name in table:
+                    key = prefix + name
+                    if key not in sd and not prefix and "module." + name in sd:
+                        key = "module." + name                       # DataParallel-prefixed checkpoint (main.py:147)
+                    if key in sd:
+                        getter(name).copy_(sd[key])
+                    elif strict:
+                        missing.append(key)
+        self._weights_dirty = True
+
+    def load_state_dict(self, sd, strict=True):
+        missing = []
+        self._copy_from(sd, "", strict, missing)
+        if missing:
+            raise KeyError(missing[0])
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        self._copy_from(state_dict, prefix, strict, missing_keys)
+
+    def _plan(self, B, G, H, W):
+        key = (B, G, H, W)
+        if key in self._plans:
+            return self._plans[key]
+        _lib.require_gpu()
+        lib = load()
+        for old in list(self._plans):                                # one live plan (a plan owns its workspace)
+            lib.rxb_rn50_destroy(self._plans.pop(old)["handle"])
+        cfg = Rn50Config(B, G, H, W, self.nb_classes, self.size_features, self.bn_eps)
+        assert lib.rxb_rn50_param_count(ctypes.byref(cfg)) == self.flat.numel()
+        assert lib.rxb_rn50_buffer_count(ctypes.byref(cfg)) == self.bn_buffers.numel()
+        nbytes = lib.rxb_rn50_workspace_bytes(ctypes.byref(cfg))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+        handle = ctypes.c_void_p()
+        check(lib.rxb_rn50_create(ctypes.byref(cfg), ptr(self.flat.data), ptr(self.bn_buffers), ptr(ws), nbytes,
+                                  ctypes.byref(handle)))
+        plan = {"handle": handle, "ws": ws, "synced": False}
+        self._plans[key] = plan
+        return plan
+
+    def __del__(self):
+        try:
+            lib = load()
+            for p in self._plans.values():
+                lib.rxb_rn50_destroy(p["handle"])
+        except Exception:
+            pass
+
+    def forward(self, x, G=None):
+        """x: float [B,G,6,H,W] (the reference's item layout, models.py:42) or the fused loader's bf16 S2D32
+        [B*G,H/2,W/2,32] together with G.  Returns logits f32 [B, nb_classes]."""
+        if self.training:
+            raise _lib.RxbError("TwoSitesResNet50 runs in evaluation mode only (call .eval()): training the ResNet-50 "
+                                "trunk natively is not implemented, and there is no PyTorch fallback")
+        if x.dim() == 5:
+            G = x.shape[1]
+            x = to_s2d32(x.reshape(-1, *x.shape[2:]).to(self.flat.device))
+        elif G is None:
+            raise _lib.RxbError("TwoSitesResNet50: a loader-layout batch needs G (images per sample)")
+        x = x.contiguous()
+        B, H, W = x.shape[0] // G, x.shape[1] * 2, x.shape[2] * 2
+        plan = self._plan(B, G, H, W)
+        if self._weights_dirty or not plan["synced"]:
+            check(load().rxb_rn50_sync_weights(plan["handle"], stream_ptr()))
+            plan["synced"], self._weights_dirty = True, False
+        logits = torch.empty(B, self.nb_classes, dtype=torch.float32, device=x.device)
+        check(load().rxb_rn50_forward(plan["handle"], ptr(x), ptr(logits), stream_ptr()))
+        return logits
+
+
 class TwoSitesNN(DenseNet121):
-    """Reference constructor signature (models.py:8-12); DenseNet-121 trunk per the north star.
+    """Reference constructor signature (models.py:8-12).  trunk='densenet121' (default, the north star's trunk; also
+    RXB_TRUNK=densenet121) or trunk='resnet50' (RXB_TRUNK=resnet50): the reference's own model, evaluation mode —
+    then the object returned is a TwoSitesResNet50.
     pretrained=True (main.py:43 sets it whenever CUDA is available) loads torchvision's ImageNet densenet121 through
     the reference's stem surgery (3-channel stem -> channel mean replicated 6x, models.py:24-26; the 1000-class head is
     dropped); when the weights cannot be found (no network, no RXB_PRETRAINED_DENSENET121 file) it warns and keeps the
     random initialisation instead of failing, so an unchanged main.py still runs."""
 
-    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None):
+    def __new__(cls, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None, trunk=None):
+        import os
+        trunk = trunk or os.environ.get("RXB_TRUNK", "densenet121")
+        if trunk == "resnet50":
+            return TwoSitesResNet50(pretrained=pretrained, nb_classes=nb_classes, size_features=size_features,
+                                    dropout=dropout, device=device)
+        if trunk != "densenet121":
+            raise ValueError("trunk must be 'densenet121' or 'resnet50'")
+        return super().__new__(cls)
+
+    def __init__(self, pretrained=False, nb_classes=1108, size_features=1024, dropout=0.3, device=None, trunk=None):
         super().__init__(nb_classes=nb_classes, device=device)
         self.pretrained_loaded = False
         if pretrained:

@@ -676,6 +676,7 @@ repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ aren
     case RP_1x1_DGRAD: total = (long long)N * K; break;
     case RP_3x3_FWD:
     case RP_3x3_DGRAD: total = 9ll * N * K; break;
+    case RP_3x3S2_FWD: total = 16ll * N * K; break;   // [4 taps][N][4K]
     default: total = 16ll * N * 32; break;  // stem: [16 taps][N][32]
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -697,6 +698,15 @@ repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ aren
         const long long r = i / N;
         const int k = (int)(r % K), tapf = (int)(r / K);
         v = src[((long long)n * K + k) * 9 + (8 - tapf)];
+      } break;
+      case RP_3x3S2_FWD: {                                      // dst[(sy,sx)][n][(py*2+px)*K + c] = W[n][c][dy][dx]
+        const int cc = (int)(i % (4 * K));
+        const long long r = i / (4 * K);
+        const int n = (int)(r % N), tap = (int)(r / N);
+        const int sy = tap >> 1, sx = tap & 1;
+        const int q = cc / K, c = cc - q * K;
+        const int dy = 2 * sy + (q >> 1) - 1, dx = 2 * sx + (q & 1) - 1;
+        if (dy >= 0 && dy < 3 && dx >= 0 && dx < 3) v = src[(((long long)n * K + c) * 3 + dy) * 3 + dx];
       } break;
       default: {                                                // stem: dst[(sy,sx)][n][(py,px,c)] = W[n][c][dy][dx]
         const int cc = (int)(i % 32);

@@ -80,7 +80,10 @@ int column_sum(const float* A, int rows, int cols, long long ld, float* out, cud
 int sum_scale(const float* v, int n, float scale, float* out, cudaStream_t st);
 
 // fp32 OIHW master weights -> bf16 GEMM operand layouts (one launch over a job table).
-enum RepackType { RP_1x1_FWD = 0, RP_1x1_DGRAD = 1, RP_3x3_FWD = 2, RP_3x3_DGRAD = 3, RP_STEM_FWD = 4 };
+enum RepackType { RP_1x1_FWD = 0, RP_1x1_DGRAD = 1, RP_3x3_FWD = 2, RP_3x3_DGRAD = 3, RP_STEM_FWD = 4,
+                  // 3x3 stride-2 pad-1 weights as the 2x2-tap stride-1 operand over the 2x2 space-to-depth input
+                  // (resnet_ops.cuh s2d_bn_relu): dst[(sy,sx)][n][(py*2+px)*K + c] = W[n][c][2sy+py-1][2sx+px-1] (0 outside)
+                  RP_3x3S2_FWD = 5 };
 struct RepackJob {
   long long src_off;   // into the flat fp32 parameter buffer
   long long dst_off;   // into the bf16 operand arena (elements)

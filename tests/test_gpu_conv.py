@@ -49,6 +49,16 @@ CASES = [
     # two accumulator stages and both staging buffers wrap several times
     (16, 128, 128, 224, 256, 128, 1, True),  # last dense layer of block 1
     (16, 128, 128, 128, 128, 32, 3, True),   # x-merged 3x3, 2960 tiles / 148 CTAs = 20 per CTA
+    # ResNet-50 bottleneck shapes (csrc/resnet.cu): wide 3x3 convs whose weight panel is streamed (row-halo mode),
+    # several N tiles, odd image sizes, and the 2x2-tap form of a stride-2 3x3 over a space-to-depth input
+    (2, 23, 23, 256, 256, 256, 3, True),
+    (3, 12, 12, 512, 512, 512, 3, True),
+    (2, 46, 46, 128, 128, 128, 3, True),
+    (2, 91, 91, 64, 64, 64, 3, True),
+    (2, 46, 46, 512, 512, 128, 2, False),
+    (4, 6, 6, 2048, 2048, 512, 2, False),
+    (2, 12, 12, 2048, 2048, 512, 1, False),
+    (2, 23, 23, 256, 256, 1024, 1, True),
 ]
 
 
@@ -61,7 +71,7 @@ def test_conv_fwd_matches_torch(cuda, B, H, W, Cin, ldA, Cout, k, prologue):
     if prologue:
         scale = torch.rand(Cin, generator=gen) + 0.5
         shift = torch.randn(Cin, generator=gen) * 0.3
-    pad = {1: 0, 3: 1, 4: 2}[k]
+    pad = {1: 0, 2: 1, 3: 1, 4: 2}[k]
     # the 4x4 stem reads rows y+ty-2: torch's symmetric padding 2 gives one extra row/col at the end
     ref = _ref_conv(A[..., :Cin], Wt, pad, scale, shift)[:, :H, :W]
     ldC, c_off = Cout + 64, 32

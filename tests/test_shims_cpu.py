@@ -581,3 +581,35 @@ def test_config4_case_is_well_separated(tmp_path):
         noise = rng.standard_normal(L.shape).astype(np.float32)
         noise *= 0.06 * np.linalg.norm(L) / np.linalg.norm(noise)
         np.testing.assert_array_equal(C.oracle_assign(L + noise, pg, df.plate.values)[1], res)
+
+
+def test_two_sites_resnet50_layout_is_the_references(tmp_path):
+    """Host side of TwoSitesResNet50 (no GPU): parameter / buffer names, order and shapes are the reference model's
+    own (through the oracle restatement that is pinned against the reference's golden logits), a seed reproduces the
+    reference constructor's initial weights, `module.`-prefixed checkpoints load, and TwoSitesNN(trunk=...) selects it."""
+    import ctypes
+    from oracle import oracle_np as O
+    from recursion_cellular_image_classification_b200 import _lib
+    from recursion_cellular_image_classification_b200.cell_classifier.models import (TwoSitesNN, TwoSitesResNet50,
+                                                                                      two_sites_resnet50_param_specs)
+    ref = O.two_sites_resnet50(seed=5)
+    specs, bufs = two_sites_resnet50_param_specs()
+    assert [(n, tuple(p.shape)) for n, p in ref.named_parameters()] == [(n, tuple(s)) for n, s in specs]
+    assert [n for n, _ in ref.named_buffers() if "num_batches" not in n] == [n for n, _ in bufs]
+    net = TwoSitesResNet50(device="cpu", seed=5)
+    sd = net.state_dict()
+    for k, v in ref.state_dict().items():
+        if "num_batches" not in k:
+            assert torch.equal(sd[k], v), k
+    cfg = _lib.Rn50Config(2, 3, 64, 64, 1108, 1024, 1e-5)
+    lib = _lib.load()
+    assert lib.rxb_rn50_param_count(ctypes.byref(cfg)) == net.flat.numel() == sum(p.numel() for p in ref.parameters())
+    assert lib.rxb_rn50_buffer_count(ctypes.byref(cfg)) == net.bn_buffers.numel()
+    net2 = TwoSitesNN(pretrained=False, nb_classes=1108, trunk="resnet50", device="cpu")
+    assert isinstance(net2, TwoSitesResNet50) and net2.wants_controls
+    net2.load_state_dict({"module." + k: v for k, v in sd.items()})
+    assert torch.equal(net2.flat.data, net.flat.data)
+    net2.train()
+    with pytest.raises(_lib.RxbError):
+        net2(torch.zeros(1, 3, 6, 32, 32))
+    assert not isinstance(TwoSitesNN(pretrained=False, device="cpu"), TwoSitesResNet50)
