@@ -261,8 +261,9 @@ int rxb_dn121_sgd(rxb_dn121* net, float lr, float mu, float wd, int nesterov, fl
  * positive-control thirds concatenated (models.py:44-53), and the BatchNorm1d -> Dropout -> Linear(6144,
  * size_features) -> ReLU -> BatchNorm1d -> Dropout -> Linear(size_features, num_classes) head (models.py:31-39).
  * Replaces TwoSitesNN.forward as test.py:23-27 calls it (model.eval(): running statistics, Dropout = identity), so a
- * checkpoint trained with the reference (main.py:147) can be served natively.  Convolutions are the tcgen05
- * implicit GEMMs above (stride-2 3x3 as a 2x2-tap convolution over a space-to-depth pass, see csrc/resnet.cu).
+ * checkpoint trained with the reference (main.py:147) can be served natively, and the reference's train step
+ * (rxb_rn50_train_step / rxb_rn50_sgd below).  Convolutions are the tcgen05 implicit GEMMs above (stride-2 3x3 as a
+ * 2x2-tap convolution over a space-to-depth pass, see csrc/resnet.cu).
  */
 typedef struct rxb_rn50 rxb_rn50; /* opaque */
 typedef struct rxb_rn50_config {
@@ -272,21 +273,38 @@ typedef struct rxb_rn50_config {
   int num_classes;   /* 1108 */
   int size_features; /* 1024 (models.py:11) */
   float bn_eps;      /* 1e-5 */
+  float bn_momentum; /* 0.1 (training: running-statistics update) */
 } rxb_rn50_config;
 /* fp32 parameters in the reference model's named_parameters() order (base_nn.conv1.weight, base_nn.bn1.weight, ...,
  * mlp.6.bias; conv weights OIHW) and fp32 buffers (running_mean, running_var per BatchNorm in module order; the
  * int64 num_batches_tracked entries are not part of it). */
 int64_t rxb_rn50_param_count(const rxb_rn50_config* cfg);
 int64_t rxb_rn50_buffer_count(const rxb_rn50_config* cfg);
-size_t rxb_rn50_workspace_bytes(const rxb_rn50_config* cfg);
-int rxb_rn50_create(const rxb_rn50_config* cfg, float* params, float* buffers, void* workspace, size_t workspace_bytes,
-                    rxb_rn50** out);
+int64_t rxb_rn50_head_offset(const rxb_rn50_config* cfg);   /* first mlp.* parameter: the head is the flat buffer's tail */
+size_t rxb_rn50_workspace_bytes(const rxb_rn50_config* cfg, int training);
+/* grads / momentum (fp32[param_count]) are needed for training plans only. */
+int rxb_rn50_create(const rxb_rn50_config* cfg, float* params, float* grads, float* momentum, float* buffers,
+                    void* workspace, size_t workspace_bytes, int training, rxb_rn50** out);
 void rxb_rn50_destroy(rxb_rn50* net);
 /* Re-derive the bf16 GEMM operand copies from the fp32 parameters (after loading a checkpoint). */
 int rxb_rn50_sync_weights(rxb_rn50* net, rxb_stream_t stream);
 /* input: bf16 S2D32 [B*G, H/2, W/2, 32] from rxb_load_norm_aug (sample-major: the G images of a sample are
  * consecutive, thirds in the reference's order).  logits_out f32 [B, num_classes]. */
 int rxb_rn50_forward(rxb_rn50* net, const void* input_s2d, float* logits_out, rxb_stream_t stream);
+/* The reference's train step on this rank's B samples (train.py:37,44: zero_grad, forward in training mode,
+ * CrossEntropy mean over `global_batch`, backward): BatchNorm2d / BatchNorm1d with batch statistics (running statistics
+ * updated), Dropout(p) as multiplication by the caller's masks (f32 [B, 3*2048] and [B, size_features] holding 0 or
+ * 1/(1-p): the caller owns the random stream, which is what makes parity testable), gradients of every parameter
+ * into grads (overwritten).  loss_out f32[1]: this rank's share of the mean loss; logits_out f32[B,num_classes] or
+ * NULL: the training-mode logits. */
+int rxb_rn50_train_step(rxb_rn50* net, const void* input_s2d, const int64_t* target, const float* drop_mask0,
+                        const float* drop_mask1, int global_batch, float* loss_out, float* logits_out,
+                        rxb_stream_t stream);
+/* nesterov SGD (main.py:89-93) on the flat buffers, then refresh the bf16 operands.  head_only = 1 updates the mlp.*
+ * parameters alone: the reference's first two epochs with a pretrained trunk (train.py:46-58 freezes every child of
+ * the model except 'mlp'). */
+int rxb_rn50_sgd(rxb_rn50* net, float lr, float mu, float wd, int nesterov, float grad_scale, int head_only,
+                 rxb_stream_t stream);
 
 /* number of kernels the last forward/train_step/sgd call enqueued (bench.py's gpu_launches). */
 int64_t rxb_launch_count(void);

@@ -38,7 +38,7 @@ class Dn121Config(ctypes.Structure):
 class Rn50Config(ctypes.Structure):
     """struct rxb_rn50_config (include/rxb.h)."""
     _fields_ = [("B", c_int), ("G", c_int), ("H", c_int), ("W", c_int), ("num_classes", c_int),
-                ("size_features", c_int), ("bn_eps", c_float)]
+                ("size_features", c_int), ("bn_eps", c_float), ("bn_momentum", c_float)]
 
 
 # name -> (restype, argtypes); every symbol include/rxb.h declares
@@ -88,9 +88,13 @@ SIGNATURES = {
     "rxb_dn121_sgd": (c_int, [c_void_p, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     "rxb_rn50_param_count": (c_int64, [ctypes.POINTER(Rn50Config)]),
     "rxb_rn50_buffer_count": (c_int64, [ctypes.POINTER(Rn50Config)]),
-    "rxb_rn50_workspace_bytes": (c_size_t, [ctypes.POINTER(Rn50Config)]),
-    "rxb_rn50_create": (c_int, [ctypes.POINTER(Rn50Config), c_void_p, c_void_p, c_void_p, c_size_t,
-                                ctypes.POINTER(c_void_p)]),
+    "rxb_rn50_head_offset": (c_int64, [ctypes.POINTER(Rn50Config)]),
+    "rxb_rn50_workspace_bytes": (c_size_t, [ctypes.POINTER(Rn50Config), c_int]),
+    "rxb_rn50_create": (c_int, [ctypes.POINTER(Rn50Config), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                c_int, ctypes.POINTER(c_void_p)]),
+    "rxb_rn50_train_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
+    "rxb_rn50_sgd": (c_int, [c_void_p, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]),
     "rxb_rn50_destroy": (None, [c_void_p]),
     "rxb_rn50_sync_weights": (c_int, [c_void_p, c_void_p]),
     "rxb_rn50_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

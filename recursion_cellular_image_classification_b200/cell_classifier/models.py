@@ -438,8 +438,11 @@ class TwoSitesResNet50(torch.nn.Module):
     the image / negative-control / positive-control thirds of an item concatenated, BatchNorm1d/Dropout/Linear MLP
     head — executed by librxb's rxb_rn50 executor (csrc/resnet.cu, tcgen05 implicit-GEMM convolutions).  state_dict()
     / load_state_dict() speak the reference's own names (`base_nn.*`, `mlp.*`, optionally `module.`-prefixed), so a
-    checkpoint written by the reference's train() loads unchanged.  Training this trunk natively is not implemented:
-    forward() in training mode raises (no silent fallback to PyTorch)."""
+    checkpoint written by the reference's train() loads unchanged.  Training runs natively too: `train_step()` is the
+    reference's step (BatchNorm batch statistics, Dropout, CrossEntropy, full backward) and `sgd_step()` its optimizer,
+    with `head_only=True` for the two-epoch freeze of a pretrained trunk (train.py:46-67); cell_classifier.train.train()
+    drives them.  forward() itself is evaluation only: in training mode it raises (there is no autograd graph to hand
+    to an external trainer, and no PyTorch fallback)."""
 
     wants_controls = True          # test() must hand it the full reference item (image + control thirds)
 
@@ -454,8 +457,11 @@ class TwoSitesResNet50(torch.nn.Module):
         n = sum(math.prod(sh) for _, sh in self.specs)
         nb = sum(math.prod(sh) for _, sh in self.buf_specs)
         dev = torch.device(device)
-        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32, device=dev), requires_grad=False)
+        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32, device=dev))
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.register_buffer("momentum_buf", torch.zeros(n, dtype=torch.float32, device=dev))
         self.register_buffer("bn_buffers", torch.zeros(nb, dtype=torch.float32, device=dev))
+        self.bn_momentum = 0.1
         self._views, self._bviews, off = OrderedDict(), OrderedDict(), 0
         for name, shape in self.specs:
             k = math.prod(shape)
@@ -475,6 +481,10 @@ class TwoSitesResNet50(torch.nn.Module):
     def view(self, name):
         off, k, shape = self._views[name]
         return self.flat.data[off:off + k].view(shape)
+
+    def grad_view(self, name):
+        off, k, shape = self._views[name]
+        return self.flat.grad[off:off + k].view(shape)
 
     def buffer_view(self, name):
         off, k, shape = self._bviews[name]
@@ -497,7 +507,7 @@ class TwoSitesResNet50(torch.nn.Module):
                     key = prefix + name
                     if key not in sd and not prefix and "module." + name in sd:
                         key = "module." + name                       # DataParallel-prefixed checkpoint (main.py:147)
-                    if key in sd:
+                    if key in sd and tuple(sd[key].shape) == tuple(getter(name).shape):
                         getter(name).copy_(sd[key])
                     elif strict:
                         missing.append(key)
@@ -512,25 +522,34 @@ class TwoSitesResNet50(torch.nn.Module):
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         self._copy_from(state_dict, prefix, strict, missing_keys)
 
-    def _plan(self, B, G, H, W):
-        key = (B, G, H, W)
+    def _plan(self, B, G, H, W, training=False):
+        key = (B, G, H, W, bool(training))
         if key in self._plans:
             return self._plans[key]
         _lib.require_gpu()
         lib = load()
-        for old in list(self._plans):                                # one live plan (a plan owns its workspace)
+        for old in [k for k in self._plans if k[4] == bool(training)]:          # one live plan per mode
             lib.rxb_rn50_destroy(self._plans.pop(old)["handle"])
-        cfg = Rn50Config(B, G, H, W, self.nb_classes, self.size_features, self.bn_eps)
+        cfg = Rn50Config(B, G, H, W, self.nb_classes, self.size_features, self.bn_eps, self.bn_momentum)
         assert lib.rxb_rn50_param_count(ctypes.byref(cfg)) == self.flat.numel()
         assert lib.rxb_rn50_buffer_count(ctypes.byref(cfg)) == self.bn_buffers.numel()
-        nbytes = lib.rxb_rn50_workspace_bytes(ctypes.byref(cfg))
+        nbytes = lib.rxb_rn50_workspace_bytes(ctypes.byref(cfg), 1 if training else 0)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
         handle = ctypes.c_void_p()
-        check(lib.rxb_rn50_create(ctypes.byref(cfg), ptr(self.flat.data), ptr(self.bn_buffers), ptr(ws), nbytes,
-                                  ctypes.byref(handle)))
+        check(lib.rxb_rn50_create(ctypes.byref(cfg), ptr(self.flat.data), ptr(self.flat.grad), ptr(self.momentum_buf),
+                                  ptr(self.bn_buffers), ptr(ws), nbytes, 1 if training else 0, ctypes.byref(handle)))
         plan = {"handle": handle, "ws": ws, "synced": False}
         self._plans[key] = plan
         return plan
+
+    def _sync(self, plan):
+        if self._weights_dirty:
+            for p in self._plans.values():
+                p["synced"] = False
+            self._weights_dirty = False
+        if not plan["synced"]:
+            check(load().rxb_rn50_sync_weights(plan["handle"], stream_ptr()))
+            plan["synced"] = True
 
     def __del__(self):
         try:
@@ -540,26 +559,63 @@ class TwoSitesResNet50(torch.nn.Module):
         except Exception:
             pass
 
-    def forward(self, x, G=None):
-        """x: float [B,G,6,H,W] (the reference's item layout, models.py:42) or the fused loader's bf16 S2D32
-        [B*G,H/2,W/2,32] together with G.  Returns logits f32 [B, nb_classes]."""
-        if self.training:
-            raise _lib.RxbError("TwoSitesResNet50 runs in evaluation mode only (call .eval()): training the ResNet-50 "
-                                "trunk natively is not implemented, and there is no PyTorch fallback")
+    def _as_s2d(self, x, G):
         if x.dim() == 5:
             G = x.shape[1]
             x = to_s2d32(x.reshape(-1, *x.shape[2:]).to(self.flat.device))
         elif G is None:
             raise _lib.RxbError("TwoSitesResNet50: a loader-layout batch needs G (images per sample)")
-        x = x.contiguous()
+        return x.contiguous(), G
+
+    def forward(self, x, G=None):
+        """x: float [B,G,6,H,W] (the reference's item layout, models.py:42) or the fused loader's bf16 S2D32
+        [B*G,H/2,W/2,32] together with G.  Returns logits f32 [B, nb_classes].  Evaluation mode only."""
+        if self.training:
+            raise _lib.RxbError("TwoSitesResNet50.forward runs in evaluation mode only (call .eval()); training goes "
+                                "through train_step() / sgd_step() - there is no autograd graph and no PyTorch fallback")
+        x, G = self._as_s2d(x, G)
         B, H, W = x.shape[0] // G, x.shape[1] * 2, x.shape[2] * 2
-        plan = self._plan(B, G, H, W)
-        if self._weights_dirty or not plan["synced"]:
-            check(load().rxb_rn50_sync_weights(plan["handle"], stream_ptr()))
-            plan["synced"], self._weights_dirty = True, False
+        plan = self._plan(B, G, H, W, False)
+        self._sync(plan)
         logits = torch.empty(B, self.nb_classes, dtype=torch.float32, device=x.device)
         check(load().rxb_rn50_forward(plan["handle"], ptr(x), ptr(logits), stream_ptr()))
         return logits
+
+    def dropout_masks(self, B, generator=None):
+        """The two Dropout(p) masks of the head (models.py:33,37) as multipliers: 0 with probability p, else 1/(1-p)."""
+        dev, p = self.flat.device, self.dropout
+        keep = 1.0 - p
+        draw = lambda f: (torch.rand(B, f, device=dev, generator=generator) < keep).float() / keep
+        return draw(3 * 2048), draw(self.size_features)
+
+    def train_step(self, x, target, G=None, masks=None, global_batch=None, loss_out=None, logits_out=None):
+        """The reference's train step natively (train.py:37,44): forward with batch statistics and Dropout, mean
+        CrossEntropy over global_batch samples, backward into self.flat.grad.  `masks` = dropout_masks(B) unless
+        given (explicit masks make the step reproducible).  Returns the device scalar with this rank's loss share."""
+        x, G = self._as_s2d(x, G)
+        B, H, W = x.shape[0] // G, x.shape[1] * 2, x.shape[2] * 2
+        plan = self._plan(B, G, H, W, True)
+        self._sync(plan)
+        m0, m1 = masks if masks is not None else self.dropout_masks(B)
+        if loss_out is None:
+            loss_out = torch.empty(1, dtype=torch.float32, device=x.device)
+        check(load().rxb_rn50_train_step(plan["handle"], ptr(x), ptr(target.contiguous()), ptr(m0.contiguous()),
+                                         ptr(m1.contiguous()), global_batch or B, ptr(loss_out), ptr(logits_out),
+                                         stream_ptr()))
+        return loss_out
+
+    def head_range(self):
+        """[begin, end) of the mlp.* parameters in the flat buffers (what stays trainable while a pretrained trunk is
+        frozen, train.py:46-58)."""
+        off, _, _ = self._views["mlp.0.weight"]
+        return off, self.flat.numel()
+
+    def sgd_step(self, B, G, H, W, lr, momentum=0.9, weight_decay=3e-5, nesterov=True, grad_scale=1.0, head_only=False):
+        plan = self._plan(B, G, H, W, True)
+        check(load().rxb_rn50_sgd(plan["handle"], lr, momentum, weight_decay, 1 if nesterov else 0, grad_scale,
+                                  1 if head_only else 0, stream_ptr()))
+        for p in self._plans.values():
+            p["synced"] = p is plan
 
 
 class TwoSitesNN(DenseNet121):

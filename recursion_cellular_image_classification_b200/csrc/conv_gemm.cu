@@ -1166,6 +1166,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.w_mode == 0) {
             base = (long long)ch * taps + tp;
             nstride = (long long)p.cin * taps;
+          } else if (p.w_mode == 2) {
+            // 3x3 stride-2 weights behind the 2x2-tap space-to-depth form (resnet.cu): tap (sy,sx) of 2x2,
+            // ch = (py*2+px)*K + c with K = cin/4  ->  W[n][c][dy][dx], dy = 2*sy+py-1, dx = 2*sx+px-1
+            const int K4 = p.cin >> 2;
+            const int sy = tp / p.taps_x, sx = tp - sy * p.taps_x;
+            const int qq = ch / K4, c = ch - qq * K4;
+            const int dy = 2 * sy + (qq >> 1) - 1, dx = 2 * sx + (qq & 1) - 1;
+            ok = ok && dy >= 0 && dy < 3 && dx >= 0 && dx < 3;
+            base = ((long long)c * 3 + dy) * 3 + dx;
+            nstride = (long long)K4 * 9;
           } else {  // space-to-depth stem: tap (sy,sx) of 4x4, ch = (py*2+px)*8 + c  ->  W[n][c][dy][dx], 7x7, 6 ch
             const int sy = tp / p.taps_x, sx = tp - sy * p.taps_x;
             const int c = ch & 7, px = (ch >> 3) & 1, py = (ch >> 4) & 1;

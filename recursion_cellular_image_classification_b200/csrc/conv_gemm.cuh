@@ -99,7 +99,8 @@ struct WgradParams {
   const float* shift;
   float* dW;            // fp32, torch OIHW [Cout_total][cin_w][taps_y_w][taps_x_w], atomically accumulated
   int cout_total;
-  int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch)
+  int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch) ;
+                        // 2: 3x3 stride-2 weights behind the 2x2-tap space-to-depth conv (cin = 4 x real channels)
   int a_halo;           // 1: multi-tap, bkc*taps_x == 128, no prologue: ONE full-halo A box per pixel tile; chunk = filter
                         //    row ty whose taps_x taps are M atoms one pixel row apart (the stem's 4x4 taps)
   unsigned long long* dbg;  // development timeline of CTA (0,0) (RXB_DBG_TIMELINE), else nullptr

@@ -392,8 +392,8 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 // dx = scale*(dy - m1 - xhat*m2) = scale*dy + cb*x + cc  with  cb = -scale*rstd*m2,  cc = scale*(rstd*m2*mean - m1).
 // A thread keeps ONE channel group (its folded constants live in registers) and walks pixels, four rows in flight.
 __global__ void __launch_bounds__(kEwThreads)
-bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
-                    BnFold f, const float* __restrict__ m1, const float* __restrict__ m2) {
+bn_bwd_apply_kernel(__nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
+                    BnFold f, const float* __restrict__ m1, const float* __restrict__ m2, __nv_bfloat16* dst) {
   pdl_sync();
   const int groups = C >> 3;                         // divides the block size (C = 64 or 128)
   const int cg = threadIdx.x % groups;
@@ -428,7 +428,7 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       unpack8(xv[u], x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
-      st_stream_v4(dy + (row + u * stride) * C + cg * 8, pack8(d));
+      st_stream_v4(dst + (row + u * stride) * C + cg * 8, pack8(d));
     }
   }
   for (; row < M; row += stride) {
@@ -437,16 +437,46 @@ bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     unpack8(ld_stream_v4(X + row * C + cg * 8), x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
-    st_stream_v4(dy + row * C + cg * 8, pack8(d));
+    st_stream_v4(dst + row * C + cg * 8, pack8(d));
+  }
+}
+
+// Channel counts that do not divide the 256-thread block (ResNet's 2048-wide maps are fine; anything with C/8 > 256 or
+// not a power of two): a plain grid-stride variant, one 8-channel group per thread per iteration.
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_wide_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long long M, int C, BnFold f,
+                         const float* __restrict__ m1, const float* __restrict__ m2, __nv_bfloat16* dst) {
+  pdl_sync();
+  const int groups = C >> 3;
+  const long long total = M * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    float sc[8], mu[8], rs[8], a1[8], a2[8], d[8], x[8];
+    load8f(f.scale + cg * 8, sc);
+    load8f(f.mean + cg * 8, mu);
+    load8f(f.rstd + cg * 8, rs);
+    load8f(m1 + cg * 8, a1);
+    load8f(m2 + cg * 8, a2);
+    unpack8(*reinterpret_cast<const uint4*>(dy + i * 8), d);
+    unpack8(ld_stream_v4(X + i * 8), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = sc[e] * (d[e] - a1[e] - (x[e] - mu[e]) * rs[e] * a2[e]);
+    st_stream_v4(dst + i * 8, pack8(d));
   }
 }
 
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st) {
-  if (C % 8 || kEwThreads % (C / 8)) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must divide into the block", C);
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst) {
+  if (C % 8) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+  if (dst == nullptr) dst = dy;
   RXB_PROF(st, PROF_EW_BN_APPLY);
-  const int rows_per_block = kEwThreads / (C / 8);
-  RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2));
+  if (C / 8 > kEwThreads || kEwThreads % (C / 8)) {
+    RXB_CUDA(launch_k(bn_bwd_apply_wide_kernel, dim3(ew_grid(M * (C / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st,
+                      (const __nv_bfloat16*)dy, X, M, C, f, m1, m2, dst));
+  } else {
+    const int rows_per_block = kEwThreads / (C / 8);
+    RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2, dst));
+  }
   RXB_LAUNCH_OK();
   return RXB_OK;
 }
@@ -676,7 +706,8 @@ repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ aren
     case RP_1x1_DGRAD: total = (long long)N * K; break;
     case RP_3x3_FWD:
     case RP_3x3_DGRAD: total = 9ll * N * K; break;
-    case RP_3x3S2_FWD: total = 16ll * N * K; break;   // [4 taps][N][4K]
+    case RP_3x3S2_FWD:
+    case RP_3x3S2_DGRAD: total = 16ll * N * K; break;   // [4 taps][N][4K] / [4 taps][4K][N]
     default: total = 16ll * N * 32; break;  // stem: [16 taps][N][32]
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -704,6 +735,15 @@ repack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ aren
         const long long r = i / (4 * K);
         const int n = (int)(r % N), tap = (int)(r / N);
         const int sy = tap >> 1, sx = tap & 1;
+        const int q = cc / K, c = cc - q * K;
+        const int dy = 2 * sy + (q >> 1) - 1, dx = 2 * sx + (q & 1) - 1;
+        if (dy >= 0 && dy < 3 && dx >= 0 && dx < 3) v = src[(((long long)n * K + c) * 3 + dy) * 3 + dx];
+      } break;
+      case RP_3x3S2_DGRAD: {                                    // dst[flipped tap][(py*2+px)*K + c][n]
+        const int n = (int)(i % N);
+        const long long r = i / N;
+        const int cc = (int)(r % (4 * K)), tapf = (int)(r / (4 * K));
+        const int sy = 1 - (tapf >> 1), sx = 1 - (tapf & 1);
         const int q = cc / K, c = cc - q * K;
         const int dy = 2 * sy + (q >> 1) - 1, dx = 2 * sx + (q & 1) - 1;
         if (dy >= 0 && dy < 3 && dx >= 0 && dx < 3) v = src[(((long long)n * K + c) * 3 + dy) * 3 + dx];

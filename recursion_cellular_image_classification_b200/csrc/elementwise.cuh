@@ -57,9 +57,9 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int taps, const float* scale,
                             const float* shift, const float* sum_dy, float* out, cudaStream_t st);
 
-// dx[p,c] = scale[c] * (dy[p,c] - m1[c] - xhat[p,c]*m2[c]) in place on dy (bf16 [M,C] dense).
+// dx[p,c] = scale[c] * (dy[p,c] - m1[c] - xhat[p,c]*m2[c])  (bf16 [M,C] dense), in place on dy, or into dst when given.
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st);
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst = nullptr);
 
 // dst[p, c] = G[p, c0+c] - corrA[c0+c] - xhat[p, c0+c]*corrB[c0+c]   for c in [0, nch)   (bf16 dense out)
 int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long M, int c0, int nch,
@@ -83,7 +83,10 @@ int sum_scale(const float* v, int n, float scale, float* out, cudaStream_t st);
 enum RepackType { RP_1x1_FWD = 0, RP_1x1_DGRAD = 1, RP_3x3_FWD = 2, RP_3x3_DGRAD = 3, RP_STEM_FWD = 4,
                   // 3x3 stride-2 pad-1 weights as the 2x2-tap stride-1 operand over the 2x2 space-to-depth input
                   // (resnet_ops.cuh s2d_bn_relu): dst[(sy,sx)][n][(py*2+px)*K + c] = W[n][c][2sy+py-1][2sx+px-1] (0 outside)
-                  RP_3x3S2_FWD = 5 };
+                  RP_3x3S2_FWD = 5,
+                  // its data-gradient operand (a plain 2x2-tap pad-0 conv over dOut producing the space-to-depth
+                  // gradient): dst[(1-sy,1-sx)][(py*2+px)*K + c][n] = W[n][c][2sy+py-1][2sx+px-1]
+                  RP_3x3S2_DGRAD = 6 };
 struct RepackJob {
   long long src_off;   // into the flat fp32 parameter buffer
   long long dst_off;   // into the bf16 operand arena (elements)

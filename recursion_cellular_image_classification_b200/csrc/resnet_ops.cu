@@ -229,3 +229,324 @@ int bn_fold_eval_all(const float* params, const float* buffers, const BnFoldJob*
 }
 
 }  // namespace rxb
+
+// ================================================================================================ training pieces
+namespace rxb {
+
+namespace {
+// Per-thread partials for channel group cg (8 channels) -> shared -> one global atomic per channel per CTA.
+__device__ __forceinline__ void block_channel_reduce2(const float (&s)[8], const float (&q)[8], int cg, int C, float* gsum,
+                                                      float* gsq, float* sh) {
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (s[e] != 0.f) atomicAdd(&sh[cg * 8 + e], s[e]);
+    if (q[e] != 0.f) atomicAdd(&sh[C + cg * 8 + e], q[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (sh[i] != 0.f) atomicAdd(gsum + i, sh[i]);
+    if (sh[C + i] != 0.f) atomicAdd(gsq + i, sh[C + i]);
+  }
+  __syncthreads();
+}
+}  // namespace
+
+template <bool DOWN>
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_sums_kernel(__nv_bfloat16* D, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ c3, BnFold f3,
+                     const __nv_bfloat16* __restrict__ cd, BnFold fd, long long M, int C, float* __restrict__ dsum3,
+                     float* __restrict__ dsq3, float* __restrict__ dsumd, float* __restrict__ dsqd) {
+  pdl_sync();
+  extern __shared__ float sh[];
+  const int groups = C >> 3;
+  const int cg = threadIdx.x % groups;
+  const int ppi = blockDim.x / groups;
+  float as[8], a3[8], ad[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) as[e] = a3[e] = ad[e] = 0.f;
+  for (long long pix = (long long)blockIdx.x * ppi + threadIdx.x / groups; pix < M; pix += (long long)gridDim.x * ppi) {
+    const long long at = pix * C + cg * 8;
+    float d[8], o[8], x3[8];
+    unpack8(*reinterpret_cast<const uint4*>(D + at), d);
+    unpack8(ld_stream_v4(out + at), o);
+    unpack8(ld_stream_v4(c3 + at), x3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d[e] = o[e] > 0.f ? d[e] : 0.f;
+      as[e] += d[e];
+      a3[e] = fmaf(d[e], x3[e], a3[e]);
+    }
+    if (DOWN) {
+      float xd[8];
+      unpack8(ld_stream_v4(cd + at), xd);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ad[e] = fmaf(d[e], xd[e], ad[e]);
+    }
+    *reinterpret_cast<uint4*>(D + at) = pack8(d);
+  }
+  {
+    float mu[8], rs[8];
+    load8f(f3.mean + cg * 8, mu);
+    load8f(f3.rstd + cg * 8, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a3[e] = rs[e] * (a3[e] - mu[e] * as[e]);     // sum du*xhat
+  }
+  block_channel_reduce2(as, a3, cg, C, dsum3, dsq3, sh);
+  if (DOWN) {
+    float mu[8], rs[8];
+    load8f(fd.mean + cg * 8, mu);
+    load8f(fd.rstd + cg * 8, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ad[e] = rs[e] * (ad[e] - mu[e] * as[e]);
+    block_channel_reduce2(as, ad, cg, C, dsumd, dsqd, sh);
+  }
+}
+
+int relu_bwd_sums(__nv_bfloat16* D, const __nv_bfloat16* out, const __nv_bfloat16* c3, BnFold f3, const __nv_bfloat16* cd,
+                  BnFold fd, long long M, int C, float* dsum3, float* dsq3, float* dsumd, float* dsqd, cudaStream_t st) {
+  const int groups = C / 8;
+  if (C % 8 || groups > kThreads || kThreads % groups) return set_error(RXB_ERR_INVALID, "relu_bwd_sums: C=%d", C);
+  RXB_PROF(st, PROF_ELEMENTWISE);
+  const int ppi = kThreads / groups;
+  long long blocks = ceil_div<long long>(M, (long long)ppi * 4);
+  const long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (cd != nullptr)
+    RXB_CUDA(launch_k((relu_bwd_sums_kernel<true>), dim3((unsigned)blocks), dim3(kThreads), smem, st, D, out, c3, f3, cd, fd, M, C, dsum3, dsq3, dsumd, dsqd));
+  else
+    RXB_CUDA(launch_k((relu_bwd_sums_kernel<false>), dim3((unsigned)blocks), dim3(kThreads), smem, st, D, out, c3, f3, cd, fd, M, C, dsum3, dsq3, dsumd, dsqd));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void __launch_bounds__(kThreads)
+s2d_bn_relu_bwd_kernel(const __nv_bfloat16* __restrict__ DS, const __nv_bfloat16* __restrict__ X, int B, int H, int W, int C,
+                       BnFold f, __nv_bfloat16* __restrict__ dz, float* __restrict__ dsum, float* __restrict__ dsq) {
+  pdl_sync();
+  extern __shared__ float sh[];
+  const int groups = C >> 3, Ho = (H + 1) >> 1, Wo = (W + 1) >> 1;
+  const int cg = threadIdx.x % groups;
+  const int ppi = blockDim.x / groups;
+  const long long M = (long long)B * H * W;
+  float sc[8], sf[8], as[8], aq[8];
+  load8f(f.scale + cg * 8, sc);
+  load8f(f.shift + cg * 8, sf);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) as[e] = aq[e] = 0.f;
+  for (long long pix = (long long)blockIdx.x * ppi + threadIdx.x / groups; pix < M; pix += (long long)gridDim.x * ppi) {
+    const int x_ = (int)(pix % W);
+    const long long r = pix / W;
+    const int y_ = (int)(r % H), b = (int)(r / H);
+    const int q = ((y_ & 1) << 1) | (x_ & 1);
+    float g[8], x[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(DS + ((((long long)b * Ho + (y_ >> 1)) * Wo + (x_ >> 1)) * 4 + q) * C + cg * 8)), g);
+    unpack8(ld_stream_v4(X + pix * C + cg * 8), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[e] = fmaf(x[e], sc[e], sf[e]) > 0.f ? g[e] : 0.f;
+      as[e] += g[e];
+      aq[e] = fmaf(g[e], x[e], aq[e]);
+    }
+    *reinterpret_cast<uint4*>(dz + pix * C + cg * 8) = pack8(g);
+  }
+  {
+    float mu[8], rs[8];
+    load8f(f.mean + cg * 8, mu);
+    load8f(f.rstd + cg * 8, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) aq[e] = rs[e] * (aq[e] - mu[e] * as[e]);
+  }
+  block_channel_reduce2(as, aq, cg, C, dsum, dsq, sh);
+}
+
+int s2d_bn_relu_bwd(const __nv_bfloat16* DS, const __nv_bfloat16* X, int B, int H, int W, int C, BnFold f,
+                    __nv_bfloat16* dz, float* dsum, float* dsq, cudaStream_t st) {
+  const int groups = C / 8;
+  if (C % 8 || groups > kThreads || kThreads % groups) return set_error(RXB_ERR_INVALID, "s2d_bn_relu_bwd: C=%d", C);
+  RXB_PROF(st, PROF_ELEMENTWISE);
+  const int ppi = kThreads / groups;
+  long long blocks = ceil_div<long long>((long long)B * H * W, (long long)ppi * 4);
+  const long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  RXB_CUDA(launch_k(s2d_bn_relu_bwd_kernel, dim3((unsigned)blocks), dim3(kThreads), 2 * (size_t)C * sizeof(float), st, DS, X, B, H, W, C, f, dz, dsum, dsq));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void __launch_bounds__(kThreads)
+upsample2_add_kernel(const __nv_bfloat16* __restrict__ DXS, int B, int H, int W, int C, __nv_bfloat16* Din) {
+  pdl_sync();
+  const int groups = C >> 3, Ho = (H + 1) >> 1, Wo = (W + 1) >> 1;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    long long r = i / groups;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho), b = (int)(r / Ho);
+    __nv_bfloat16* dst = Din + (((long long)b * H + 2 * oy) * W + 2 * ox) * C + cg * 8;
+    float a[8], d[8];
+    unpack8(*reinterpret_cast<const uint4*>(dst), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(DXS + i * 8)), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += d[e];
+    *reinterpret_cast<uint4*>(dst) = pack8(a);
+  }
+}
+
+int upsample2_add(const __nv_bfloat16* DXS, int B, int H, int W, int C, __nv_bfloat16* Din, cudaStream_t st) {
+  if (C % 8) return set_error(RXB_ERR_INVALID, "upsample2_add: C=%d", C);
+  RXB_PROF(st, PROF_ELEMENTWISE);
+  const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  RXB_CUDA(launch_k(upsample2_add_kernel, dim3(grid_for(total)), dim3(kThreads), (size_t)0, st, DXS, B, H, W, C, Din));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void __launch_bounds__(kThreads)
+gap_mean_bwd_kernel(const float* __restrict__ dfeat, int B, int HW, int C, __nv_bfloat16* __restrict__ D) {
+  pdl_sync();
+  const int groups = C >> 3;
+  const long long total = (long long)B * HW * groups;
+  const float inv = 1.f / (float)HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const int b = (int)(i / ((long long)HW * groups));
+    float v[8];
+    load8f(dfeat + (long long)b * C + cg * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= inv;
+    *reinterpret_cast<uint4*>(D + i * 8) = pack8(v);
+  }
+}
+
+int gap_mean_bwd(const float* dfeat, int B, int HW, int C, __nv_bfloat16* D, cudaStream_t st) {
+  if (C % 8) return set_error(RXB_ERR_INVALID, "gap_mean_bwd: C=%d", C);
+  RXB_PROF(st, PROF_ELEMENTWISE);
+  RXB_CUDA(launch_k(gap_mean_bwd_kernel, dim3(grid_for((long long)B * HW * (C / 8))), dim3(kThreads), (size_t)0, st, dfeat, B, HW, C, D));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void two_sites_concat_bwd_kernel(const float* __restrict__ dcat, int bs, int G, int F, float* __restrict__ dfeat) {
+  pdl_sync();
+  const long long total = (long long)bs * G * F;
+  const int per = G / 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long r = i / F;
+    const int g = (int)(r % G), b = (int)(r / G);
+    int third = g / per;
+    if (third > 2) third = 2;
+    const int cnt = third == 2 ? G - 2 * per : per;
+    dfeat[i] = dcat[((long long)b * 3 + third) * F + f] / (float)cnt;
+  }
+}
+
+int two_sites_concat_bwd(const float* dcat, int bs, int G, int F, float* dfeat, cudaStream_t st) {
+  RXB_PROF(st, PROF_HEAD);
+  RXB_CUDA(launch_k(two_sites_concat_bwd_kernel, dim3(grid_for((long long)bs * G * F)), dim3(kThreads), (size_t)0, st, dcat, bs, G, F, dfeat));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void bn1d_train_fwd_kernel(const float* __restrict__ x, int rows, int F, int pre_relu, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar, float eps,
+                                      float momentum, float* __restrict__ y, float* __restrict__ save_mean,
+                                      float* __restrict__ save_rstd) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    float v = x[(long long)r * F + f];
+    if (pre_relu) v = fmaxf(v, 0.f);
+    s += v;
+  }
+  const float mean = s / (float)rows;
+  float q = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    float v = x[(long long)r * F + f];
+    if (pre_relu) v = fmaxf(v, 0.f);
+    q = fmaf(v - mean, v - mean, q);
+  }
+  const float var = q / (float)rows;
+  const float rstd = rsqrtf(var + eps);
+  const float g = gamma[f], bta = beta[f];
+  for (int r = 0; r < rows; ++r) {
+    float v = x[(long long)r * F + f];
+    if (pre_relu) v = fmaxf(v, 0.f);
+    y[(long long)r * F + f] = fmaf((v - mean) * rstd, g, bta);
+  }
+  save_mean[f] = mean;
+  save_rstd[f] = rstd;
+  const float unbiased = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+  rmean[f] = (1.f - momentum) * rmean[f] + momentum * mean;
+  rvar[f] = (1.f - momentum) * rvar[f] + momentum * unbiased;
+}
+
+int bn1d_train_fwd(const float* x, int rows, int F, int pre_relu, const float* gamma, const float* beta, float* rmean,
+                   float* rvar, float eps, float momentum, float* y, float* save_mean, float* save_rstd, cudaStream_t st) {
+  RXB_PROF(st, PROF_HEAD);
+  RXB_CUDA(launch_k(bn1d_train_fwd_kernel, dim3(ceil_div(F, 128)), dim3(128), (size_t)0, st, x, rows, F, pre_relu, gamma, beta, rmean, rvar, eps,
+                    momentum, y, save_mean, save_rstd));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void bn1d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int rows, int F, int pre_relu,
+                                const float* __restrict__ gamma, const float* __restrict__ save_mean,
+                                const float* __restrict__ save_rstd, float* __restrict__ dx, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta) {
+  pdl_sync();
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const float mean = save_mean[f], rstd = save_rstd[f], g = gamma[f];
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    float v = x[(long long)r * F + f];
+    if (pre_relu) v = fmaxf(v, 0.f);
+    const float d = dy[(long long)r * F + f];
+    s1 += d;
+    s2 = fmaf(d, (v - mean) * rstd, s2);
+  }
+  dgamma[f] = s2;
+  dbeta[f] = s1;
+  const float m1 = s1 / (float)rows, m2 = s2 / (float)rows;
+  for (int r = 0; r < rows; ++r) {
+    const float raw = x[(long long)r * F + f];
+    const float v = pre_relu ? fmaxf(raw, 0.f) : raw;
+    float d = g * rstd * (dy[(long long)r * F + f] - m1 - (v - mean) * rstd * m2);
+    if (pre_relu && !(raw > 0.f)) d = 0.f;
+    dx[(long long)r * F + f] = d;
+  }
+}
+
+int bn1d_bwd(const float* dy, const float* x, int rows, int F, int pre_relu, const float* gamma, const float* save_mean,
+             const float* save_rstd, float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+  RXB_PROF(st, PROF_HEAD);
+  RXB_CUDA(launch_k(bn1d_bwd_kernel, dim3(ceil_div(F, 128)), dim3(128), (size_t)0, st, dy, x, rows, F, pre_relu, gamma, save_mean, save_rstd, dx,
+                    dgamma, dbeta));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+__global__ void mul_elems_kernel(const float* x, const float* __restrict__ m, long long n, float* y) {   // y may alias x
+  pdl_sync();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * m[i];
+}
+
+int mul_elems(const float* x, const float* m, long long n, float* y, cudaStream_t st) {
+  RXB_PROF(st, PROF_HEAD);
+  RXB_CUDA(launch_k(mul_elems_kernel, dim3(grid_for(n)), dim3(kThreads), (size_t)0, st, x, m, n, y));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
+}  // namespace rxb

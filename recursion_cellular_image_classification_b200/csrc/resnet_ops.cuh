@@ -39,3 +39,35 @@ int bn_fold_eval_all(const float* params, const float* buffers, const BnFoldJob*
                      float* fold_scale, float* fold_shift, cudaStream_t st);
 
 }  // namespace rxb
+
+// ---------------------------------------------------------------------------------------------- training pieces
+namespace rxb {
+
+// Residual-join backward (torchvision Bottleneck: out = relu(bn3(c3) + idn)), first half:
+//   du = D * [out > 0]   written over D (bf16 [M,C] dense);
+//   dsum3 += sum du ; dsq3 += sum du*xhat(c3)           (BatchNorm3 backward reductions, xhat from f3.mean / f3.rstd)
+//   dsumd / dsqd likewise against cd when the block has a downsample BatchNorm (cd != nullptr).
+int relu_bwd_sums(__nv_bfloat16* D, const __nv_bfloat16* out, const __nv_bfloat16* c3, BnFold f3, const __nv_bfloat16* cd,
+                  BnFold fd, long long M, int C, float* dsum3, float* dsq3, float* dsumd, float* dsqd, cudaStream_t st);
+// Backward of s2d_bn_relu: dz[b,y,x,c] = DS[b,y/2,x/2,(y%2*2+x%2)*C+c] * [X*scale+shift > 0]   (bf16 [B,H,W,C]);
+// dsum += sum dz ; dsq += sum dz*xhat(X).
+int s2d_bn_relu_bwd(const __nv_bfloat16* DS, const __nv_bfloat16* X, int B, int H, int W, int C, BnFold f,
+                    __nv_bfloat16* dz, float* dsum, float* dsq, cudaStream_t st);
+// Backward of subsample2: Din[b,2i,2j,c] += DXS[b,i,j,c]
+int upsample2_add(const __nv_bfloat16* DXS, int B, int H, int W, int C, __nv_bfloat16* Din, cudaStream_t st);
+// Backward of gap_mean: D[b,p,c] = dfeat[b,c] / HW   (bf16)
+int gap_mean_bwd(const float* dfeat, int B, int HW, int C, __nv_bfloat16* D, cudaStream_t st);
+// Backward of two_sites_concat: dfeat[b*G+g, f] = dcat[b, third(g)*F + f] / (images in that third)
+int two_sites_concat_bwd(const float* dcat, int bs, int G, int F, float* dfeat, cudaStream_t st);
+// BatchNorm1d in training mode over rows [rows, F] (models.py:32,36), optionally on relu(x) (the ReLU of models.py:35
+// sits between Linear and BatchNorm1d): y = (x' - mean) * rstd * gamma + beta with the batch's biased variance,
+// running statistics updated with momentum and the unbiased variance; mean / rstd saved for backward.
+int bn1d_train_fwd(const float* x, int rows, int F, int pre_relu, const float* gamma, const float* beta, float* rmean,
+                   float* rvar, float eps, float momentum, float* y, float* save_mean, float* save_rstd, cudaStream_t st);
+// dx = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) (times [x > 0] when pre_relu); dgamma = sum dy*xhat; dbeta = sum dy
+int bn1d_bwd(const float* dy, const float* x, int rows, int F, int pre_relu, const float* gamma, const float* save_mean,
+             const float* save_rstd, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+// y[i] = x[i] * m[i]   (Dropout with an explicit mask holding 0 or 1/(1-p); the same call is its backward)
+int mul_elems(const float* x, const float* m, long long n, float* y, cudaStream_t st);
+
+}  // namespace rxb
