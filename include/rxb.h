@@ -296,10 +296,10 @@ int rxb_rn50_forward(rxb_rn50* net, const void* input_s2d, float* logits_out, rx
  * updated), Dropout(p) as multiplication by the caller's masks (f32 [B, 3*2048] and [B, size_features] holding 0 or
  * 1/(1-p): the caller owns the random stream, which is what makes parity testable), gradients of every parameter
  * into grads (overwritten).  loss_out f32[1]: this rank's share of the mean loss; logits_out f32[B,num_classes] or
- * NULL: the training-mode logits. */
+ * NULL: the training-mode logits; feat_out f32[B*G,2048] or NULL: the trunk's pooled features (base_nn output). */
 int rxb_rn50_train_step(rxb_rn50* net, const void* input_s2d, const int64_t* target, const float* drop_mask0,
                         const float* drop_mask1, int global_batch, float* loss_out, float* logits_out,
-                        rxb_stream_t stream);
+                        float* feat_out, rxb_stream_t stream);
 /* nesterov SGD (main.py:89-93) on the flat buffers, then refresh the bf16 operands.  head_only = 1 updates the mlp.*
  * parameters alone: the reference's first two epochs with a pretrained trunk (train.py:46-58 freezes every child of
  * the model except 'mlp'). */

@@ -93,7 +93,7 @@ SIGNATURES = {
     "rxb_rn50_create": (c_int, [ctypes.POINTER(Rn50Config), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                 c_int, ctypes.POINTER(c_void_p)]),
     "rxb_rn50_train_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                    c_void_p]),
+                                    c_void_p, c_void_p]),
     "rxb_rn50_sgd": (c_int, [c_void_p, c_float, c_float, c_float, c_int, c_float, c_int, c_void_p]),
     "rxb_rn50_destroy": (None, [c_void_p]),
     "rxb_rn50_sync_weights": (c_int, [c_void_p, c_void_p]),

@@ -588,7 +588,8 @@ class TwoSitesResNet50(torch.nn.Module):
         draw = lambda f: (torch.rand(B, f, device=dev, generator=generator) < keep).float() / keep
         return draw(3 * 2048), draw(self.size_features)
 
-    def train_step(self, x, target, G=None, masks=None, global_batch=None, loss_out=None, logits_out=None):
+    def train_step(self, x, target, G=None, masks=None, global_batch=None, loss_out=None, logits_out=None,
+                   feat_out=None):
         """The reference's train step natively (train.py:37,44): forward with batch statistics and Dropout, mean
         CrossEntropy over global_batch samples, backward into self.flat.grad.  `masks` = dropout_masks(B) unless
         given (explicit masks make the step reproducible).  Returns the device scalar with this rank's loss share."""
@@ -601,7 +602,7 @@ class TwoSitesResNet50(torch.nn.Module):
             loss_out = torch.empty(1, dtype=torch.float32, device=x.device)
         check(load().rxb_rn50_train_step(plan["handle"], ptr(x), ptr(target.contiguous()), ptr(m0.contiguous()),
                                          ptr(m1.contiguous()), global_batch or B, ptr(loss_out), ptr(logits_out),
-                                         stream_ptr()))
+                                         ptr(feat_out), stream_ptr()))
         return loss_out
 
     def head_range(self):

@@ -39,14 +39,15 @@ def evaluate(model, ds, bs, num_workers, device):
     net = _unwrap(model)
     was_training = net.training
     net.eval()
-    loader = torch.utils.data.DataLoader(RawView(ds, controls=False), batch_size=bs, shuffle=False,
+    triplet = bool(getattr(net, "wants_controls", False))       # the reference's own model consumes the control thirds
+    loader = torch.utils.data.DataLoader(RawView(ds, controls=triplet), batch_size=bs, shuffle=False,
                                          num_workers=num_workers, collate_fn=collate_raw)
     correct, total, loss_sum = 0, 0, 0.0
     dev = torch.device(device)
     for batch in loader:
         xs = ds.device_batch(batch, dev)                              # one image per sample (its own site, no controls)
         y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
-        logits = net(xs)
+        logits = net(xs, G=batch["codes"].shape[1]) if triplet else net(xs)
         loss_rows, _ = ops.softmax_ce(logits, y)
         loss_sum += loss_rows.sum().item()
         correct += (logits.argmax(1) == y).sum().item()
@@ -64,7 +65,10 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     lr0 = hyperparams.get('lr', group['lr'])
     momentum, nesterov, wd = group.get('momentum', 0.0), group.get('nesterov', False), group.get('weight_decay', 0.0)
     nb_epochs = hyperparams['nb_epochs']
-    crop = hyperparams.get('crop', 512)
+    # TwoSitesResNet50 (the reference's own model): items keep their control wells, one native step per batch
+    # (models.TwoSitesResNet50.train_step), default crop 364 like the reference (dataloader.py:47,50)
+    triplet = bool(getattr(net, "wants_controls", False))
+    crop = hyperparams.get('crop', 364 if triplet else 512)
     ds_train.crop = ds_val.crop = crop
 
     sampler = None
@@ -73,7 +77,7 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     # items carry the sample's own image only (controls=False): the control wells cannot reach DenseNet's single
     # linear classifier (see cell_classifier/models.py), so they are neither decoded nor copied — train, validation
     # and test() all follow this one rule
-    loader = torch.utils.data.DataLoader(RawView(ds_train, controls=False), batch_size=bs, shuffle=sampler is None,
+    loader = torch.utils.data.DataLoader(RawView(ds_train, controls=triplet), batch_size=bs, shuffle=sampler is None,
                                          sampler=sampler, num_workers=num_workers, collate_fn=collate_raw,
                                          drop_last=world > 1)
     net.train()
@@ -93,7 +97,7 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
     # CUDA-graph replay of the executor's phases (models.DenseNet121.train_step): on by default on the device;
     # hyperparams['cuda_graph'] = False or RXB_NO_GRAPH=1 keeps plain stream launches
     use_graph = bool(hyperparams.get('cuda_graph', True)) and dev.type == "cuda" and hasattr(net, "static_buffers") \
-        and os.environ.get("RXB_NO_GRAPH", "0") != "1"
+        and os.environ.get("RXB_NO_GRAPH", "0") != "1" and not triplet
     graph_kw = {"graph": True} if use_graph else {}
 
     def validate(epoch):
@@ -135,6 +139,18 @@ def train(experiment_id, ds_train, ds_val, model, optimizer, hyperparams, num_wo
         t_epoch = time.perf_counter()
         for batch in loader:
             y = torch.tensor(batch["label"], dtype=torch.int64, device=dev)
+            if triplet:
+                xs = ds_train.device_batch(batch, dev)                        # [B*3, h/2, w/2, 32]: image, neg, pos per sample
+                G = batch["codes"].shape[1]
+                B, H, W = xs.shape[0] // G, xs.shape[1] * 2, xs.shape[2] * 2
+                net.train_step(xs, y, G=G, global_batch=B * world, loss_out=loss_dev)
+                if world > 1:
+                    torch.distributed.all_reduce(net.flat.grad)
+                net.sgd_step(B, G, H, W, lr=lr, momentum=momentum, weight_decay=wd, nesterov=nesterov, **frozen)
+                loss_hist[n_it:n_it + 1].copy_(loss_dev.to(loss_hist.dtype))
+                n_it += 1
+                n_img += B * G
+                continue
             if use_graph:
                 # the loader writes straight into the executor's fixed-address step buffer, the labels are copied
                 # beside it, and every backward phase is replayed from a CUDA graph (captured on its second use)

@@ -754,7 +754,8 @@ int64_t rxb_rn50_head_offset(const rxb_rn50_config* cfg) {
 }
 
 int rxb_rn50_train_step(rxb_rn50* net, const void* input_s2d, const int64_t* target, const float* drop_mask0,
-                        const float* drop_mask1, int global_batch, float* loss_out, float* logits_out, rxb_stream_t stream) {
+                        const float* drop_mask1, int global_batch, float* loss_out, float* logits_out, float* feat_out,
+                        rxb_stream_t stream) {
   using namespace rxb;
   RXB_CHECK_ARG(net && input_s2d && target && drop_mask0 && drop_mask1, "rxb_rn50_train_step: null pointer");
   RXB_CHECK_ARG(net->training, "rxb_rn50_train_step: plan was created for inference");
@@ -768,6 +769,8 @@ int rxb_rn50_train_step(rxb_rn50* net, const void* input_s2d, const int64_t* tar
   if (loss_out) RXB_TRY(sum_scale(n.loss_rows, n.cfg.B, 1.f / (float)global_batch, loss_out, st));
   if (logits_out)
     RXB_CUDA(cudaMemcpyAsync(logits_out, n.logits, sizeof(float) * n.cfg.B * n.cfg.num_classes, cudaMemcpyDeviceToDevice, st));
+  if (feat_out)
+    RXB_CUDA(cudaMemcpyAsync(feat_out, n.feat, sizeof(float) * n.Bi * n.feat_dim, cudaMemcpyDeviceToDevice, st));
   RXB_TRY(backward(n, input_s2d, drop_mask0, drop_mask1, st));
   return RXB_OK;
 }

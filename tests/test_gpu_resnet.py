@@ -107,19 +107,40 @@ def _oracle_train_forward(ref, x, m0, m1):
     return m[6](m[4](torch.relu(h1)) * m1)
 
 
-@pytest.mark.parametrize("B,G,S", [(4, 3, 128), (2, 3, 364)])
+def _distinct_samples(B, G, S, g):
+    """Inputs whose samples differ in contrast, brightness and spatial structure, so that the head's BatchNorm1d over
+    the B samples is well conditioned (B noise images of one distribution have nearly identical features: their batch
+    variance is rounding noise and any two floating-point paths disagree after dividing by it)."""
+    x = torch.randn(B, G, 6, S, S, generator=g)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, S), torch.linspace(-1, 1, S), indexing="ij")
+    for b in range(B):
+        pat = torch.sin((1 + b % 5) * 3.0 * yy + 0.7 * b) * torch.cos((1 + b % 3) * 2.0 * xx) + (b % 4 - 1.5) * 0.5 * yy * xx
+        x[b] = x[b] * (0.3 + 0.25 * b) + 2.0 * pat + 0.4 * (b - B / 2)
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("B,G,S", [(16, 3, 160), (8, 3, 364)])
 def test_train_step_matches_fp32_oracle(cuda, B, G, S):
     """One training step of the reference's model (train.py:37,44): BatchNorm batch statistics in the trunk and the
-    head, Dropout with explicit masks, CrossEntropy, full backward — loss and training-mode logits within 2e-2 of
-    torch fp32, every parameter gradient as close to fp32 as PyTorch's own bf16 autocast path, running statistics
-    updated like torch's."""
+    head, Dropout with explicit masks, CrossEntropy, full backward, against torch fp32.
+    Conditioning matters here and is part of the seeded case: at random initialisation a 50-layer residual trunk under
+    batch statistics amplifies bf16 rounding (PyTorch's own bf16 autocast is 8-20 % away from its fp32 in the pooled
+    features, 50-60 % in the logits - measured), so the case uses small last-BatchNorm weights in every bottleneck
+    (the usual zero-init-residual regime, here 0.05 x) and samples that differ in contrast and structure.  Then:
+    pooled trunk features and loss within 2e-2; training-mode logits within 2e-2 or, because the head's two
+    BatchNorm1d over B samples amplify the trunk's rounding 3-4x for any bf16 path, within 1.25 x what PyTorch's bf16
+    autocast shows on the same case; every parameter gradient as close to fp32 as that path; running statistics."""
     import copy
     ref = O.two_sites_resnet50(seed=11).to(cuda)
     _randomise_running_stats(ref, 12)
+    with torch.no_grad():
+        for name, mod in ref.named_modules():
+            if name.endswith("bn3"):
+                mod.weight.mul_(0.05)
     net = TwoSitesResNet50(device=cuda)
     net.load_state_dict(ref.state_dict(), strict=False)
     g = torch.Generator().manual_seed(S + B)
-    x = torch.randn(B, G, 6, S, S, generator=g).to(torch.bfloat16).float().to(cuda)
+    x = _distinct_samples(B, G, S, g).to(cuda)
     y = torch.randint(0, 1108, (B,), generator=g).to(cuda)
     keep = 0.7
     m0 = ((torch.rand(B, 6144, generator=g) < keep).float() / keep).to(cuda)
@@ -128,17 +149,28 @@ def test_train_step_matches_fp32_oracle(cuda, B, G, S):
     cal = copy.deepcopy(ref)
     cal.train()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        lc = torch.nn.CrossEntropyLoss()(_oracle_train_forward(cal, x, m0, m1).float(), y)
+        out_cal = _oracle_train_forward(cal, x, m0, m1).float()
+        lc = torch.nn.CrossEntropyLoss()(out_cal, y)
     lc.backward()
     ref.train()
+    feats_ref = {}
+
+    def keep_features(mod, inp, outp):           # (a hook that returns a value would replace the module's output)
+        feats_ref["f"] = outp.detach()
+
+    hook = ref.base_nn.register_forward_hook(keep_features)
     out = _oracle_train_forward(ref, x, m0, m1)
+    hook.remove()
     loss = torch.nn.CrossEntropyLoss()(out, y)
     loss.backward()
     logits = torch.empty(B, 1108, device=cuda)
+    feats = torch.empty(B * G, 2048, device=cuda)
     net.train()
-    my_loss = net.train_step(x, y, masks=(m0, m1), logits_out=logits).item()
+    my_loss = net.train_step(x, y, masks=(m0, m1), logits_out=logits, feat_out=feats).item()
     torch.cuda.synchronize()
     rel_logits = _rel(logits, out.detach())
+    rel_feats = _rel(feats, feats_ref["f"])
+    rel_logits_cal = _rel(out_cal.detach(), out.detach())
     flat_ref = torch.cat([p.grad.flatten() for _, p in ref.named_parameters()])
     flat_cal = torch.cat([p.grad.flatten() for _, p in cal.named_parameters()])
     cos = torch.nn.functional.cosine_similarity(flat_ref, net.flat.grad, dim=0).item()
@@ -150,11 +182,13 @@ def test_train_step_matches_fp32_oracle(cuda, B, G, S):
         e_my, e_cal, n_ref = (g_my - g_ref).norm().item(), (g_cal - g_ref).norm().item(), g_ref.norm().item()
         worst.append((e_my / (2.0 * e_cal + 0.02 * n_ref + 1e-12), name, e_my, e_cal, n_ref))
     worst.sort(reverse=True)
-    print("\nResNet-50 TwoSitesNN train step B=%d G=%d S=%d: loss ours %.5f fp32 %.5f | logits rel %.4f | grad cos %.4f "
-          "(torch-bf16 %.4f) | worst (our err)/(2 x torch-bf16 err + 2%%): %s" %
-          (B, G, S, my_loss, loss.item(), rel_logits, cos, cos_cal, [(round(w[0], 2), w[1]) for w in worst[:4]]))
+    print("\nResNet-50 TwoSitesNN train step B=%d G=%d S=%d: loss ours %.5f fp32 %.5f (torch-bf16 %.5f) | pooled features "
+          "rel %.4f | logits rel %.4f (torch-bf16 %.4f) | grad cos %.4f (torch-bf16 %.4f) | worst (our err)/(2 x torch-bf16 "
+          "err + 2%%): %s" % (B, G, S, my_loss, loss.item(), lc.item(), rel_feats, rel_logits, rel_logits_cal, cos, cos_cal,
+                             [(round(w[0], 2), w[1]) for w in worst[:4]]))
     assert abs(my_loss - loss.item()) < 2e-2 * abs(loss.item())
-    assert rel_logits < 2e-2, rel_logits
+    assert rel_feats < 2e-2, rel_feats
+    assert rel_logits < max(2e-2, 1.25 * rel_logits_cal), (rel_logits, rel_logits_cal)
     assert cos > cos_cal - 0.03, (cos, cos_cal)
     assert worst[0][0] < 1.0, worst[:5]
     for name, buf in ref.named_buffers():
@@ -181,3 +215,32 @@ def test_sgd_steps_learn_and_head_only_freezes_the_trunk(cuda):
     assert losses[-1] < losses[0], losses
     net.eval()
     assert torch.isfinite(net(x)).all()
+
+
+def test_train_and_test_shims_drive_the_reference_model(cuda, tmp_path, monkeypatch):
+    """train() with TwoSitesNN(trunk='resnet50'): triplet items through the DataLoader, native steps, head-only SGD in
+    the first two epochs of a 'pretrained' run (train.py:46-67), validation, the `module.`-prefixed checkpoint with the
+    reference's own parameter names — which the oracle restatement of the reference model loads."""
+    from test_gpu_shims import _write_tree
+    from recursion_cellular_image_classification_b200.cell_classifier import dataloader as dl
+    from recursion_cellular_image_classification_b200.cell_classifier.train import train as rxb_train
+    monkeypatch.chdir(tmp_path)
+    root = str(tmp_path / "data")
+    df, dfc, _, exp = _write_tree(root, S=64)
+    stats = {exp: {"mean": np.full(6, 0.08), "std": np.full(6, 0.06)}}
+    ds_train = dl.ImagesDS(df, dfc, stats, root, "train", verbose=False)
+    ds_val = dl.ImagesDS(df, dfc, stats, root, "val", verbose=False)
+    model = TwoSitesNN(pretrained=False, nb_classes=1108, trunk="resnet50", device=cuda)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=3e-5)
+    hp = {"bs": 4, "nb_epochs": 3, "scheduler": True, "lr": 0.01, "early_stopping": False, "patience": 10,
+          "pretrained": True, "crop": 64, "tensorboard": False}
+    trunk0 = model.flat.detach()[:model.head_range()[0]].clone()
+    head0 = model.flat.detach()[model.head_range()[0]:].clone()
+    hist = rxb_train("rn50", ds_train, ds_val, model, opt, hp, num_workers=0, device="cuda", debug=True)
+    assert len(hist) == 4 and all(np.isfinite(h["val_loss"]) for h in hist)
+    assert not torch.equal(head0, model.flat.detach()[model.head_range()[0]:])
+    assert not torch.equal(trunk0, model.flat.detach()[:model.head_range()[0]])          # unfrozen from epoch 3
+    sd = torch.load("models/best_model_rn50.pth")
+    assert all(k.startswith("module.base_nn.") or k.startswith("module.mlp.") for k in sd)
+    ref = O.two_sites_resnet50(seed=0)
+    ref.load_state_dict({k[len("module."):]: v for k, v in sd.items()}, strict=False)   # (num_batches_tracked absent)
