@@ -1515,6 +1515,8 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
     return set_error(RXB_ERR_INVALID, "conv_wgrad: cin too large");
   m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
   int pix_ctas = num_sms() / chunk_groups;
+  static const int dbg_wg_pix = getenv("RXB_DBG_WG_PIX") ? atoi(getenv("RXB_DBG_WG_PIX")) : 0;   // experiment: cap
+  if (dbg_wg_pix > 0 && pix_ctas > dbg_wg_pix) pix_ctas = dbg_wg_pix;
   if (pix_ctas < 1) pix_ctas = 1;
   if (pix_ctas > m_tiles) pix_ctas = m_tiles;
   p.pix_tiles_per_cta = ceil_div(m_tiles, pix_ctas);
