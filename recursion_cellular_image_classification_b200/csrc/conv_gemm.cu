@@ -1115,6 +1115,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int n = et; n < p.n; n += 128)
             ptx::bulk_reduce_add_f32(p.dW + (long long)(p.n_off + n) * rowlen, stg + (size_t)n * rowlen, rowlen * 4);
           ptx::tma_store_commit();
+        } else if (taps > 1) {
+          // classic multi-tap mode into the TAP-MAJOR scratch layout dW[tap][n][cin] (w_mode 3): chunk cl holds the two
+          // 64-channel boxes kk = (chunk0+cl)*2 + {0,1}, each a contiguous run of one (tap, n) row of the scratch
+          const int nbuf = p.bulk_bufs;
+          for (int cl = 0; cl < n_local; ++cl) {
+            float* sb = stg + (size_t)(cl % nbuf) * p.n * 128;
+            if (cl >= nbuf) {
+              if (nbuf == 2) ptx::tma_store_wait_read_pending<1>(); else ptx::tma_store_wait_read_pending<0>();
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            for (int c = 0; c < p.n; c += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + cl * p.n + c, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sb[(c + i) * 128 + row] = __uint_as_float(r[i]);
+            }
+            ptx::fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int ib2 = 0; ib2 < 2; ++ib2) {
+              const int kk = (chunk0 + cl) * 2 + ib2;
+              if (kk >= total_boxes) break;
+              const int tp = kk / p.boxes_per_tap;
+              const int c0 = (kk - tp * p.boxes_per_tap) * 64;
+              const int valid = min(64, p.cin - c0);
+              if (valid <= 0) continue;
+              for (int n = et; n < p.n; n += 128)
+                ptx::bulk_reduce_add_f32(p.dW + ((long long)tp * p.cout_total + p.n_off + n) * p.cin + c0, sb + n * 128 + ib2 * 64,
+                                         valid * 4);
+            }
+            ptx::tma_store_commit();
+          }
         } else {
           // 1x1: chunk cl holds input channels [ (chunk0+cl)*128, +128 )
           const int nbuf = p.bulk_bufs;
@@ -1461,7 +1493,9 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   const int taps = p.taps_x * p.taps_y;
   p.boxes_per_tap = ceil_div(p.cin, p.bkc);
   p.boxes_per_chunk = 128 / p.bkc;
-  p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512) ? 1 : 0;
+  p.shift_dout = (taps > 1 && p.bkc == 64 && p.cin <= 128 && taps * p.n <= 512 && p.w_mode != 3) ? 1 : 0;
+  if (p.w_mode == 3 && (taps == 1 || p.bkc != 64 || p.cin % 4))
+    return set_error(RXB_ERR_INVALID, "conv_wgrad: the tap-major scratch layout is for multi-tap filters with cin >= 64");
   if (p.shift_dout && p.n <= 64 && p.taps_x * p.n <= 256 && p.taps_x > 1) {
     // full-halo dOut box: needs 8-pixel tile rows (one K group per row); the tall tiling also keeps the halo small
     static const int dbg_no_wg_halo = getenv("RXB_DBG_NO_WG_HALO") ? atoi(getenv("RXB_DBG_NO_WG_HALO")) : 0;
@@ -1550,6 +1584,11 @@ int launch_conv_wgrad(WgradParams p, const void* A, long long ldA, const void* d
   const size_t pipe_bytes = (size_t)stages * per_stage + d_fixed;
   p.bulk_out = 0;
   p.bulk_bufs = 1;
+  if (p.w_mode == 3 && !p.a_halo) {
+    if ((size_t)p.n * 512 > pipe_bytes) return set_error(RXB_ERR_INVALID, "conv_wgrad: staging does not fit");
+    p.bulk_out = 1;
+    p.bulk_bufs = (size_t)p.n * 1024 <= pipe_bytes ? 2 : 1;
+  }
   if (p.w_mode == 0 && p.cin % 8 == 0) {
     if (p.shift_dout && (size_t)p.n * p.cin * taps * 4 <= pipe_bytes) p.bulk_out = 1;
     if (!p.shift_dout && taps == 1 && p.bkc == 64 && (size_t)p.n * 512 <= pipe_bytes) {

@@ -101,6 +101,9 @@ struct WgradParams {
   int cout_total;
   int w_mode;           // 0: generic OIHW (k -> (tap, channel)) ; 1: space-to-depth stem (7x7 stride 2, 6 ch) ;
                         // 2: 3x3 stride-2 weights behind the 2x2-tap space-to-depth conv (cin = 4 x real channels)
+                        // 3: multi-tap, TAP-MAJOR fp32 scratch dW[tap][cout_total][cin] (zeroed by the caller), added by
+                        //    bulk L2 reduce-adds of contiguous channel runs instead of 4-byte atomics; a finish kernel
+                        //    (resnet_ops wgrad_finish) transposes it into OIHW
   int a_halo;           // 1: multi-tap, bkc*taps_x == 128, no prologue: ONE full-halo A box per pixel tile; chunk = filter
                         //    row ty whose taps_x taps are M atoms one pixel row apart (the stem's 4x4 taps)
   unsigned long long* dbg;  // development timeline of CTA (0,0) (RXB_DBG_TIMELINE), else nullptr

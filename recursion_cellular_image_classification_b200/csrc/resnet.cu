@@ -61,7 +61,8 @@ struct rxb_rn50 {
   long long head_off = 0;   // first mlp.* parameter
   // training state: per-BatchNorm arrays indexed by RnBn::fold_off (fold_scale / fold_shift double as the fold's scale / shift)
   float *fold_mean = nullptr, *fold_rstd = nullptr, *st_sum = nullptr, *st_sq = nullptr, *d_sum = nullptr, *d_sq = nullptr;
-  float *ones = nullptr, *big = nullptr, *scratch_c = nullptr;
+  float *ones = nullptr, *big = nullptr, *scratch_c = nullptr, *wg_scratch = nullptr;
+  long long wg_scratch_elems = 0;
   uint8_t* zero_begin = nullptr;
   size_t zero_bytes = 0;
   __nv_bfloat16 *X0 = nullptr, *dy0 = nullptr, *Da = nullptr, *Db = nullptr, *DC3 = nullptr, *DCD = nullptr, *DZ2 = nullptr,
@@ -290,6 +291,10 @@ size_t plan(rxb_rn50& n, uint8_t* ws) {
       }
       mx_in = std::max(mx_in, Min * b.cin);
     }
+    long long mx_wg = 0;
+    for (auto& b : n.blocks) mx_wg = std::max(mx_wg, (b.stride == 2 ? 16ll : 9ll) * b.width * b.width);
+    n.wg_scratch_elems = mx_wg;
+    n.wg_scratch = bp.take<float>(mx_wg);
     n.dy0 = bp.take<__nv_bfloat16>(Bi * n.Hs * n.Ws * 64);
     n.Da = bp.take<__nv_bfloat16>(std::max(mx_x, mx_in));
     n.Db = bp.take<__nv_bfloat16>(std::max(mx_x, mx_in));
@@ -490,8 +495,9 @@ int dgrad_accumulate(const rxb_rn50& n, int B, int H, int W, const __nv_bfloat16
 }
 
 int wgrad(int B, int H, int W, const __nv_bfloat16* A, int cin, int taps, int pad, const BnFold* pro, const __nv_bfloat16* dOut,
-          int cout, float* dW, int w_mode, cudaStream_t st) {
-  const int n_tile = cout <= 256 ? cout : (cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64));
+          int cout, float* dW, int w_mode, cudaStream_t st, int n_tile_override = 0) {
+  const int n_tile = n_tile_override ? n_tile_override
+                                     : cout <= 256 ? cout : (cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64));
   for (int n_off = 0; n_off < cout; n_off += n_tile) {
     WgradParams p = {};
     p.t = make_tiling(B, H, W);
@@ -623,11 +629,23 @@ int backward(rxb_rn50& n, const void* input, const float* mask0, const float* ma
     RXB_TRY(apply_t(n, b.b2, n.DZ2, b.sC2, Mout, nullptr, st));                         // DZ2 := dc2
     // conv2
     if (b.stride == 1) {
-      RXB_TRY(wgrad(Bi, b.Hin, b.Win, b.sC1, w, 3, 1, &f1, n.DZ2, w, n.grads + b.c2.w_off, 0, st));
+      if (w <= 128) {
+        // 3x3 weight gradient, Cin <= 128: 32 output channels per launch keep the nine tap accumulators inside the 512
+        // TMEM columns, so the activation tile is loaded and transformed ONCE per pixel tile and the taps are offsets
+        // into one full-halo dOut box (conv_gemm.cu shift_dout mode) instead of nine shifted re-loads of A
+        RXB_TRY(wgrad(Bi, b.Hin, b.Win, b.sC1, w, 3, 1, &f1, n.DZ2, w, n.grads + b.c2.w_off, 0, st, 32));
+      } else {
+        // wider: per-tap A boxes; result into the tap-major scratch by bulk L2 reduce-adds, then transposed into OIHW
+        RXB_CUDA(cudaMemsetAsync(n.wg_scratch, 0, sizeof(float) * 9ll * w * w, st));
+        RXB_TRY(wgrad(Bi, b.Hin, b.Win, b.sC1, w, 3, 1, &f1, n.DZ2, w, n.wg_scratch, 3, st));
+        RXB_TRY(wgrad_finish(n.wg_scratch, w, w, 3, 0, n.grads + b.c2.w_off, st));
+      }
       RXB_TRY(dgrad_bn(n, Bi, b.Hin, b.Win, n.DZ2, w, b.c2.dgrad_off, w, 3, 1, b.sC1, b.b1, n.DZ1, st));
       RXB_TRY(finalize_t(n, b.b1, &b.c2, (float)Min, st));
     } else {
-      RXB_TRY(wgrad(Bi, b.Hout, b.Wout, b.sS2, 4 * w, 2, 1, nullptr, n.DZ2, w, n.grads + b.c2.w_off, 2, st));
+      RXB_CUDA(cudaMemsetAsync(n.wg_scratch, 0, sizeof(float) * 16ll * w * w, st));
+      RXB_TRY(wgrad(Bi, b.Hout, b.Wout, b.sS2, 4 * w, 2, 1, nullptr, n.DZ2, w, n.wg_scratch, 3, st));
+      RXB_TRY(wgrad_finish(n.wg_scratch, w, w, 3, 1, n.grads + b.c2.w_off, st));
       RXB_TRY(dgrad_plain(n, Bi, b.Hout, b.Wout, n.DZ2, w, b.c2.dgrad_off, 4 * w, 2, 0, n.DS2, st));
       RXB_TRY(s2d_bn_relu_bwd(n.DS2, b.sC1, Bi, b.Hin, b.Win, w, f1, n.DZ1, n.d_sum + b.b1.fold_off, n.d_sq + b.b1.fold_off, st));
       RXB_TRY(finalize_t(n, b.b1, nullptr, (float)Min, st));

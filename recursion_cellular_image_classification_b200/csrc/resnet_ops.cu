@@ -549,4 +549,32 @@ int mul_elems(const float* x, const float* m, long long n, float* y, cudaStream_
   return RXB_OK;
 }
 
+__global__ void wgrad_finish_kernel(const float* __restrict__ scratch, int N, int K, int k, int s2d, float* __restrict__ dW) {
+  pdl_sync();
+  const int taps = k * k;
+  const long long total = (long long)N * K * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    const int c = (int)(r % K), n = (int)(r / K);
+    float v;
+    if (!s2d) {
+      v = scratch[((long long)t * N + n) * K + c];
+    } else {
+      const int dy = t / 3, dx = t - dy * 3;                 // k == 3
+      const int sy = dy == 0 ? 0 : 1, py = dy == 1 ? 0 : 1;   // dy = 2*sy + py - 1
+      const int sx = dx == 0 ? 0 : 1, px = dx == 1 ? 0 : 1;
+      v = scratch[((long long)(sy * 2 + sx) * N + n) * (4 * K) + (py * 2 + px) * K + c];
+    }
+    dW[i] = v;
+  }
+}
+
+int wgrad_finish(const float* scratch, int N, int K, int k, int s2d, float* dW, cudaStream_t st) {
+  RXB_PROF(st, PROF_WGRAD_OTHER);
+  RXB_CUDA(launch_k(wgrad_finish_kernel, dim3(grid_for((long long)N * K * k * k)), dim3(kThreads), (size_t)0, st, scratch, N, K, k, s2d, dW));
+  RXB_LAUNCH_OK();
+  return RXB_OK;
+}
+
 }  // namespace rxb

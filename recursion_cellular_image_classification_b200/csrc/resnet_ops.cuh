@@ -67,6 +67,11 @@ int bn1d_train_fwd(const float* x, int rows, int F, int pre_relu, const float* g
 // dx = gamma*rstd*(dy - mean(dy) - xhat*mean(dy*xhat)) (times [x > 0] when pre_relu); dgamma = sum dy*xhat; dbeta = sum dy
 int bn1d_bwd(const float* dy, const float* x, int rows, int F, int pre_relu, const float* gamma, const float* save_mean,
              const float* save_rstd, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+// Weight gradient from the tap-major scratch of conv_wgrad's w_mode 3 into torch's OIHW layout (overwrites dW):
+//   s2d == 0: scratch [k*k][N][K]            -> dW[n][c][t] = scratch[t][n][c]                       (k x k filter)
+//   s2d == 1: scratch [4][N][4K] (2x2 taps over the space-to-depth input) -> dW[n][c][dy][dx] (3x3 stride-2 filter),
+//             dy = 2*sy+py-1, dx = 2*sx+px-1, channel (py*2+px)*K + c
+int wgrad_finish(const float* scratch, int N, int K, int k, int s2d, float* dW, cudaStream_t st);
 // y[i] = x[i] * m[i]   (Dropout with an explicit mask holding 0 or 1/(1-p); the same call is its backward)
 int mul_elems(const float* x, const float* m, long long n, float* y, cudaStream_t st);
 
