@@ -3,7 +3,7 @@
 same assignment on every rank.  Runs the seeded config-4 case of tests/c4_case.py (expected classes known from the
 fp32 oracle) with 1 and 8 D4 views and prints one JSON line from rank 0.
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/test_ranks.py"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu/run_test_ranks.py"""
 import json
 import os
 import sys
@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

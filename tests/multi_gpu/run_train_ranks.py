@@ -2,13 +2,13 @@
 """train() itself on N GPUs (round 1 measured the N>1 step only through bench.py's own loop; train()'s multi-rank path
 is covered on CPU by gloo tests with a stand-in model).  Launch:
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_two_ranks.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu/run_train_ranks.py
 
 Builds a small RxRx1-shaped tree (lossless PNG bytes under .jpeg names), trains DenseNet-121 for two epochs at 64x64
 with a global batch of 8 and checks, on every rank: the replicas' parameters are bit-identical after training (gradient
 all-reduce + replicated SGD), the loss is finite, and rank 0 wrote the checkpoint.  Prints one JSON line from rank 0.
 
-    ... tools/train_two_ranks.py --size 512 --samples 256 --bs 64 --decode gpu --workers 4
+    ... tests/multi_gpu/run_train_ranks.py --size 512 --samples 256 --bs 64 --decode gpu --workers 4
 measures train()'s own throughput at the benchmark's image size: real q95 JPEG files through torch's DataLoader
 (worker processes), host or device decode, fused loader, native step, phased all-reduce; images/s = all ranks' images
 of the second epoch / the slowest rank's wall time for it."""
@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

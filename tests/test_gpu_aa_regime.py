@@ -166,3 +166,28 @@ def test_bn_backward_with_small_and_negative_gammas(cuda):
     print("BatchNorm gradients, degenerate gammas: (our error)/(2 x torch-bf16 error + 2%) worst:",
           [(round(w[0], 3), w[1]) for w in worst[:5]])
     assert worst[0][0] < 1.0, worst[:5]
+
+
+def test_two_identical_steps_agree_to_accumulation_order(cuda):
+    """The same training step twice from the same state at 512x512: the only run-to-run freedom is the order of the
+    fp32 atomics / L2 reduce-adds behind the BatchNorm sums and the weight gradients (~1e-6 relative), so loss and every
+    gradient tensor agree to 1e-4 of the tensor's norm — a stale or recycled tile anywhere in forward or backward would
+    not (companion of the bit-exact repeat-launch stress of the data-gradient kernel in test_gpu_conv.py)."""
+    B, S = 16, 512
+    _, net = _pair(cuda, seed=6)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, 6, S, S, generator=g).to(torch.bfloat16).float().to(cuda)
+    y = torch.randint(0, 1108, (B,), generator=g).to(cuda)
+    net.train()
+    buffers0 = net.bn_buffers.clone()
+    runs = []
+    for _ in range(3):
+        net.bn_buffers.copy_(buffers0)
+        loss = net.train_step(x, y).item()
+        runs.append((loss, net.flat.grad.clone()))
+    for loss, grad in runs[1:]:
+        assert abs(loss - runs[0][0]) < 1e-5 * abs(runs[0][0])
+        for name in net._views:
+            off, k, _ = net._views[name]
+            a, b = grad[off:off + k], runs[0][1][off:off + k]
+            assert (a - b).norm().item() <= 1e-4 * b.norm().item() + 1e-12, name
