@@ -9,7 +9,7 @@ at a time through rxb_stats_accumulate and rxb_load_norm_aug.
 The corpus is regenerated on the device chunk by chunk (generation is outside the timed regions); every chunk is
 larger than the 126 MB L2.  Prints one JSON line (rank 0): GB/s of each pass against the measured HBM copy peak, and
 a known-answer check of the statistics (the exact integer sums of a re-generated chunk).
-Written at the end of round 1 without a GPU left to run it on: unmeasured."""
+Measured in round 2: profiles/r02_corpus_sweep_51_experiments.json (1 GPU), profiles/r02_n2_corpus_sweep.json."""
 import argparse
 import json
 import os
@@ -36,6 +36,14 @@ def main():
     e_begin, e_end = parallel.shard_range(n_exp, rank, world)
     acc = tuple(torch.zeros(n_exp, 6, dtype=torch.int64, device=dev) for _ in range(3))
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    # untimed first launches (module load, first-touch) so that no rank's sum starts with a cold kernel
+    warm = synth_planes_torch(1, 4, dev)
+    ops.stats_accumulate(warm, torch.zeros(4, dtype=torch.int32, device=dev), 1)
+    ops.load_norm_aug(warm, torch.arange(4, dtype=torch.int32, device=dev), torch.zeros(4, dtype=torch.int32, device=dev),
+                      torch.zeros(4, dtype=torch.uint8, device=dev), torch.zeros(4, 2, dtype=torch.int32, device=dev),
+                      torch.zeros(1, 6, device=dev), torch.ones(1, 6, device=dev), (512, 512), ops.OUT_BF16_S2D32)
+    torch.cuda.synchronize()
+    del warm
     stats_ms, images = 0.0, 0
     for e in range(e_begin, e_end):
         for c0 in range(0, per_exp, chunk):
