@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# what the driver runs at round end, on the committed tree: GPU suite, smoke, both bench arms
+set -u
+out=gpurun_out/r02_final
+mkdir -p "$out"
+( time timeout 900 python -m pytest tests -x -q -m gpu ) > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$out/pytest_gpu.log"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; echo "smoke rc=$?"; tail -1 "$out/smoke.log"
+( time timeout 400 python bench.py > "$out/bench.json" 2> "$out/bench.err" ); echo "bench rc=$?"; tail -2 "$out/bench.err"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/r02_final/bench.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "stream", d["stream_launch_comparison"]["value"], "launches", d["gpu_launches"], d["clocks"])
+print("roofline", d["roofline"]["kernel"][:40], round(d["roofline"]["frac"], 3), round(d["roofline"]["share_of_step"], 3), "step", {k: round(v, 3) for k, v in d["step_roofline"].items()})
+PY
+( time timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > "$out/bench_reference.json" 2>/dev/null ); cut -c1-200 "$out/bench_reference.json"
