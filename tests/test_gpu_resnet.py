@@ -197,22 +197,22 @@ def test_train_step_matches_fp32_oracle(cuda, B, G, S):
 
 
 def test_sgd_steps_learn_and_head_only_freezes_the_trunk(cuda):
-    B, G, S = 4, 3, 64
+    B, G, S = 8, 3, 64
     net = TwoSitesResNet50(device=cuda, seed=3)
     g = torch.Generator().manual_seed(1)
-    x = torch.randn(B, G, 6, S, S, generator=g).to(cuda)
+    x = _distinct_samples(B, G, S, g).to(cuda)
     y = torch.randint(0, 1108, (B,), generator=g).to(cuda)
     masks = tuple(torch.ones_like(m) for m in net.dropout_masks(B))
     net.train()
     trunk_before = net.flat.data[:net.head_range()[0]].clone()
     losses = []
-    for i in range(6):
+    for i in range(8):
         losses.append(net.train_step(x, y, masks=masks).item())
-        net.sgd_step(B, G, S, S, lr=0.01, head_only=i < 2)
+        net.sgd_step(B, G, S, S, lr=0.002, head_only=i < 2)
         if i == 1:
             assert torch.equal(net.flat.data[:net.head_range()[0]], trunk_before)      # train.py:46-58: trunk frozen
     assert not torch.equal(net.flat.data[:net.head_range()[0]], trunk_before)
-    assert losses[-1] < losses[0], losses
+    assert all(np.isfinite(losses)) and min(losses[1:]) < 0.8 * losses[0], losses      # it learns (memorises 8 samples)
     net.eval()
     assert torch.isfinite(net(x)).all()
 

@@ -3,7 +3,7 @@
 set -u
 out=gpurun_out/r02_final
 mkdir -p "$out"
-( time timeout 900 python -m pytest tests -x -q -m gpu ) > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$out/pytest_gpu.log"
+( time timeout 900 python -m pytest tests -q -m gpu ) > "$out/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$out/pytest_gpu.log"
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; echo "smoke rc=$?"; tail -1 "$out/smoke.log"
 ( time timeout 400 python bench.py > "$out/bench.json" 2> "$out/bench.err" ); echo "bench rc=$?"; tail -2 "$out/bench.err"
 python - <<'PY'
