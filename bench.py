@@ -256,7 +256,10 @@ def step_traffic_model(B):
             t["conv_wgrad_3x3"] += 2.0 * M * (128 + 32)
             t["conv_dgrad_3x3"] += 2.0 * M * (32 + 128 + 128)
             t["bn_bwd_apply"] += 2.0 * M * 128 * 3
-            t["conv_wgrad_1x1"] += 2.0 * M * (cin + 128)
+            # the 1x1 weight gradient is accumulated by the 1x1 data-gradient kernel from the tiles it already holds
+            # (conv_gemm.cu EPI 3) and moves no bytes of its own; RXB_DBG_NO_WGFUSE=1 restores the separate launch
+            if os.environ.get("RXB_DBG_NO_WGFUSE", "0") not in ("", "0"):
+                t["conv_wgrad_1x1"] += 2.0 * M * (cin + 128)
             t["conv_dgrad_1x1"] += 2.0 * M * (128 + 3 * cin)
         C += 32 * n_layers
         t["grad_fixup"] += 2.0 * M * C0 * 3                         # exact gradient of the block input
@@ -343,6 +346,9 @@ def conv_kernel_rooflines(B, dev, peaks):
     ms = timeit(lambda: ops.conv_dgrad_bn(dy2, W1d, X, sc224, sh224, 224, out_mode=ops.OUT_G_ACCUM, out=G))
     entry("dgrad_1x1_bn_accum", ms, M * (128 + 3 * 224) * 2, 2.0 * M * 224 * 128,
           "1x1 data gradient + ReLU/BN1 backward, L2 reduce-add into the concat gradient (Cin 224)")
+    ms = timeit(lambda: ops.conv_dgrad_bn(dy2, W1d, X, sc224, sh224, 224, out_mode=ops.OUT_G_ACCUM, out=G, wgrad=True))
+    entry("dgrad_1x1_bn_accum_wgrad", ms, M * (128 + 3 * 224) * 2, 2.0 * M * 224 * 128 * 2,
+          "the same launch also accumulating the 1x1 weight gradient from the tiles it holds (what the step runs)")
     ms = timeit(lambda: ops.conv_wgrad(Y, dZ, 128, 32, taps=(3, 3), pad=(1, 1), scale=sc128, shift=sh128))
     entry("wgrad_3x3", ms, M * (128 + 32) * 2, 2.0 * M * 32 * 128 * 9, "3x3 weight gradient")
     ms = timeit(lambda: ops.conv_wgrad(X, dy2, 224, 128, scale=sc224, shift=sh224))

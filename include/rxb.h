@@ -202,6 +202,17 @@ int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const vo
                          int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
                          const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
                          rxb_stream_t stream);
+/* The same launch for a 1x1 convolution (taps 1x1, Cin <= 128) that ALSO accumulates that convolution's weight
+ * gradient from the tiles it already holds in shared memory (torch autograd: a separate convolution_backward weight
+ * kernel that re-reads both tensors):
+ *   dW[k][c] += sum_p dOut[p,k] * A'[p,c],  A' = bf16(relu(X[p,c]*bf16(bn_scale[c]) + bf16(bn_shift[c])))
+ * dW: f32 [Cin][Cout] = the forward convolution's OIHW weight gradient (its output channels are this launch's
+ * contraction channels).  A' is exactly what the forward prologue of rxb_conv_fwd fed the convolution, and the ReLU
+ * mask of dy becomes the test A' > 0.  bn_gamma / bn_beta / sum_dyx may be NULL together. */
+int rxb_conv_dgrad_bn_wgrad(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
+                            int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
+                            const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
+                            float* dW, rxb_stream_t stream);
 /* sum_dyx[c] = sum_p dy[p,c]*X[p,c] for the BatchNorm in front of a convolution, from that convolution's weights and
  * finished weight gradient (fp32 OIHW [Cout][Cin][taps]):  with z = bn_scale*x + bn_shift,
  *   sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap]   (both equal sum_p dL/dA' * A', A' = relu(z)),

@@ -70,6 +70,9 @@ SIGNATURES = {
                                   c_int, c_void_p, c_void_p, c_void_p]),
     "rxb_conv_dgrad_bn_ex": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rxb_conv_dgrad_bn_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     "rxb_bn_sum_dyx_from_wdw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "rxb_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int,

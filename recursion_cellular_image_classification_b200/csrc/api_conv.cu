@@ -52,6 +52,14 @@ int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const vo
                          int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
                          const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
                          rxb_stream_t stream) {
+  return rxb_conv_dgrad_bn_wgrad(d, dOut_bf16, Wt_bf16, X_bf16, ldX, bn_scale, bn_shift, bn_gamma, bn_beta, out_mode,
+                                 out_bf16, sum_dy, sum_dyx, nullptr, stream);
+}
+
+int rxb_conv_dgrad_bn_wgrad(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
+                            int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
+                            const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
+                            float* dW, rxb_stream_t stream) {
   using namespace rxb;
   RXB_CHECK_ARG(d && dOut_bf16 && Wt_bf16 && X_bf16 && bn_scale && bn_shift && out_bf16 && sum_dy,
                 "rxb_conv_dgrad_bn: null pointer");
@@ -76,6 +84,7 @@ int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const vo
   p.e_shift = bn_shift;
   p.e_gamma = bn_gamma;
   p.e_beta = bn_beta;
+  p.wg_dW = dW;
   return launch_conv_gemm(p, dOut_bf16, d->ldA, Wt_bf16, out_bf16, d->ldC, 0, X_bf16, ldX, d->Cin <= 32 ? 32 : 64, false,
                           as_stream(stream));
 }

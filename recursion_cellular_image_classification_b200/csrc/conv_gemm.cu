@@ -69,6 +69,13 @@ struct __align__(16) GemmAux {
   uint64_t stg_free[4];    // store warp has read the staged tile and the statistics MMAs over it are complete
   uint64_t b_full;         // resident weights landed
   uint64_t stats_done;
+  // fused 1x1 weight gradient (EPI 3): thresholds on the RAW activation for the direct reductions of degenerate
+  // channels (e_thr2 / e_sgn2 then hold the test "A' > 0" on the transformed tile), and its barriers
+  uint32_t d_thr2[kMaxBN / 2];
+  uint32_t d_sgn2[kMaxBN / 2];
+  uint64_t xa_ready[4];      // [buffer] activation tile transformed to A' = relu(bn(x)) in place (epilogue group -> MMA warp)
+  uint64_t wg_done[4][2];    // [buffer][epilogue group] the weight-gradient MMAs have finished reading the A' tile
+  uint64_t wg_final;         // every weight-gradient MMA of this CTA has completed
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -252,8 +259,21 @@ __device__ __noinline__ void dgrad_direct_sums(uint32_t fl16, uint32_t taddr, co
   } while (0)
 
 // EPI: 0 = store epilogue for 128-wide tiles (statistics, if any, on the tensor pipe); 1 = store epilogue for
-// narrow tiles (bn < 128: shuffle statistics, x-merged 3x3 tiles); 2 = fused ReLU/BatchNorm-backward dgrad epilogue.
+// narrow tiles (bn < 128: shuffle statistics, x-merged 3x3 tiles); 2 = fused ReLU/BatchNorm-backward dgrad epilogue;
+// 3 = EPI 2 of a 1x1 convolution that ALSO accumulates that convolution's weight gradient (see "fused weight
+// gradient" below): the kernel already holds both of its operands in shared memory.
 // Compile-time so each variant keeps only its own epilogue (register pressure under the 96-register cap).
+//
+// Fused weight gradient (EPI 3).  dW[k][c] = sum_p dY[p][k] * A'[p][c] with A' = relu(bn(X)) contracts over pixels the
+// very tiles this kernel loads for the data gradient: dY (its A operand, two 64-channel stages) and X (the activation
+// tile of the epilogue).  The owning epilogue group turns the X tile into A' in place as soon as it lands (the
+// forward prologue's fma.rn.relu.bf16x2, so the ReLU mask becomes the test A' > 0 - exactly the forward's mask), the
+// MMA warp then issues 2 x 8 MN-major MMAs  D[c][k] += A'^T dY  into TMEM columns [256,384) (unused by the dgrad
+// variant) after the tile's data-gradient MMAs, releases the dY stages and tells the group that the A' tile may be
+// overwritten by the staged result.  At the end four warps transpose the 128x128 fp32 accumulator through the dead
+// pipeline stages and add it to dW with bulk L2 reduce-adds, like conv_wgrad_kernel.  The kernel is HBM-bound with
+// the tensor pipe and shared memory mostly idle, so the extra MMAs are free and the separate weight-gradient launch
+// (re-reading X and dY from HBM) disappears.
 template <int BK, bool PROLOGUE, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -278,7 +298,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int cw = p.bn >= 64 ? 64 : 32;                         // channels per staging / store box
   const int n_boxes = (p.bn + cw - 1) / cw;
   const int stage_tile = 128 * n_boxes * cw * 2;
-  constexpr bool dgrad = EPI == 2;
+  constexpr bool dgrad = EPI >= 2;
+  constexpr bool wg = EPI == 3;
   constexpr bool narrow = EPI == 1;
   uint8_t* smA = smem;
   uint8_t* smB = smA + (size_t)stages * a_stage;
@@ -324,6 +345,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     ptx::mbar_init(&aux->b_full, 1);
     ptx::mbar_init(&aux->stats_done, 1);
+    if (wg) {
+      for (int a = 0; a < 4; ++a) {
+        ptx::mbar_init(&aux->xa_ready[a], 1);
+        ptx::mbar_init(&aux->wg_done[a][0], 1);
+        ptx::mbar_init(&aux->wg_done[a][1], 1);
+      }
+      ptx::mbar_init(&aux->wg_final, 1);
+    }
     ptx::fence_barrier_init();
   }
   if (p.mma_stats) {
@@ -380,6 +409,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool in = dgrad && n0 + c < p.n_total;
     aux->e_scale[c] = in ? p.e_scale[n0 + c] : 0.f;
     aux->e_shift[c] = in ? p.e_shift[n0 + c] : 0.f;
+    if (wg) {   // the forward prologue's fold operands: the same fp32 fold rounded to bf16
+      aux->s_scale[c] = __float2bfloat16_rn(in ? p.e_scale[n0 + c] : 0.f);
+      aux->s_shift[c] = __float2bfloat16_rn(in ? p.e_shift[n0 + c] : 0.f);
+    }
   }
   if (dgrad) {
     for (int c2 = threadIdx.x; c2 < kMaxBN / 2; c2 += kConvThreads) {
@@ -392,8 +425,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         thr |= t1 << (16 * h);
         sg |= sg1 << (16 * h);
       }
-      aux->e_thr2[c2] = thr;
-      aux->e_sgn2[c2] = sg;
+      // fused weight gradient: the epilogue sees A' = relu(bn(x)), whose mask is A' > 0 (thr = +0, no sign flip)
+      aux->e_thr2[c2] = wg ? 0u : thr;
+      aux->e_sgn2[c2] = wg ? 0u : sg;
+      aux->d_thr2[c2] = thr;
+      aux->d_sgn2[c2] = sg;
     }
     if (threadIdx.x < kMaxBN) {   // warps 0-3: one column per lane, the warp's ballot is two flag words
       const int c = n0 + (int)threadIdx.x;
@@ -509,7 +545,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      // fused weight gradient: D[c][k] (128 lanes x 64 columns per dY stage) += A'^T dY, both operands MN-major
+      const uint32_t idesc_wg = ptx::make_idesc_bf16(128, 64, 1, 1);
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
+        const int wg_stage0 = stage;   // first dY stage of this tile (released after the weight-gradient MMAs)
         // accumulator stage it % n_acc, used (it / n_acc) times before: the MMA warp runs up to n_acc tiles ahead of
         // the epilogue groups (each group holds a stage for the whole of its TMEM reads)
         const int acc = it % p.n_acc;
@@ -560,7 +599,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   }
                 }
               }
-              ptx::umma_commit(&aux->empty[stage]);
+              if (!wg) ptx::umma_commit(&aux->empty[stage]);
             }
             __syncwarp();
             accumulate = 1;
@@ -570,7 +609,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ptx::elect_one()) ptx::umma_commit(&aux->tmem_full[acc]);
         __syncwarp();
         if (lane == 0) RXB_TL(1, it, 2);
+        if (wg) {
+          // this tile's weight-gradient MMAs: A = the activation tile turned into A' in place by its epilogue group,
+          // B = the tile's dY stages (still held); then the stages go back to the producer
+          const int sb = it % p.n_stg;
+          ptx::mbar_wait(&aux->xa_ready[sb], (uint32_t)(it / p.n_stg) & 1u, 20);
+          ptx::tcgen05_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
+                                                     ptx::kSwizzle128B);
+            int s2 = wg_stage0;
+            for (int kb = 0; kb < p.kb_per_tap; ++kb) {
+              const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smA + (size_t)s2 * a_stage), 16384, 1024,
+                                                       ptx::kSwizzle128B);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                ptx::umma_bf16_ss(tmem_base + kGramCol + kb * 64, da0 + (uint64_t)(ks * (2048 >> 4)),
+                                  db0 + (uint64_t)(ks * (2048 >> 4)), idesc_wg, (it > 0 || ks > 0) ? 1u : 0u);
+              ptx::umma_commit(&aux->empty[s2]);
+              if (++s2 == stages) s2 = 0;
+            }
+            ptx::umma_commit(&aux->wg_done[sb][it & 1]);
+          }
+          __syncwarp();
+        }
         if (p.mma_stats && it > 0) issue_stats(it - 1);   // the previous tile's epilogue ran under this tile's main loop
+      }
+      if (wg) {
+        if (ptx::elect_one()) ptx::umma_commit(&aux->wg_final);
+        __syncwarp();
       }
       if (p.mma_stats) {
         if (it > 0) issue_stats(it - 1);
@@ -638,9 +705,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       if (leader) RXB_TL(2, it, 2);
       // this group's own barrier of the buffer, used (it / period) times before; period = lcm(n_stg, 2) tiles
-      if (dgrad) {
-        const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
-        ptx::mbar_wait(&aux->epi_in_full[sb][g2], (it / period) & 1, 7);
+      const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
+      if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb][g2], (it / period) & 1, 7);
+      // fused weight gradient: the activation tile becomes A' = relu(bn(x)) in place (both 64-channel boxes, this
+      // group's 256 threads) and is handed to the MMA warp.  CTAs with degenerate BatchNorm channels (rare) need the
+      // raw x for their direct reductions and transform after that pass, below.
+      auto wg_transform = [&]() {
+        for (int bx = 0; bx < n_boxes; ++bx)
+          transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
+                              x0, y0, b0);
+        ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+        if (leader) ptx::mbar_arrive(&aux->xa_ready[sb]);
+      };
+      bool any_flag = false;
+      if constexpr (dgrad) {
+        const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
+        any_flag = (any4.x | any4.y | any4.z | any4.w) != 0;
+      }
+      if constexpr (wg) {
+        if (!any_flag) wg_transform();
       }
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
@@ -657,8 +741,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (dgrad) {
         // degenerate BatchNorm channels (kernel-uniform test, rare): a separate pass over the flagged 16-column chunks
         // BEFORE the activation tile is overwritten, so the main loop below carries no trace of it
-        const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
-        if ((any4.x | any4.y | any4.z | any4.w) != 0) {
+        if (any_flag) {
           for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
             for (int hc = 0; hc < 32; hc += 16) {
               const int cc = c + hc;
@@ -666,11 +749,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (fl16 != 0)
                 dgrad_direct_sums(fl16, tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride + cc,
                                   staging_chunk(so, cw, row, cc), staging_chunk(so, cw, row, cc + 8),
-                                  aux->e_thr2 + (cc >> 1), aux->e_sgn2 + (cc >> 1), row_valid, &aux->s_stat[0][cc],
+                                  aux->d_thr2 + (cc >> 1), aux->d_sgn2 + (cc >> 1), row_valid, &aux->s_stat[0][cc],
                                   &aux->s_stat[1][cc], lane);
             }
           }
+          if constexpr (wg) {
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");   // all raw-x reads done
+            wg_transform();
+          }
         }
+      }
+      if constexpr (wg) {
+        // the staged result overwrites the A' tile: its weight-gradient MMAs must have completed (per-group barrier,
+        // like epi_in_full: a group observes every phase of the barrier it waits on)
+        ptx::mbar_wait(&aux->wg_done[sb][g2], (it / period) & 1, 22);
+        ptx::tcgen05_fence_after();
       }
       for (int c = grp * 32; c < p.bn; c += n_grp * 32) {
         if (n0 + c >= p.n_total) break;
@@ -822,6 +915,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float a = aux->s_stat[0][c], bq = aux->s_stat[1][c];
         if (a != 0.f) atomicAdd(p.ch_sum + n0 + c, a);
         if (bq != 0.f) atomicAdd(p.ch_sumsq + n0 + c, bq);
+      }
+    }
+    if constexpr (wg) {
+      // fused weight gradient out: TMEM lane = input channel c of this N tile, column = dY channel k.  Every MMA of
+      // the CTA has completed, so the A pipeline stages are dead: the fp32 result is transposed into them in torch's
+      // OIHW order (row k = 128 consecutive input channels) and leaves as one bulk L2 reduce-add per k.  (The staging
+      // area runs from the A stages into the weight area that follows them - both dead.)
+      if (g2 == 0 && grp == 0 && my_tiles > 0) {
+        ptx::mbar_wait(&aux->wg_final, 0, 21);
+        ptx::tcgen05_fence_after();
+        float* stg = reinterpret_cast<float*>(smA);
+        const int kcols = p.kb_per_tap * BK;
+        for (int c = 0; c < kcols; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kGramCol + c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[(c + i) * 128 + row] = __uint_as_float(r[i]);
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 4, 128;" ::: "memory");
+        const int valid = min(128, p.n_total - n0);
+        for (int k = et; k < p.cin; k += 128)
+          ptx::bulk_reduce_add_f32(p.wg_dW + (long long)k * p.n_total + n0, stg + k * 128, (uint32_t)valid * 4u);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_all();
       }
     }
   } else {
@@ -1303,6 +1422,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
 
   if (dgrad && prologue) return set_error(RXB_ERR_INVALID, "conv_gemm: the dgrad epilogue has no A prologue");
   if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
+  if (p.wg_dW != nullptr && !(dgrad && p.taps_x == 1 && p.taps_y == 1 && bk == 64 && p.cin <= 128))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: the fused weight gradient is for 1x1 data gradients with cin <= 128");
   // dgrad, and stores of >= 128 channels with statistics, run 128-wide N tiles whose column sums come from the
   // tensor pipe (columns past n_total are zero weights / clipped stores)
   if (p.e_gamma != nullptr && (p.e_beta == nullptr || p.ch_sumsq == nullptr))
@@ -1432,6 +1553,10 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (stages < 2) return set_error(RXB_ERR_INVALID, "conv_gemm: tile too large for shared memory");
   if (p.halo >= 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
   p.stages = (int)stages;
+  // (the result is staged in the A stages AND the weight area behind them: both are dead once every MMA has completed)
+  if (p.wg_dW != nullptr &&
+      stages * a_stage + (p.b_resident ? b_panel : stages * b_stage) < (long long)p.kb_per_tap * bk * 512)
+    return set_error(RXB_ERR_INVALID, "conv_gemm: fused weight gradient: pipeline too small to stage the result");
   const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) +
                                (dgrad ? p.n_stg - 1 : p.n_stg) * stage_tile + fixed);
   dim3 grid(gx, p.n_tiles);
@@ -1453,9 +1578,9 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_, EPI_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, \
                       tmX, p));                                                                                 \
   } while (0)
-  const int epi = dgrad ? 2 : (p.bn < kMaxBN ? 1 : 0);
+  const int epi = dgrad ? (p.wg_dW != nullptr ? 3 : 2) : (p.bn < kMaxBN ? 1 : 0);
   if (bk == 64 && prologue) { if (epi == 1) RXB_LAUNCH_GEMM(64, true, 1); else RXB_LAUNCH_GEMM(64, true, 0); }
-  else if (bk == 64) { if (epi == 2) RXB_LAUNCH_GEMM(64, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(64, false, 1); else RXB_LAUNCH_GEMM(64, false, 0); }
+  else if (bk == 64) { if (epi == 3) RXB_LAUNCH_GEMM(64, false, 3); else if (epi == 2) RXB_LAUNCH_GEMM(64, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(64, false, 1); else RXB_LAUNCH_GEMM(64, false, 0); }
   else { if (epi == 2) RXB_LAUNCH_GEMM(32, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(32, false, 1); else RXB_LAUNCH_GEMM(32, false, 0); }
 #undef RXB_LAUNCH_GEMM
   RXB_LAUNCH_OK();

@@ -58,6 +58,10 @@ struct GemmParams {
   const float* e_shift;
   const float* e_gamma;   // optional (with e_beta and ch_sumsq): BatchNorm weight / bias per N channel; channels that
   const float* e_beta;    // bn_degenerate() flags get direct sum(dy) / sum(dy*x) reductions in the epilogue
+  // EPI_DGRAD_BN of a 1x1 convolution with cin <= 128 (optional): fp32 [cin][n_total] = the convolution's OIHW weight
+  // gradient, dW[k][c] += sum_p A[p][k] * relu(X[p][c]*e_scale[c] + e_shift[c]) (fold operands rounded to bf16 like
+  // the forward prologue), accumulated by the same kernel from the tiles it already holds (conv_gemm.cu, EPI 3)
+  float* wg_dW;
   // ---- filled by launch_conv_gemm
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;

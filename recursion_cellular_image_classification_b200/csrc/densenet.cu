@@ -17,6 +17,7 @@
 //     correction terms into corrA/corrB; the exact gradient of a channel,
 //       dX = G - corrA - xhat * corrB,
 //     is materialised only for the 32-channel slice whose producer is being differentiated.
+#include <stdlib.h>
 #include <vector>
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
@@ -285,7 +286,8 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
 // dgrad with the fused ReLU/BatchNorm backward epilogue (reduction: bn.dsum = sum dy; sum dy*x follows from W.dW)
 static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* dOut, int ldD, int cout,
                          const ConvLayer& cv, int Nprime, int taps, int pad, const __nv_bfloat16* X, int ldx,
-                         const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st) {
+                         const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st,
+                         float* fused_dW = nullptr) {
   GemmParams p = {};
   p.B = B; p.H = H; p.W = W;
   p.n_total = Nprime;
@@ -298,6 +300,7 @@ static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfl
   p.ch_sum = bn.dsum; p.ch_sumsq = bn.dsq;
   p.e_scale = bn.fold.scale; p.e_shift = bn.fold.shift;
   p.e_gamma = n.params + bn.gamma_off; p.e_beta = n.params + bn.beta_off;   // degenerate channels: direct reductions
+  p.wg_dW = fused_dW;   // 1x1: the conv's weight gradient accumulated by the same kernel
   return launch_conv_gemm(p, dOut, ldD, n.arena + cv.dgrad_off, out, ldc, 0, X, ldx, cout <= 32 ? 32 : 64, false, st);
 }
 
@@ -435,11 +438,14 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
                             n.grads + L.bn2.beta_off, nullptr, nullptr, n.params + L.bn2.gamma_off,
                             n.params + L.bn2.beta_off, st));
     RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st));  // dy2 := dY
-    // 1x1 conv
-    RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, 1, 0, &L.bn1.fold, n.dy2, kBott, kBott,
-                           n.grads + L.c1.w_off, 0, st));
+    // 1x1 conv: ONE kernel for its data gradient (into the concat gradient) and its weight gradient - both contract
+    // the same dY and X tiles (RXB_DBG_NO_WGFUSE=1: the separate weight-gradient launch, for comparison)
+    static const bool no_wgfuse = getenv("RXB_DBG_NO_WGFUSE") && atoi(getenv("RXB_DBG_NO_WGFUSE")) != 0;
+    if (no_wgfuse)
+      RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, 1, 0, &L.bn1.fold, n.dy2, kBott, kBott,
+                             n.grads + L.c1.w_off, 0, st));
     RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
-                          OUT_G_ACCUM, blk.G, blk.Ctot, st));
+                          OUT_G_ACCUM, blk.G, blk.Ctot, st, no_wgfuse ? nullptr : n.grads + L.c1.w_off));
     RXB_TRY(bn_bwd_finalize(0, n.params + L.c1.w_off, n.grads + L.c1.w_off, kBott, 1, L.bn1.dsum, L.bn1.dsq,
                             L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
                             n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, n.params + L.bn1.gamma_off,

@@ -304,14 +304,15 @@ OUT_DY, OUT_G_WRITE, OUT_G_ACCUM = 0, 1, 2
 
 
 def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=None, Cin=None, pad=(0, 0),
-                  bn_gamma=None, bn_beta=None):
+                  bn_gamma=None, bn_beta=None, wgrad=False):
     """Data gradient fused with the ReLU/BatchNorm backward of the layer that produced the conv input.
     dOut bf16 [B,H,W,ldD]; Wt bf16 [ty,tx,Cout,Cin] = the dgrad operand (tap-flipped, transposed weights);
     X bf16 [B,H,W,ldX] raw activation whose relu(bn(.)) fed the conv (channels 0..Cout).
     Returns (out bf16 [B,H,W,ldC], sum_dy f32 [Cout]); the second BatchNorm-backward reduction comes from
     bn_sum_dyx_from_wdw.  With bn_gamma / bn_beta (the BatchNorm's weight and bias, f32 [Cout]) the channels the
     library flags as degenerate get direct reductions and a third value is returned: sum_dyx f32 [Cout] (zero for
-    the channels that were not flagged)."""
+    the channels that were not flagged).  wgrad=True (1x1, Cin <= 128): the same launch also accumulates the forward
+    convolution's OIHW weight gradient dW f32 [Cin, Cout] (= sum_p dOut[p,k] * relu(bn(X))[p,c]), returned last."""
     require_gpu()
     dOut = _cuda(dOut, torch.bfloat16)
     Wt = _cuda(Wt, torch.bfloat16)
@@ -324,6 +325,15 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     ldC = out.shape[-1]
     s1 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
     d = _desc(B, H, W, Cin, ldD, Cout, ldC, 0, (ty, tx), pad, False, True)
+    if wgrad:
+        dW = torch.zeros(Cin, Cout, dtype=torch.float32, device=dOut.device)
+        s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device) if bn_gamma is not None else None
+        check(load().rxb_conv_dgrad_bn_wgrad(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1],
+                                             ptr(_cuda(bn_scale)), ptr(_cuda(bn_shift)),
+                                             ptr(_cuda(bn_gamma)) if bn_gamma is not None else None,
+                                             ptr(_cuda(bn_beta)) if bn_beta is not None else None, out_mode,
+                                             ptr(out), ptr(s1), ptr(s2), ptr(dW), stream_ptr()))
+        return (out, s1, s2, dW) if s2 is not None else (out, s1, dW)
     if bn_gamma is not None:
         s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
         check(load().rxb_conv_dgrad_bn_ex(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1],

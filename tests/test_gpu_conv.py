@@ -189,6 +189,91 @@ def test_conv_dgrad_bn_matches_torch(cuda, B, H, W, Cd, Cx, ldX, k, out_mode):
                                atol=4e-3 * d64.abs().sum(0).max().item())
 
 
+WGF_CASES = [
+    # B, H, W, Cd (dOut channels = the forward conv's outputs), Cx (its inputs), ldX, out_mode, degenerate channels
+    (2, 16, 16, 128, 96, 256, 2, False),
+    (3, 8, 8, 128, 224, 256, 1, False),        # two images per 128-pixel tile, the last tile half empty
+    (2, 16, 16, 64, 128, 128, 0, False),       # one dY stage
+    (1, 128, 128, 128, 160, 256, 2, False),
+    (2, 12, 20, 128, 160, 192, 2, True),       # tiles hang over the image edge; direct reductions before the transform
+    (2, 32, 32, 128, 992, 1024, 2, False),     # eight N tiles (block 3/4 widths)
+    (16, 128, 128, 128, 224, 256, 2, False),   # benchmark regime: ~14 tiles per CTA, every buffer and stage wraps
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cd,Cx,ldX,out_mode,degenerate", WGF_CASES)
+def test_conv_dgrad_bn_fused_wgrad(cuda, B, H, W, Cd, Cx, ldX, out_mode, degenerate):
+    """rxb_conv_dgrad_bn_wgrad: the 1x1 data gradient with the weight gradient of the same convolution accumulated by
+    the same kernel.  A' = bf16(relu(x*bf16(s) + bf16(h))) is what the forward prologue fed the convolution:
+    dW[k][c] = sum_p dOut[p,k] * A'[p,c], and the ReLU mask of dy is A' > 0."""
+    gen = torch.Generator().manual_seed(B * 131 + H + Cd + Cx)
+    dOut = _rand_bf16((B, H, W, Cd), gen)
+    Wt = _rand_bf16((Cx, Cd, 1, 1), gen, scale=Cd ** -0.5)
+    X = _rand_bf16((B, H, W, ldX), gen)
+    gamma = torch.rand(Cx, generator=gen) + 0.5
+    beta = torch.randn(Cx, generator=gen) * 0.3
+    flagged = []
+    if degenerate:
+        gamma[3], gamma[17], gamma[64], gamma[100] = 0.0, 1e-4, -2e-4, 0.01
+        beta[100], beta[3] = 0.9, 0.25
+        flagged = [3, 17, 64, 100]
+    rstd = torch.rand(Cx, generator=gen) + 0.5
+    mean = torch.randn(Cx, generator=gen) * 0.1
+    s = gamma * rstd
+    h = beta - mean * s
+    G0 = _rand_bf16((B, H, W, ldX), gen)
+    acc = _ref_conv(dOut, Wt, 0)
+    xv = X[..., :Cx].float()
+    a_prime = torch.relu(xv * s.bfloat16().float() + h.bfloat16().float()).to(torch.bfloat16).float()
+    dy = acc * (a_prime > 0)
+    ref = {0: dy, 1: s * dy, 2: G0[..., :Cx].float() + s * dy}[out_mode]
+    ref_dW = dOut.double().reshape(-1, Cd).t() @ a_prime.double().reshape(-1, Cx)          # [Cd, Cx]
+    out = G0.clone().to(cuda)
+    kw = dict(bn_gamma=gamma.to(cuda), bn_beta=beta.to(cuda)) if degenerate else {}
+    res = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
+                            out_mode=out_mode, out=out, wgrad=True, **kw)
+    torch.cuda.synchronize()
+    out, s1, dW = res[0], res[1], res[-1]
+    got = out[..., :Cx].float().cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), "max err %g vs %g" % (err, ref.abs().max().item())
+    assert torch.equal(out[..., Cx:].cpu(), G0[..., Cx:]), "channels beyond Cout must stay untouched"
+    d64 = dy.double().reshape(-1, Cx)
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=4e-3,
+                               atol=4e-3 * d64.abs().sum(0).max().item())
+    werr = (dW.cpu().double() - ref_dW).abs().max().item()
+    assert werr <= 2e-3 * ref_dW.abs().max().item() + 1e-3, "dW max err %g vs %g" % (werr, ref_dW.abs().max().item())
+    if degenerate:
+        s2 = res[2].cpu().numpy()
+        # the direct reductions use the mask of the raw activation with the fp32 fold (they run before the transform)
+        dy_raw = (acc * ((xv * s + h) > 0)).double().reshape(-1, Cx)
+        want2 = (dy_raw * xv.double().reshape(-1, Cx)).sum(0).numpy()
+        np.testing.assert_allclose(s2[flagged], want2[flagged], rtol=1e-4,
+                                   atol=1e-5 * (dy_raw * xv.double().reshape(-1, Cx)).abs().sum(0).max().item())
+        assert (s2[[c for c in range(Cx) if c not in flagged]] == 0).all()
+
+
+def test_conv_dgrad_bn_fused_wgrad_repeatable_output(cuda):
+    """50 launches at ~14 tiles per CTA: the data-gradient output is bit-identical every time (the tile hand-offs
+    between the epilogue groups, the MMA warp and the TMA engine hold), dW agrees to accumulation-order noise."""
+    B, H, W, Cd, Cx, ldX = 16, 128, 128, 128, 224, 256
+    gen = torch.Generator().manual_seed(5)
+    dOut = _rand_bf16((B, H, W, Cd), gen).to(cuda)
+    Wt = _tap_major(_rand_bf16((Cx, Cd, 1, 1), gen, scale=Cd ** -0.5)).to(cuda)
+    X = _rand_bf16((B, H, W, ldX), gen).to(cuda)
+    s = (torch.rand(Cx, generator=gen) + 0.5).to(cuda)
+    h = (torch.randn(Cx, generator=gen) * 0.3).to(cuda)
+    first = None
+    for i in range(50):
+        out, s1, dW = ops.conv_dgrad_bn(dOut, Wt, X, s, h, Cx, out_mode=1, wgrad=True)
+        torch.cuda.synchronize()
+        if first is None:
+            first = (out.clone(), dW.clone())
+        else:
+            assert torch.equal(out, first[0]), "launch %d: output differs" % i
+            assert (dW - first[1]).abs().max().item() <= 1e-4 * first[1].abs().max().item()
+
+
 @pytest.mark.parametrize("k,Cin,Cout", [(1, 96, 128), (3, 128, 32)])
 def test_bn_backward_sums_from_wdw(cuda, k, Cin, Cout):
     """The BatchNorm-backward reduction sum(dy*x) recovered from W.dW equals the direct reduction: forward
