@@ -208,7 +208,9 @@ int rxb_conv_dgrad_bn_ex(const rxb_conv_desc* d, const void* dOut_bf16, const vo
  *   dW[k][c] += sum_p dOut[p,k] * A'[p,c],  A' = bf16(relu(X[p,c]*bf16(bn_scale[c]) + bf16(bn_shift[c])))
  * dW: f32 [Cin][Cout] = the forward convolution's OIHW weight gradient (its output channels are this launch's
  * contraction channels).  A' is exactly what the forward prologue of rxb_conv_fwd fed the convolution, and the ReLU
- * mask of dy becomes the test A' > 0.  bn_gamma / bn_beta / sum_dyx may be NULL together. */
+ * mask of dy becomes the test A' > 0.  bn_gamma / bn_beta / sum_dyx may be NULL together.
+ * Also accepted: the dense layers' 3x3 data gradient (taps 3x3, pad 1, Cin 32 -> Cout 128, H > 8, W > 4), with
+ * dW f32 [32][128][3][3] (OIHW of the forward 3x3 convolution) - its full-halo dOut box serves both contractions. */
 int rxb_conv_dgrad_bn_wgrad(const rxb_conv_desc* d, const void* dOut_bf16, const void* Wt_bf16, const void* X_bf16,
                             int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
                             const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,

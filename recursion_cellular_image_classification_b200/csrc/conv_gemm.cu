@@ -100,6 +100,14 @@ PixelTiling make_tiling(int B, int H, int W) {
   return t;
 }
 
+// The dense layers' 3x3 data gradient can carry its weight gradient (EPI 4) when the tall 8x16 single-image tiling
+// applies, i.e. when launch_conv_gemm picks the full-halo tile for it.
+bool conv_dgrad3x3_wgrad_fusable(int B, int H, int W) {
+  (void)B;
+  static const int off = getenv("RXB_DBG_NO_WGFUSE3") ? atoi(getenv("RXB_DBG_NO_WGFUSE3")) : 0;
+  return !off && H > 8 && W > 4;
+}
+
 PixelTiling make_tiling_tall(int B, int H, int W) {
   PixelTiling t;
   t.W = W; t.H = H; t.B = B;
@@ -274,6 +282,14 @@ __device__ __noinline__ void dgrad_direct_sums(uint32_t fl16, uint32_t taddr, co
 // pipeline stages and add it to dW with bulk L2 reduce-adds, like conv_wgrad_kernel.  The kernel is HBM-bound with
 // the tensor pipe and shared memory mostly idle, so the extra MMAs are free and the separate weight-gradient launch
 // (re-reading X and dY from HBM) disappears.
+//
+// EPI 4 is the same for the dense layers' 3x3 convolution (dZ 32 channels -> 128): the data gradient's A stage IS the
+// full-halo dZ box the weight-gradient kernel's "shifted dOut" mode reads (same origin, same 8x16 tall tiling), so a
+// filter row's three taps are ONE N = 96 MMA  D_ty[c][(tx,n)] += A'^T dZ(shifted)  - 3 x 8 MMAs per tile into TMEM
+// columns [128,416).  That leaves room for ONE data-gradient accumulator stage, so this variant runs one epilogue
+// group of sixteen warps (four column groups) that reads the whole accumulator into registers at once, hands the
+// stage back, and only then waits for the weight-gradient MMAs before overwriting the A' tile with the staged result:
+// the tensor pipe alternates data-gradient and weight-gradient MMAs without waiting for the epilogue.
 template <int BK, bool PROLOGUE, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -299,7 +315,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int n_boxes = (p.bn + cw - 1) / cw;
   const int stage_tile = 128 * n_boxes * cw * 2;
   constexpr bool dgrad = EPI >= 2;
-  constexpr bool wg = EPI == 3;
+  constexpr bool wg = EPI >= 3;
+  constexpr bool wg3 = EPI == 4;                      // 3x3: one accumulator stage, one epilogue group
+  constexpr int kWgCol = wg3 ? kAccStride : kGramCol;   // TMEM columns of the weight-gradient accumulators
+  constexpr int kSumC = wg3 ? 448 : kSumCol;            // ... and of the running column sums
   constexpr bool narrow = EPI == 1;
   uint8_t* smA = smem;
   uint8_t* smB = smA + (size_t)stages * a_stage;
@@ -334,7 +353,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&aux->tmem_full[a], 1);
-      ptx::mbar_init(&aux->tmem_empty[a], n_epi_threads / 64);  // one arrival per warp of the stage's epilogue group
+      ptx::mbar_init(&aux->tmem_empty[a], wg3 ? n_epi_threads / 32 : n_epi_threads / 64);  // one arrival per warp of the stage's epilogue group
     }
     for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&aux->epi_in_full[a][0], 1);
@@ -473,10 +492,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int xb = it % p.n_stg;
           ptx::mbar_wait(&aux->epi_in_empty[xb], ((it / p.n_stg) & 1) ^ 1, 6);
           RXB_TL(0, it, 1);
-          ptx::mbar_arrive_expect_tx(&aux->epi_in_full[xb][it & 1], stage_tile);
+          uint64_t* xbar = &aux->epi_in_full[xb][wg3 ? 0 : (it & 1)];   // the barrier of the group that owns the tile
+          ptx::mbar_arrive_expect_tx(xbar, stage_tile);
           for (int bx = 0; bx < n_boxes; ++bx)
-            ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, &aux->epi_in_full[xb][it & 1],
-                             n0 + bx * cw, x0, y0, b0);
+            ptx::tma_load_4d(st_x + (size_t)xb * stage_tile + bx * (128 * cw * 2), &tmX, xbar, n0 + bx * cw, x0, y0, b0);
         }
         for (int g = 0; g < groups; ++g) {
           const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
@@ -532,7 +551,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t ds = ds0 + (uint64_t)(ks * (2048 >> 4));
             const uint32_t accumulate = (j > 0 || ks > 0) ? 1u : 0u;
             if (!dgrad) ptx::umma_bf16_ss(tmem_base + kGramCol, ds, ds, idesc_gram, accumulate);
-            ptx::umma_bf16_ss(tmem_base + kSumCol, ds, d_ones, idesc_sum, accumulate);
+            ptx::umma_bf16_ss(tmem_base + kSumC, ds, d_ones, idesc_sum, accumulate);
           }
           ptx::umma_commit(dgrad ? &aux->epi_in_empty[sb] : &aux->stg_free[sb]);
         }
@@ -615,7 +634,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int sb = it % p.n_stg;
           ptx::mbar_wait(&aux->xa_ready[sb], (uint32_t)(it / p.n_stg) & 1u, 20);
           ptx::tcgen05_fence_after();
-          if (ptx::elect_one()) {
+          if (wg3) {
+            if (ptx::elect_one()) {
+              // A = the A' tile (two 64-channel boxes, MN-major); B = the full-halo dZ box of this tile's A stage: a
+              // filter row's taps are N atoms ONE box row apart in descending tx order, an 8-pixel K group is one tile
+              // row, consecutive groups lie box_w rows apart (conv_wgrad_kernel's shift_dout == 2 addressing)
+              const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
+                                                       ptx::kSwizzle128B);
+              const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smA + (size_t)wg_stage0 * a_stage), ROW_BYTES,
+                                                       (uint32_t)box_w * ROW_BYTES, kSwz);
+              const uint32_t idesc_wg3 = ptx::make_idesc_bf16(128, 96, 1, 1);
+              const uint32_t kstep_b = (2u * (uint32_t)box_w * ROW_BYTES) >> 4;   // 16 pixels = two tile rows
+              for (int ty = 0; ty < 3; ++ty) {
+                const uint64_t db_t = db0 + (uint64_t)(((uint32_t)((2 - ty) * box_w) * ROW_BYTES) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  ptx::umma_bf16_ss(tmem_base + kWgCol + ty * 96, da0 + (uint64_t)(ks * (2048 >> 4)),
+                                    db_t + (uint64_t)(ks * kstep_b), idesc_wg3, (it > 0 || ks > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit(&aux->empty[wg_stage0]);
+              ptx::umma_commit(&aux->wg_done[sb][0]);
+            }
+          } else if (ptx::elect_one()) {
             const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
                                                      ptx::kSwizzle128B);
             int s2 = wg_stage0;
@@ -624,7 +664,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                        ptx::kSwizzle128B);
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                ptx::umma_bf16_ss(tmem_base + kGramCol + kb * 64, da0 + (uint64_t)(ks * (2048 >> 4)),
+                ptx::umma_bf16_ss(tmem_base + kWgCol + kb * 64, da0 + (uint64_t)(ks * (2048 >> 4)),
                                   db0 + (uint64_t)(ks * (2048 >> 4)), idesc_wg, (it > 0 || ks > 0) ? 1u : 0u);
               ptx::umma_commit(&aux->empty[s2]);
               if (++s2 == stages) s2 = 0;
@@ -679,18 +719,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int first_epi_warp = dgrad ? kWorker0 : kWorker0 + 8;
-    const int warps_per_group = dgrad ? 8 : 4;
+    const int warps_per_group = wg3 ? 16 : dgrad ? 8 : 4;   // EPI 4: ONE group of sixteen warps takes every tile
     const int e = warp - first_epi_warp;
     const int g2 = e / warps_per_group;                       // epilogue group = accumulator stage
     const int grp = (e - g2 * warps_per_group) >> 2;          // column group inside the epilogue group
-    const int n_grp = dgrad ? 2 : 1;
+    const int n_grp = wg3 ? 4 : dgrad ? 2 : 1;
     const int group_threads = warps_per_group * 32;
     const int et = threadIdx.x - (first_epi_warp + g2 * warps_per_group) * 32;   // 0..group_threads-1
     const bool leader = et == 0;
     const uint32_t bar_threads = (uint32_t)group_threads;
     const uint32_t bar_id = 1 + g2;
-    for (int it = g2; it < my_tiles; it += 2) {
-      const int acc = it % p.n_acc;                              // n_acc is even: a stage always belongs to one group
+    for (int it = g2; it < my_tiles; it += (wg3 ? 1 : 2)) {
+      const int acc = it % p.n_acc;                              // n_acc is even (or 1 with one group): a stage always belongs to one group
       const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
       const int m_tile = blockIdx.x + it * gridDim.x;
       int x0, y0, b0;
@@ -705,15 +745,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       if (leader) RXB_TL(2, it, 2);
       // this group's own barrier of the buffer, used (it / period) times before; period = lcm(n_stg, 2) tiles
-      const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
+      const int period = (wg3 || !(p.n_stg & 1)) ? p.n_stg : 2 * p.n_stg;
       if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb][g2], (it / period) & 1, 7);
       // fused weight gradient: the activation tile becomes A' = relu(bn(x)) in place (both 64-channel boxes, this
       // group's 256 threads) and is handed to the MMA warp.  CTAs with degenerate BatchNorm channels (rare) need the
       // raw x for their direct reductions and transform after that pass, below.
       auto wg_transform = [&]() {
-        for (int bx = 0; bx < n_boxes; ++bx)
-          transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
-                              x0, y0, b0);
+        if (wg3) {   // 512 threads: one 64-channel box per half
+          const int bx = et >> 8;
+          transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et & 255, p.t, tw,
+                              th, x0, y0, b0);
+        } else {
+          for (int bx = 0; bx < n_boxes; ++bx)
+            transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
+                                x0, y0, b0);
+        }
         ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
         asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
         if (leader) ptx::mbar_arrive(&aux->xa_ready[sb]);
@@ -759,7 +805,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if constexpr (wg) {
+      if constexpr (wg && !wg3) {
         // the staged result overwrites the A' tile: its weight-gradient MMAs must have completed (per-group barrier,
         // like epi_in_full: a group observes every phase of the barrier it waits on)
         ptx::mbar_wait(&aux->wg_done[sb][g2], (it / period) & 1, 22);
@@ -772,6 +818,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // written over the activation chunk this thread just read.  The mask is a packed-bf16 threshold test.
           // Sixteen columns at a time (register pressure).
           const bool scaled = p.out_mode != OUT_DY;
+          uint32_t pkd[wg3 ? 16 : 1];   // EPI 4: the 32 columns' packed results, written after the accumulator is released
 #pragma unroll
           for (int hc = 0; hc < 32; hc += 16) {
             const int cc = c + hc;
@@ -805,8 +852,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 pk[pi] = pack_bf16x2(m0 ? a0 : 0.f, m1 ? a1 : 0.f);
               }
             }
-            *xc0 = row_valid ? make_uint4(pk[0], pk[1], pk[2], pk[3]) : make_uint4(0u, 0u, 0u, 0u);
-            *xc1 = row_valid ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (wg3) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pkd[hc / 2 + i] = row_valid ? pk[i] : 0u;
+            } else {
+              *xc0 = row_valid ? make_uint4(pk[0], pk[1], pk[2], pk[3]) : make_uint4(0u, 0u, 0u, 0u);
+              *xc1 = row_valid ? make_uint4(pk[4], pk[5], pk[6], pk[7]) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          if constexpr (wg3) {
+            // the accumulator is in registers: hand the stage back (the next tile's data-gradient MMAs queue behind this
+            // tile's weight-gradient MMAs), then wait for those MMAs before overwriting the A' tile they read
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
+            ptx::mbar_wait(&aux->wg_done[sb][0], (it / period) & 1, 22);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *staging_chunk(so, cw, row, c + 8 * i) = make_uint4(pkd[4 * i], pkd[4 * i + 1], pkd[4 * i + 2], pkd[4 * i + 3]);
           }
           continue;
         }
@@ -866,9 +929,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (leader) RXB_TL(2, it, 5);
-      ptx::tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
+      if constexpr (!wg3) {
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
+      }
       // hand the staged tile to the store warp (and to the MMA warp for the column statistics)
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
@@ -885,7 +950,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tcgen05_fence_after();
         const int ch = n0 + row;
         uint32_t s16[16];
-        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kSumCol, s16);
+        ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kSumC, s16);
         ptx::tmem_ld_wait();
         float total = __uint_as_float(s16[0]);
         if (dgrad) {
@@ -922,14 +987,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // the CTA has completed, so the A pipeline stages are dead: the fp32 result is transposed into them in torch's
       // OIHW order (row k = 128 consecutive input channels) and leaves as one bulk L2 reduce-add per k.  (The staging
       // area runs from the A stages into the weight area that follows them - both dead.)
-      if (g2 == 0 && grp == 0 && my_tiles > 0) {
+      if (wg3 && g2 == 0 && grp == 0 && my_tiles > 0) {
+        // 3x3: accumulator group (ty, j) holds tap (ty, 2-j), lane = input channel c, column = output channel n.  OIHW
+        // row n = [c][tap] is 128*9 floats; sixteen rows (72 KB) are staged at a time.
+        ptx::mbar_wait(&aux->wg_final, 0, 21);
+        ptx::tcgen05_fence_after();
+        float* stg = reinterpret_cast<float*>(smA);
+        const int rowlen = 128 * 9;
+        for (int half = 0; half < 2; ++half) {
+          if (half) {   // the reduce-adds of the first half must be done with the staging area
+            ptx::tma_store_wait_read();
+            asm volatile("bar.sync 4, 128;" ::: "memory");
+          }
+          for (int tp = 0; tp < 9; ++tp) {
+            const int tyy = tp / 3, txx = tp - tyy * 3;
+            uint32_t r16[16];
+            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kWgCol + (tyy * 3 + (2 - txx)) * 32 + half * 16, r16);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) stg[i * rowlen + row * 9 + tp] = __uint_as_float(r16[i]);
+          }
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 4, 128;" ::: "memory");
+          if (et < 16)
+            ptx::bulk_reduce_add_f32(p.wg_dW + (long long)(half * 16 + et) * rowlen, stg + et * rowlen, (uint32_t)rowlen * 4u);
+          ptx::tma_store_commit();
+        }
+        ptx::tma_store_wait_all();
+      } else if (!wg3 && g2 == 0 && grp == 0 && my_tiles > 0) {
         ptx::mbar_wait(&aux->wg_final, 0, 21);
         ptx::tcgen05_fence_after();
         float* stg = reinterpret_cast<float*>(smA);
         const int kcols = p.kb_per_tap * BK;
         for (int c = 0; c < kcols; c += 32) {
           uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kGramCol + c, r);
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kWgCol + c, r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) stg[(c + i) * 128 + row] = __uint_as_float(r[i]);
@@ -1422,8 +1514,13 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
 
   if (dgrad && prologue) return set_error(RXB_ERR_INVALID, "conv_gemm: the dgrad epilogue has no A prologue");
   if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
-  if (p.wg_dW != nullptr && !(dgrad && p.taps_x == 1 && p.taps_y == 1 && bk == 64 && p.cin <= 128))
+  const bool wg3 = p.wg_dW != nullptr && p.taps_x == 3 && p.taps_y == 3;
+  if (p.wg_dW != nullptr && !wg3 && !(dgrad && p.taps_x == 1 && p.taps_y == 1 && bk == 64 && p.cin <= 128))
     return set_error(RXB_ERR_INVALID, "conv_gemm: the fused weight gradient is for 1x1 data gradients with cin <= 128");
+  if (wg3 && !(dgrad && bk == 32 && p.cin == 32 && p.n_total == 128 && p.pad_x == 1 && p.pad_y == 1 &&
+               conv_dgrad3x3_wgrad_fusable(p.B, p.H, p.W)))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: the fused 3x3 weight gradient needs 32 -> 128 channels, pad 1 and an "
+                                      "image the 8x16 full-halo tiling covers (H > 8, W > 4)");
   // dgrad, and stores of >= 128 channels with statistics, run 128-wide N tiles whose column sums come from the
   // tensor pipe (columns past n_total are zero weights / clipped stores)
   if (p.e_gamma != nullptr && (p.e_beta == nullptr || p.ch_sumsq == nullptr))
@@ -1438,6 +1535,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   // ~4k cycles per tile (profiles/r02_timelines.log)
   static const int dbg_nacc = getenv("RXB_DBG_NACC") ? atoi(getenv("RXB_DBG_NACC")) : 4;
   p.n_acc = (!dgrad && p.bn < kMaxBN && !p.mma_stats && dbg_nacc == 4) ? 4 : 2;
+  if (wg3) p.n_acc = 1;   // TMEM: 128 accumulator + 288 weight-gradient + 16 sum columns
   p.n_tiles = ceil_div(p.n_total, p.bn);
   p.kb_per_tap = ceil_div(p.cin, bk);
   if (prologue && p.kb_per_tap * bk > kMaxPrologueC + 64) return set_error(RXB_ERR_INVALID, "conv_gemm: cin too large");
@@ -1554,7 +1652,9 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (p.halo >= 2 && !p.b_resident) return set_error(RXB_ERR_INVALID, "conv_gemm: full-halo tile without resident weights");
   p.stages = (int)stages;
   // (the result is staged in the A stages AND the weight area behind them: both are dead once every MMA has completed)
-  if (p.wg_dW != nullptr &&
+  if (wg3 && (p.halo != 2 || stages * a_stage + b_panel < 16ll * 128 * 9 * 4))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: fused 3x3 weight gradient: needs the full-halo tile and 72 KB of staging");
+  if (p.wg_dW != nullptr && !wg3 &&
       stages * a_stage + (p.b_resident ? b_panel : stages * b_stage) < (long long)p.kb_per_tap * bk * 512)
     return set_error(RXB_ERR_INVALID, "conv_gemm: fused weight gradient: pipeline too small to stage the result");
   const size_t smem = (size_t)(stages * per_stage + (p.b_resident ? b_panel : 0) +
@@ -1578,10 +1678,10 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_, EPI_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, \
                       tmX, p));                                                                                 \
   } while (0)
-  const int epi = dgrad ? (p.wg_dW != nullptr ? 3 : 2) : (p.bn < kMaxBN ? 1 : 0);
+  const int epi = dgrad ? (wg3 ? 4 : p.wg_dW != nullptr ? 3 : 2) : (p.bn < kMaxBN ? 1 : 0);
   if (bk == 64 && prologue) { if (epi == 1) RXB_LAUNCH_GEMM(64, true, 1); else RXB_LAUNCH_GEMM(64, true, 0); }
   else if (bk == 64) { if (epi == 3) RXB_LAUNCH_GEMM(64, false, 3); else if (epi == 2) RXB_LAUNCH_GEMM(64, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(64, false, 1); else RXB_LAUNCH_GEMM(64, false, 0); }
-  else { if (epi == 2) RXB_LAUNCH_GEMM(32, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(32, false, 1); else RXB_LAUNCH_GEMM(32, false, 0); }
+  else { if (epi == 4) RXB_LAUNCH_GEMM(32, false, 4); else if (epi == 2) RXB_LAUNCH_GEMM(32, false, 2); else if (epi == 1) RXB_LAUNCH_GEMM(32, false, 1); else RXB_LAUNCH_GEMM(32, false, 0); }
 #undef RXB_LAUNCH_GEMM
   RXB_LAUNCH_OK();
   if (dbg_tl) {   // development: print the timeline of CTA (0,0), cycles relative to its first event

@@ -16,6 +16,7 @@ struct PixelTiling {
 };
 PixelTiling make_tiling(int B, int H, int W);       // wide tiles (tw as large as possible)
 PixelTiling make_tiling_tall(int B, int H, int W);  // tw <= 8: tall tiles for the row-halo tap reuse
+bool conv_dgrad3x3_wgrad_fusable(int B, int H, int W);   // GemmParams::wg_dW may be given for a 3x3 (32 -> 128) dgrad
 
 enum EpiMode {
   EPI_STORE = 0,     // out[p, c_off+n] = bf16(acc) ; optional per-channel sum / sum-of-squares of the stored value
@@ -58,6 +59,7 @@ struct GemmParams {
   const float* e_shift;
   const float* e_gamma;   // optional (with e_beta and ch_sumsq): BatchNorm weight / bias per N channel; channels that
   const float* e_beta;    // bn_degenerate() flags get direct sum(dy) / sum(dy*x) reductions in the epilogue
+  // (also for the dense layers' 3x3, cin 32 -> n_total 128, when conv_dgrad3x3_wgrad_fusable(): fp32 OIHW [32][128][3][3])
   // EPI_DGRAD_BN of a 1x1 convolution with cin <= 128 (optional): fp32 [cin][n_total] = the convolution's OIHW weight
   // gradient, dW[k][c] += sum_p A[p][k] * relu(X[p][c]*e_scale[c] + e_shift[c]) (fold operands rounded to bf16 like
   // the forward prologue), accumulated by the same kernel from the tiles it already holds (conv_gemm.cu, EPI 3)

@@ -428,11 +428,14 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
     // exact gradient of this layer's 32 output channels
     RXB_TRY(grad_fixup(blk.G, blk.X, blk.Ctot, blk.M, L.Cin, kGrowth, closing.fold.mean, closing.fold.rstd, blk.corrA,
                        blk.corrB, n.dZ, st));
-    // 3x3 conv: weight gradient, then data gradient fused with ReLU/BN2 backward reductions
-    RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, L.Y, kBott, kBott, 3, 1, &L.bn2.fold, n.dZ, kGrowth, kGrowth,
-                           n.grads + L.c2.w_off, 0, st));
+    // 3x3 conv: data gradient fused with ReLU/BN2 backward reductions AND the conv's weight gradient (one kernel: the
+    // full-halo dZ box and the Y tile serve both); maps too small for the 8x16 tiling keep the separate launch
+    const bool fuse3 = conv_dgrad3x3_wgrad_fusable(c.B, blk.H, blk.W);
+    if (!fuse3)
+      RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, L.Y, kBott, kBott, 3, 1, &L.bn2.fold, n.dZ, kGrowth, kGrowth,
+                             n.grads + L.c2.w_off, 0, st));
     RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
-                          n.dy2, kBott, st));
+                          n.dy2, kBott, st, fuse3 ? n.grads + L.c2.w_off : nullptr));
     RXB_TRY(bn_bwd_finalize(1, n.params + L.c2.w_off, n.grads + L.c2.w_off, kGrowth, 9, L.bn2.dsum, L.bn2.dsq,
                             L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
                             n.grads + L.bn2.beta_off, nullptr, nullptr, n.params + L.bn2.gamma_off,

@@ -312,7 +312,8 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     bn_sum_dyx_from_wdw.  With bn_gamma / bn_beta (the BatchNorm's weight and bias, f32 [Cout]) the channels the
     library flags as degenerate get direct reductions and a third value is returned: sum_dyx f32 [Cout] (zero for
     the channels that were not flagged).  wgrad=True (1x1, Cin <= 128): the same launch also accumulates the forward
-    convolution's OIHW weight gradient dW f32 [Cin, Cout] (= sum_p dOut[p,k] * relu(bn(X))[p,c]), returned last."""
+    convolution's OIHW weight gradient dW f32 [Cin, Cout] (= sum_p dOut[p,k] * relu(bn(X))[p,c]), returned last; the
+    dense layers' 3x3 (Cin 32 -> Cout 128, pad 1, H > 8, W > 4) too: dW f32 [32, 128, 3, 3]."""
     require_gpu()
     dOut = _cuda(dOut, torch.bfloat16)
     Wt = _cuda(Wt, torch.bfloat16)
@@ -326,7 +327,7 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     s1 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device)
     d = _desc(B, H, W, Cin, ldD, Cout, ldC, 0, (ty, tx), pad, False, True)
     if wgrad:
-        dW = torch.zeros(Cin, Cout, dtype=torch.float32, device=dOut.device)
+        dW = torch.zeros((Cin, Cout) if ty * tx == 1 else (Cin, Cout, ty, tx), dtype=torch.float32, device=dOut.device)
         s2 = torch.zeros(Cout, dtype=torch.float32, device=dOut.device) if bn_gamma is not None else None
         check(load().rxb_conv_dgrad_bn_wgrad(ctypes.byref(d), ptr(dOut), ptr(Wt), ptr(X), X.shape[-1],
                                              ptr(_cuda(bn_scale)), ptr(_cuda(bn_shift)),

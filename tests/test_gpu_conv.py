@@ -274,6 +274,84 @@ def test_conv_dgrad_bn_fused_wgrad_repeatable_output(cuda):
             assert (dW - first[1]).abs().max().item() <= 1e-4 * first[1].abs().max().item()
 
 
+WGF3_CASES = [
+    # B, H, W, degenerate channels
+    (2, 16, 16, False),
+    (2, 12, 20, True),         # tiles hang over the image edge; direct reductions before the transform
+    (1, 20, 28, False),
+    (2, 64, 64, False),
+    (3, 32, 32, False),        # block-3 geometry
+    (16, 128, 128, False),     # benchmark regime: ~110 tiles per CTA at B = 128, 14 here
+]
+
+
+@pytest.mark.parametrize("B,H,W,degenerate", WGF3_CASES)
+def test_conv_dgrad3x3_bn_fused_wgrad(cuda, B, H, W, degenerate):
+    """rxb_conv_dgrad_bn_wgrad on the dense layers' 3x3 (dZ 32 channels -> 128): data gradient + ReLU/BN2 backward
+    and the OIHW weight gradient of the same convolution from one kernel."""
+    Cd, Cx = 32, 128
+    gen = torch.Generator().manual_seed(B * 17 + H + W)
+    dOut = _rand_bf16((B, H, W, Cd), gen)
+    Wt = _rand_bf16((Cx, Cd, 3, 3), gen, scale=(Cd * 9) ** -0.5)
+    X = _rand_bf16((B, H, W, Cx), gen)
+    gamma = torch.rand(Cx, generator=gen) + 0.5
+    beta = torch.randn(Cx, generator=gen) * 0.3
+    flagged = []
+    if degenerate:
+        gamma[3], gamma[17], gamma[64], gamma[100] = 0.0, 1e-4, -2e-4, 0.01
+        beta[100], beta[3] = 0.9, 0.25
+        flagged = [3, 17, 64, 100]
+    rstd = torch.rand(Cx, generator=gen) + 0.5
+    mean = torch.randn(Cx, generator=gen) * 0.1
+    s = gamma * rstd
+    h = beta - mean * s
+    acc = _ref_conv(dOut, Wt, 1)
+    xv = X.float()
+    a_prime = torch.relu(xv * s.bfloat16().float() + h.bfloat16().float()).to(torch.bfloat16).float()
+    dy = acc * (a_prime > 0)
+    w = torch.zeros(Cd, Cx, 3, 3, dtype=torch.double, requires_grad=True)
+    F.conv2d(a_prime.double().permute(0, 3, 1, 2), w, padding=1).backward(dOut.double().permute(0, 3, 1, 2))
+    ref_dW = w.grad
+    kw = dict(bn_gamma=gamma.to(cuda), bn_beta=beta.to(cuda)) if degenerate else {}
+    res = ops.conv_dgrad_bn(dOut.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda), Cx,
+                            out_mode=0, pad=(1, 1), wgrad=True, **kw)
+    torch.cuda.synchronize()
+    out, s1, dW = res[0], res[1], res[-1]
+    err = (out.float().cpu() - dy).abs().max().item()
+    assert err <= 2e-2 * dy.abs().max().item(), "max err %g vs %g" % (err, dy.abs().max().item())
+    d64 = dy.double().reshape(-1, Cx)
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=4e-3,
+                               atol=4e-3 * d64.abs().sum(0).max().item())
+    werr = (dW.cpu().double() - ref_dW).abs().max().item()
+    assert werr <= 2e-3 * ref_dW.abs().max().item() + 1e-3, "dW max err %g vs %g" % (werr, ref_dW.abs().max().item())
+    if degenerate:
+        s2 = res[2].cpu().numpy()
+        dy_raw = (acc * ((xv * s + h) > 0)).double().reshape(-1, Cx)
+        want2 = (dy_raw * xv.double().reshape(-1, Cx)).sum(0).numpy()
+        np.testing.assert_allclose(s2[flagged], want2[flagged], rtol=1e-4,
+                                   atol=1e-5 * (dy_raw * xv.double().reshape(-1, Cx)).abs().sum(0).max().item())
+
+
+def test_conv_dgrad3x3_bn_fused_wgrad_repeatable_output(cuda):
+    """50 launches at ~14 tiles per CTA: bit-identical data gradient every time, dW to accumulation-order noise."""
+    B, H, W, Cd, Cx = 16, 128, 128, 32, 128
+    gen = torch.Generator().manual_seed(6)
+    dOut = _rand_bf16((B, H, W, Cd), gen).to(cuda)
+    Wt = _tap_major(_rand_bf16((Cx, Cd, 3, 3), gen, scale=(Cd * 9) ** -0.5)).to(cuda)
+    X = _rand_bf16((B, H, W, Cx), gen).to(cuda)
+    s = (torch.rand(Cx, generator=gen) + 0.5).to(cuda)
+    h = (torch.randn(Cx, generator=gen) * 0.3).to(cuda)
+    first = None
+    for i in range(50):
+        out, s1, dW = ops.conv_dgrad_bn(dOut, Wt, X, s, h, Cx, out_mode=0, pad=(1, 1), wgrad=True)
+        torch.cuda.synchronize()
+        if first is None:
+            first = (out.clone(), dW.clone())
+        else:
+            assert torch.equal(out, first[0]), "launch %d: output differs" % i
+            assert (dW - first[1]).abs().max().item() <= 1e-4 * first[1].abs().max().item()
+
+
 @pytest.mark.parametrize("k,Cin,Cout", [(1, 96, 128), (3, 128, 32)])
 def test_bn_backward_sums_from_wdw(cuda, k, Cin, Cout):
     """The BatchNorm-backward reduction sum(dy*x) recovered from W.dW equals the direct reduction: forward
