@@ -566,6 +566,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int it = 0;
       // fused weight gradient: D[c][k] (128 lanes x 64 columns per dY stage) += A'^T dY, both operands MN-major
       const uint32_t idesc_wg = ptx::make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc_wg128 = ptx::make_idesc_bf16(128, 128, 1, 1);
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x, ++it) {
         const int wg_stage0 = stage;   // first dY stage of this tile (released after the weight-gradient MMAs)
         // accumulator stage it % n_acc, used (it / n_acc) times before: the MMA warp runs up to n_acc tiles ahead of
@@ -659,6 +660,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(st_out + (size_t)sb * stage_tile), 16384, 1024,
                                                      ptx::kSwizzle128B);
             int s2 = wg_stage0;
+            if (p.kb_per_tap == 2 && wg_stage0 + 1 < stages) {
+              // the tile's two dY stages are adjacent (no wrap of the stage ring between them): ONE N = 128 MMA chain
+              // whose two 64-channel atoms lie a stage (16 KB) apart - half the MMAs
+              const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smA + (size_t)s2 * a_stage), (uint32_t)a_stage, 1024,
+                                                       ptx::kSwizzle128B);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                ptx::umma_bf16_ss(tmem_base + kWgCol, da0 + (uint64_t)(ks * (2048 >> 4)),
+                                  db0 + (uint64_t)(ks * (2048 >> 4)), idesc_wg128, (it > 0 || ks > 0) ? 1u : 0u);
+              ptx::umma_commit(&aux->empty[s2]);
+              ptx::umma_commit(&aux->empty[s2 + 1]);
+            } else
             for (int kb = 0; kb < p.kb_per_tap; ++kb) {
               const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smA + (size_t)s2 * a_stage), 16384, 1024,
                                                        ptx::kSwizzle128B);
@@ -729,6 +742,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = et == 0;
     const uint32_t bar_threads = (uint32_t)group_threads;
     const uint32_t bar_id = 1 + g2;
+    // fused weight gradient: tile `t` (buffer t % n_stg) of this CTA becomes A' = relu(bn(x)) in place (both 64-channel
+    // boxes, every thread of the group) and is handed to the MMA warp
+    auto wg_transform_tile = [&](int t) {
+      const int tsb = t % p.n_stg;
+      uint8_t* tso = st_out + (size_t)tsb * stage_tile;
+      int tx0, ty0, tb0;
+      tile_origin(p.t, blockIdx.x + t * gridDim.x, tx0, ty0, tb0);
+      if (wg3) {   // 512 threads: one 64-channel box per half
+        const int bx = et >> 8;
+        transform_box_sw128(tso + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et & 255, p.t, tw,
+                            th, tx0, ty0, tb0);
+      } else {
+        for (int bx = 0; bx < n_boxes; ++bx)
+          transform_box_sw128(tso + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
+                              tx0, ty0, tb0);
+      }
+      ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (leader) ptx::mbar_arrive(&aux->xa_ready[tsb]);
+    };
+    bool any_flag = false;
+    if constexpr (dgrad) {
+      const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
+      any_flag = (any4.x | any4.y | any4.z | any4.w) != 0;
+    }
+    // EPI 4 runs the transform one tile AHEAD (software pipelining): tile it+1 is transformed between the TMEM reads
+    // of tile it and the wait for tile it's weight-gradient MMAs, so those MMAs never wait for this group to come
+    // round again.  (CTAs with degenerate BatchNorm channels need the raw x after tmem_full and keep the simple order.)
+    const bool wg_ahead = wg3 && !any_flag;
+    if (wg_ahead && my_tiles > 0) {
+      ptx::mbar_wait(&aux->epi_in_full[0][0], 0, 23);
+      wg_transform_tile(0);
+    }
     for (int it = g2; it < my_tiles; it += (wg3 ? 1 : 2)) {
       const int acc = it % p.n_acc;                              // n_acc is even (or 1 with one group): a stage always belongs to one group
       const uint32_t acc_phase = (uint32_t)(it / p.n_acc) & 1u;
@@ -747,30 +793,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // this group's own barrier of the buffer, used (it / period) times before; period = lcm(n_stg, 2) tiles
       const int period = (wg3 || !(p.n_stg & 1)) ? p.n_stg : 2 * p.n_stg;
       if (dgrad) ptx::mbar_wait(&aux->epi_in_full[sb][g2], (it / period) & 1, 7);
-      // fused weight gradient: the activation tile becomes A' = relu(bn(x)) in place (both 64-channel boxes, this
-      // group's 256 threads) and is handed to the MMA warp.  CTAs with degenerate BatchNorm channels (rare) need the
-      // raw x for their direct reductions and transform after that pass, below.
-      auto wg_transform = [&]() {
-        if (wg3) {   // 512 threads: one 64-channel box per half
-          const int bx = et >> 8;
-          transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et & 255, p.t, tw,
-                              th, x0, y0, b0);
-        } else {
-          for (int bx = 0; bx < n_boxes; ++bx)
-            transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
-                                x0, y0, b0);
-        }
-        ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-        if (leader) ptx::mbar_arrive(&aux->xa_ready[sb]);
-      };
-      bool any_flag = false;
-      if constexpr (dgrad) {
-        const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
-        any_flag = (any4.x | any4.y | any4.z | any4.w) != 0;
-      }
+      // fused weight gradient: the activation tile is transformed as soon as it lands (EPI 4: already done, one tile
+      // ahead).  CTAs with degenerate BatchNorm channels (rare) need the raw x for their direct reductions and
+      // transform after that pass, below.
       if constexpr (wg) {
-        if (!any_flag) wg_transform();
+        if (!any_flag && !wg_ahead) wg_transform_tile(it);
       }
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
@@ -801,7 +828,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if constexpr (wg) {
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");   // all raw-x reads done
-            wg_transform();
+            wg_transform_tile(it);
           }
         }
       }
@@ -866,6 +893,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
+            if (wg_ahead && it + 1 < my_tiles) {   // the next tile's transform, ahead of its weight-gradient MMAs
+              ptx::mbar_wait(&aux->epi_in_full[(it + 1) % p.n_stg][0], (uint32_t)((it + 1) / p.n_stg) & 1u, 24);
+              wg_transform_tile(it + 1);
+            }
             ptx::mbar_wait(&aux->wg_done[sb][0], (it / period) & 1, 22);
 #pragma unroll
             for (int i = 0; i < 4; ++i)

@@ -482,6 +482,61 @@ int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------ grad fixup
+// dX = G - corrA - xhat*corrB = G + kb*x + kc  with  kb = -rstd*corrB,  kc = mean*rstd*corrB - corrA.
+// A thread keeps ONE 8-channel group of the slice (its two folded constants live in registers) and walks pixels, four
+// rows in flight: the slice is a strided 16*groups-byte run per pixel of the concat buffers, so bytes in flight - not
+// instruction count - set the rate.
+__global__ void __launch_bounds__(kEwThreads)
+grad_fixup_rows_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ X, int ld, long long M,
+                       int c0, int nch, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ corrA, const float* __restrict__ corrB, __nv_bfloat16* __restrict__ dst) {
+  pdl_sync();
+  const int groups = nch >> 3;                       // divides the block size
+  const int cg = threadIdx.x % groups;
+  const int rows_per_block = kEwThreads / groups;
+  const int c = c0 + cg * 8;
+  float kb[8], kc[8];
+  {
+    float mu[8], rs[8], ca[8], cb[8];
+    load8f(mean + c, mu);
+    load8f(rstd + c, rs);
+    load8f(corrA + c, ca);
+    load8f(corrB + c, cb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      kb[e] = -rs[e] * cb[e];
+      kc[e] = mu[e] * rs[e] * cb[e] - ca[e];
+    }
+  }
+  const long long stride = (long long)gridDim.x * rows_per_block;
+  long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / groups;
+  for (; row + 3 * stride < M; row += 4 * stride) {
+    uint4 gv[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gv[u] = ld_stream_v4(G + (row + u * stride) * ld + c);
+      xv[u] = ld_stream_v4(X + (row + u * stride) * ld + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float g[8], x[8];
+      unpack8(gv[u], g);
+      unpack8(xv[u], x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = g[e] + fmaf(kb[e], x[e], kc[e]);
+      *reinterpret_cast<uint4*>(dst + (row + u * stride) * nch + cg * 8) = pack8(g);
+    }
+  }
+  for (; row < M; row += stride) {
+    float g[8], x[8];
+    unpack8(ld_stream_v4(G + row * ld + c), g);
+    unpack8(ld_stream_v4(X + row * ld + c), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = g[e] + fmaf(kb[e], x[e], kc[e]);
+    *reinterpret_cast<uint4*>(dst + row * nch + cg * 8) = pack8(g);
+  }
+}
+
 __global__ void __launch_bounds__(kEwThreads)
 grad_fixup_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ X, int ld, long long M,
                   int c0, int nch, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -511,6 +566,14 @@ int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long
                const float* mean, const float* rstd, const float* corrA, const float* corrB, __nv_bfloat16* dst,
                cudaStream_t st) {
   RXB_PROF(st, PROF_EW_FIXUP);
+  const int groups = nch / 8;
+  if (nch % 8 == 0 && groups >= 1 && groups <= kEwThreads && kEwThreads % groups == 0) {
+    const int rows_per_block = kEwThreads / groups;
+    RXB_CUDA(launch_k(grad_fixup_rows_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, G, X,
+                      ld, M, c0, nch, mean, rstd, corrA, corrB, dst));
+    RXB_LAUNCH_OK();
+    return RXB_OK;
+  }
   RXB_CUDA(launch_k(grad_fixup_kernel, dim3(ew_grid(M * (nch / 8), kEwThreads * 2)), dim3(kEwThreads), (size_t)(0), st, G, X, ld, M, c0, nch, mean, rstd,
                                                                                  corrA, corrB, dst));
   RXB_LAUNCH_OK();

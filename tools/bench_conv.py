@@ -45,7 +45,7 @@ def run_wgrad(B, H, W, Cin, ldA, Cout, k, prologue):
     print("wgrd B%d %dx%d Cin%d(ld%d) Cout%d k%d pro%d : %.3f ms  %.1f TF/s  %.0f GB/s(min traffic)" %
           (B, H, W, Cin, ldA, Cout, k, prologue, ms, fl / ms / 1e9, by / ms / 1e6))
 
-def run_dgrad(B, H, W, Cd, Cx, ldX, k, out_mode):
+def run_dgrad(B, H, W, Cd, Cx, ldX, k, out_mode, wgrad=0):
     dO = torch.randn(B, H, W, Cd, device=dev).to(torch.bfloat16)
     Wt = (torch.randn(k, k, Cx, Cd, device=dev) * 0.05).to(torch.bfloat16)
     X = torch.randn(B, H, W, ldX, device=dev).to(torch.bfloat16)
@@ -53,12 +53,13 @@ def run_dgrad(B, H, W, Cd, Cx, ldX, k, out_mode):
     sh = torch.randn(Cx, device=dev) * 0.1
     out = torch.zeros(B, H, W, ldX if out_mode else Cx, device=dev, dtype=torch.bfloat16)
     pad = {1: 0, 3: 1}[k]
-    ms = timeit(lambda: ops.conv_dgrad_bn(dO, Wt, X, sc, sh, Cx, out_mode=out_mode, out=out, pad=(pad, pad)))
+    ms = timeit(lambda: ops.conv_dgrad_bn(dO, Wt, X, sc, sh, Cx, out_mode=out_mode, out=out, pad=(pad, pad),
+                                          wgrad=bool(wgrad)))
     M = B * H * W
-    fl = 2.0 * M * Cx * Cd * k * k
+    fl = 2.0 * M * Cx * Cd * k * k * (2 if wgrad else 1)
     by = M * (Cd + Cx * (3 if out_mode == 2 else 2)) * 2
-    print("dgrd B%d %dx%d Cd%d Cx%d(ld%d) k%d mode%d : %.3f ms  %.1f TF/s  %.0f GB/s(min traffic)" %
-          (B, H, W, Cd, Cx, ldX, k, out_mode, ms, fl / ms / 1e9, by / ms / 1e6))
+    print("dgrd B%d %dx%d Cd%d Cx%d(ld%d) k%d mode%d wgrad%d : %.3f ms  %.1f TF/s  %.0f GB/s(min traffic)" %
+          (B, H, W, Cd, Cx, ldX, k, out_mode, wgrad, ms, fl / ms / 1e9, by / ms / 1e6))
 
 
 if __name__ == "__main__":
