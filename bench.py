@@ -253,7 +253,9 @@ def step_traffic_model(B):
             t["conv_fwd_1x1"] += 2.0 * M * (cin + 128)
             t["conv_fwd_3x3"] += 2.0 * M * (128 + 32)
             t["grad_fixup"] += 2.0 * M * 32 * 3
-            t["conv_wgrad_3x3"] += 2.0 * M * (128 + 32)
+            # (the 3x3 weight gradient rides in the 3x3 data-gradient kernel wherever its 8x16 tiling applies: H > 8)
+            if H <= 8 or os.environ.get("RXB_DBG_NO_WGFUSE3", "0") not in ("", "0"):
+                t["conv_wgrad_3x3"] += 2.0 * M * (128 + 32)
             t["conv_dgrad_3x3"] += 2.0 * M * (32 + 128 + 128)
             t["bn_bwd_apply"] += 2.0 * M * 128 * 3
             # the 1x1 weight gradient is accumulated by the 1x1 data-gradient kernel from the tiles it already holds
@@ -341,6 +343,10 @@ def conv_kernel_rooflines(B, dev, peaks):
     dy2 = torch.empty(B, H, W, 128, dtype=torch.bfloat16, device=dev)
     ms = timeit(lambda: ops.conv_dgrad_bn(dZ, W3d, Y, sc128, sh128, 128, out_mode=ops.OUT_DY, out=dy2, pad=(1, 1)))
     entry("dgrad_3x3_bn", ms, M * (32 + 128 + 128) * 2, 2.0 * M * 128 * 32 * 9, "3x3 data gradient + ReLU/BN2 backward")
+    ms = timeit(lambda: ops.conv_dgrad_bn(dZ, W3d, Y, sc128, sh128, 128, out_mode=ops.OUT_DY, out=dy2, pad=(1, 1), wgrad=True))
+    entry("dgrad_3x3_bn_wgrad", ms, M * (32 + 128 + 128) * 2, 2.0 * M * 128 * 32 * 9 * 2,
+          "the same launch also accumulating the 3x3 weight gradient (what the step runs; bound by shared-memory "
+          "bandwidth of the tensor-core operand reads, DESIGN.md 5.3)")
     W1d = (torch.randn(1, 1, 224, 128, device=dev) * 0.05).to(torch.bfloat16)
     G = torch.zeros(B, H, W, 256, dtype=torch.bfloat16, device=dev)
     ms = timeit(lambda: ops.conv_dgrad_bn(dy2, W1d, X, sc224, sh224, 224, out_mode=ops.OUT_G_ACCUM, out=G))
@@ -630,13 +636,15 @@ def run_ours(args):
         # time summed over ALL its launches of the step (event-bracketed), with the tensor number beside the HBM one.
         symbols = {
             "conv_wgrad_kernel": (["conv_wgrad_1x1", "conv_wgrad_3x3", "wgrad_other"], "wgrad_1x1",
-                                  "conv_wgrad_kernel (weight gradients: dense-layer 1x1 and 3x3, transitions, stem)"),
-            "conv_gemm_kernel<64,false,2>": (["conv_dgrad_1x1"], "dgrad_1x1_bn_accum",
-                                             "conv_gemm_kernel<64,false,2> (dense-layer 1x1 data gradient + ReLU/BN backward, "
-                                             "L2 reduce-add into the concat gradient)"),
+                                  "conv_wgrad_kernel (weight gradients NOT fused into a data-gradient kernel: transitions, stem)"),
+            "conv_gemm_kernel<64,false,3>": (["conv_dgrad_1x1"], "dgrad_1x1_bn_accum_wgrad",
+                                             "conv_gemm_kernel<64,false,3> (dense-layer 1x1 data gradient + ReLU/BN backward, "
+                                             "L2 reduce-add into the concat gradient, + the 1x1 weight gradient and the "
+                                             "BatchNorm-backward reductions from the same tiles)"),
             "conv_gemm_kernel<64,true,0>": (["conv_fwd_1x1"], "fwd_1x1", "conv_gemm_kernel<64,true,0> (dense-layer 1x1 forward)"),
             "conv_gemm_kernel<64,true,1>": (["conv_fwd_3x3"], "fwd_3x3", "conv_gemm_kernel<64,true,1> (dense-layer 3x3 forward)"),
-            "conv_gemm_kernel<32,false,2>": (["conv_dgrad_3x3"], "dgrad_3x3_bn", "conv_gemm_kernel<32,false,2> (3x3 data gradient)"),
+            "conv_gemm_kernel<32,false,4>": (["conv_dgrad_3x3"], "dgrad_3x3_bn_wgrad",
+                                             "conv_gemm_kernel<32,false,4> (3x3 data gradient + ReLU/BN backward + 3x3 weight gradient)"),
         }
         share = {k: sum(fine[n]["ms_per_step"] for n in v[0]) / prof_total_ms for k, v in symbols.items()}
         top = max(share, key=share.get)
@@ -646,9 +654,9 @@ def run_ours(args):
         alg = sum(model[n] for n in cats)
         # algorithmic FLOPs per image of each symbol's launches (dense 1x1 12.17, dense 3x3 12.98 GFLOP
         # forward; a weight gradient exists for every conv: 30.84)
-        flops_share = {"conv_wgrad_kernel": 30.84e9, "conv_gemm_kernel<64,false,2>": 12.17e9,
+        flops_share = {"conv_wgrad_kernel": 30.84e9 - 12.17e9 - 12.98e9, "conv_gemm_kernel<64,false,3>": 2 * 12.17e9,
                        "conv_gemm_kernel<64,true,0>": 12.17e9, "conv_gemm_kernel<64,true,1>": 12.98e9,
-                       "conv_gemm_kernel<32,false,2>": 12.98e9}[top] * B
+                       "conv_gemm_kernel<32,false,4>": 2 * 12.98e9}[top] * B
         ach = alg / (t_ms * 1e-3) / 1e9
         roofline = {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy",

@@ -973,6 +973,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_arrive(&aux->stg_full[sb]);
       }
     }
+    float tail_s = 0.f, tail_dyx = 0.f;   // this CTA's sum(dy) / direct sum(dy*x) of channel n0 + row (fused BatchNorm tail)
+    bool tail_deg = false;
     if (!narrow && p.do_stats && p.mma_stats) {
       if (dgrad) asm volatile("bar.sync 3, %0;" ::"r"((uint32_t)n_epi_threads) : "memory");   // s_stat of both groups
       // per-channel totals of this CTA from TMEM: lane = channel; Gram diagonal and the sums column
@@ -989,7 +991,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // degenerate channel: the direct fp32 reductions replace the tensor-pipe sum of the (scaled) staged tile
             total = aux->s_stat[0][row];
             const float dyx = aux->s_stat[1][row];
-            if (ch < p.n_total && dyx != 0.f) atomicAdd(p.ch_sumsq + ch, dyx);
+            tail_deg = true;
+            tail_dyx = dyx;
+            if (ch < p.n_total && dyx != 0.f && !(wg && p.tail.mode == 1)) atomicAdd(p.ch_sumsq + ch, dyx);
           } else if (p.out_mode != OUT_DY) {  // the staged value was es*dy
             const float es = aux->e_scale[row];
             total = es != 0.f ? total / es : 0.f;
@@ -1003,7 +1007,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 32; ++i) sq = lane == i ? __uint_as_float(g[i]) : sq;
           if (ch < p.n_total && sq != 0.f) atomicAdd(p.ch_sumsq + ch, sq);
         }
-        if (ch < p.n_total && total != 0.f) atomicAdd(p.ch_sum + ch, total);
+        tail_s = total;
+        if (ch < p.n_total && total != 0.f && !(wg && p.tail.mode == 1)) atomicAdd(p.ch_sum + ch, total);
       }
     } else if (p.do_stats) {
       asm volatile("bar.sync 3, %0;" ::"r"((uint32_t)n_epi_threads) : "memory");   // both groups
@@ -1023,6 +1028,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // row n = [c][tap] is 128*9 floats; sixteen rows (72 KB) are staged at a time.
         ptx::mbar_wait(&aux->wg_final, 0, 21);
         ptx::tcgen05_fence_after();
+        if (p.tail.mode == 2) {
+          // W.dW of this CTA's partial, per input channel c = row: the accumulators against the bf16 weight panel still
+          // resident in shared memory (slot 8-tp, row c, 32 output channels n in four 64B-swizzled chunks)
+          float t = 0.f;
+          for (int tp = 0; tp < 9; ++tp) {
+            const int tyy = tp / 3, txx = tp - tyy * 3;
+            const uint8_t* wrow = smB + (size_t)(8 - tp) * b_tap + row * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r16[16];
+              ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kWgCol + (tyy * 3 + (2 - txx)) * 32 + half * 16, r16);
+              const uint4 w0 = *reinterpret_cast<const uint4*>(wrow + (((2 * half) ^ ((row >> 1) & 3)) << 4));
+              const uint4 w1 = *reinterpret_cast<const uint4*>(wrow + (((2 * half + 1) ^ ((row >> 1) & 3)) << 4));
+              const uint32_t wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                t = fmaf(bf16_lo(wv[i]), __uint_as_float(r16[2 * i]), t);
+                t = fmaf(bf16_hi(wv[i]), __uint_as_float(r16[2 * i + 1]), t);
+              }
+            }
+          }
+          if (!tail_deg && t != 0.f) atomicAdd(p.ch_sumsq + row, t);
+        }
         float* stg = reinterpret_cast<float*>(smA);
         const int rowlen = 128 * 9;
         for (int half = 0; half < 2; ++half) {
@@ -1050,12 +1079,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::tcgen05_fence_after();
         float* stg = reinterpret_cast<float*>(smA);
         const int kcols = p.kb_per_tap * BK;
+        const bool ch_ok = n0 + row < p.n_total;
+        const bool want_t = p.tail.mode == 1 && ch_ok && !tail_deg;
+        float t = 0.f;   // W.dW of this CTA's partial for input channel n0 + row (fused BatchNorm tail)
         for (int c = 0; c < kcols; c += 32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kWgCol + c, r);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) stg[(c + i) * 128 + row] = __uint_as_float(r[i]);
+          if (want_t) {
+            const float* wp = p.tail.W + (long long)c * p.n_total + n0 + row;   // W[k][channel], k = c + i
+#pragma unroll
+            for (int hb = 0; hb < 32; hb += 16) {
+              float wv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) wv[i] = c + hb + i < p.cin ? __ldg(wp + (long long)(hb + i) * p.n_total) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t = fmaf(bf16_round(wv[i]), __uint_as_float(r[hb + i]), t);
+            }
+          }
+        }
+        if (p.tail.mode == 1 && ch_ok) {
+          // bn_bwd_finalize's arithmetic on this CTA's partial sums (linear, so the CTAs' contributions add up)
+          const int ch = n0 + row;
+          const float es = bf16_round(aux->e_scale[row]), eh = bf16_round(aux->e_shift[row]);
+          const float raw = tail_deg ? tail_dyx : (es != 0.f ? (t - eh * tail_s) / es : 0.f);
+          const float qv = p.tail.rstd[ch] * (raw - p.tail.mean[ch] * tail_s);
+          const float sc = aux->e_scale[row] * p.tail.inv_count;
+          if (qv != 0.f) atomicAdd(p.tail.dgamma + ch, qv);
+          if (tail_s != 0.f) atomicAdd(p.tail.dbeta + ch, tail_s);
+          if (tail_s != 0.f) atomicAdd(p.tail.corrA + ch, sc * tail_s);
+          if (qv != 0.f) atomicAdd(p.tail.corrB + ch, sc * qv);
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 4, 128;" ::: "memory");
@@ -1546,6 +1601,14 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (dgrad && prologue) return set_error(RXB_ERR_INVALID, "conv_gemm: the dgrad epilogue has no A prologue");
   if (dgrad && p.n_total < 64) return set_error(RXB_ERR_INVALID, "conv_gemm: dgrad epilogue needs n_total >= 64");
   const bool wg3 = p.wg_dW != nullptr && p.taps_x == 3 && p.taps_y == 3;
+  if (p.tail.mode != 0) {
+    if (p.wg_dW == nullptr || !(p.tail.mode == 1 || p.tail.mode == 2) || (p.tail.mode == 2) != wg3 || !p.do_stats)
+      return set_error(RXB_ERR_INVALID, "conv_gemm: the fused BatchNorm tail needs the fused weight gradient (mode 1: 1x1, mode 2: 3x3)");
+    if (p.tail.mode == 1 && !(p.tail.W && p.tail.mean && p.tail.rstd && p.tail.dgamma && p.tail.dbeta && p.tail.corrA && p.tail.corrB))
+      return set_error(RXB_ERR_INVALID, "conv_gemm: fused BatchNorm tail (mode 1): null pointer");
+    if (p.tail.mode == 2 && p.ch_sumsq == nullptr)
+      return set_error(RXB_ERR_INVALID, "conv_gemm: fused BatchNorm tail (mode 2) needs ch_sumsq");
+  }
   if (p.wg_dW != nullptr && !wg3 && !(dgrad && p.taps_x == 1 && p.taps_y == 1 && bk == 64 && p.cin <= 128))
     return set_error(RXB_ERR_INVALID, "conv_gemm: the fused weight gradient is for 1x1 data gradients with cin <= 128");
   if (wg3 && !(dgrad && bk == 32 && p.cin == 32 && p.n_total == 128 && p.pad_x == 1 && p.pad_y == 1 &&

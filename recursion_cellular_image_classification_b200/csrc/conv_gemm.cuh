@@ -39,6 +39,26 @@ struct BnPrepArgs {
   float *f_scale, *f_shift, *f_mean, *f_rstd;
 };
 
+// Fused weight gradient (GemmParams::wg_dW) only: the consumer BatchNorm's backward reductions folded into the kernel
+// tail instead of a bn_bwd_finalize launch.  Everything bn_bwd_finalize derives is LINEAR in (sum dy, W.dW), so every
+// CTA contributes its own partial sums: t = sum bf16(W)*dW_cta per channel (the CTA's weight-gradient partial is in
+// its registers on the way out) and s = its sum(dy).
+//   mode 1 (concat BatchNorm, 1x1): dbeta += s, dgamma += q, corrA += scale*s/count, corrB += scale*q/count with
+//          q = rstd*(raw - mean*s), raw = (t - bf16(shift)*s)/bf16(scale)  (degenerate channels: raw = direct sum dy*x)
+//   mode 2 (bottleneck BatchNorm, 3x3): ch_sumsq += t for the non-degenerate channels (direct sum dy*x for the others,
+//          as before); bn_bwd_apply's raw mode turns (ch_sum, ch_sumsq) into the means itself
+struct BnTailArgs {
+  int mode;             // 0: none
+  const float* W;       // fp32 OIHW weights of the fused convolution (mode 1; mode 2 uses the bf16 panel in shared memory)
+  const float* mean;    // fold of the consumer BatchNorm, per N channel (mode 1)
+  const float* rstd;
+  float inv_count;
+  float* dgamma;
+  float* dbeta;
+  float* corrA;
+  float* corrB;
+};
+
 struct GemmParams {
   int B, H, W;      // pixel space shared by A and the output (stride-1 convolutions)
   int n_total;      // valid N (multiple of 32)
@@ -64,6 +84,7 @@ struct GemmParams {
   // gradient, dW[k][c] += sum_p A[p][k] * relu(X[p][c]*e_scale[c] + e_shift[c]) (fold operands rounded to bf16 like
   // the forward prologue), accumulated by the same kernel from the tiles it already holds (conv_gemm.cu, EPI 3)
   float* wg_dW;
+  BnTailArgs tail;      // with wg_dW: the BatchNorm-backward reductions that follow, folded into the tail (mode != 0)
   // ---- filled by launch_conv_gemm
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;

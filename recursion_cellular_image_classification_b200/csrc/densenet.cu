@@ -287,7 +287,7 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
 static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* dOut, int ldD, int cout,
                          const ConvLayer& cv, int Nprime, int taps, int pad, const __nv_bfloat16* X, int ldx,
                          const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st,
-                         float* fused_dW = nullptr) {
+                         float* fused_dW = nullptr, const BnTailArgs* tail = nullptr) {
   GemmParams p = {};
   p.B = B; p.H = H; p.W = W;
   p.n_total = Nprime;
@@ -300,7 +300,8 @@ static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfl
   p.ch_sum = bn.dsum; p.ch_sumsq = bn.dsq;
   p.e_scale = bn.fold.scale; p.e_shift = bn.fold.shift;
   p.e_gamma = n.params + bn.gamma_off; p.e_beta = n.params + bn.beta_off;   // degenerate channels: direct reductions
-  p.wg_dW = fused_dW;   // 1x1: the conv's weight gradient accumulated by the same kernel
+  p.wg_dW = fused_dW;   // the conv's weight gradient accumulated by the same kernel
+  if (tail) p.tail = *tail;   // ... and the BatchNorm-backward reductions that follow it (no bn_bwd_finalize launch)
   return launch_conv_gemm(p, dOut, ldD, n.arena + cv.dgrad_off, out, ldc, 0, X, ldx, cout <= 32 ? 32 : 64, false, st);
 }
 
@@ -434,25 +435,51 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
     if (!fuse3)
       RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, L.Y, kBott, kBott, 3, 1, &L.bn2.fold, n.dZ, kGrowth, kGrowth,
                              n.grads + L.c2.w_off, 0, st));
-    RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
-                          n.dy2, kBott, st, fuse3 ? n.grads + L.c2.w_off : nullptr));
-    RXB_TRY(bn_bwd_finalize(1, n.params + L.c2.w_off, n.grads + L.c2.w_off, kGrowth, 9, L.bn2.dsum, L.bn2.dsq,
-                            L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
-                            n.grads + L.bn2.beta_off, nullptr, nullptr, n.params + L.bn2.gamma_off,
-                            n.params + L.bn2.beta_off, st));
-    RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st));  // dy2 := dY
+    static const bool no_tail = getenv("RXB_DBG_NO_BNTAIL") && atoi(getenv("RXB_DBG_NO_BNTAIL")) != 0;
+    if (fuse3 && !no_tail) {
+      // the kernel leaves sum(dy) and W.dW (every CTA's share) in bn2.dsum / bn2.dsq; bn_bwd_apply derives the means
+      BnTailArgs t2 = {};
+      t2.mode = 2;
+      RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
+                            n.dy2, kBott, st, n.grads + L.c2.w_off, &t2));
+      const BnRawSums raw = {n.params + L.bn2.gamma_off, n.params + L.bn2.beta_off, n.grads + L.bn2.gamma_off,
+                             n.grads + L.bn2.beta_off, 1.f / (float)blk.M};
+      RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st, nullptr, &raw));  // dy2 := dY
+    } else {
+      RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
+                            n.dy2, kBott, st, fuse3 ? n.grads + L.c2.w_off : nullptr));
+      RXB_TRY(bn_bwd_finalize(1, n.params + L.c2.w_off, n.grads + L.c2.w_off, kGrowth, 9, L.bn2.dsum, L.bn2.dsq,
+                              L.bn2.fold, (float)blk.M, kBott, n.grads + L.bn2.gamma_off,
+                              n.grads + L.bn2.beta_off, nullptr, nullptr, n.params + L.bn2.gamma_off,
+                              n.params + L.bn2.beta_off, st));
+      RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st));  // dy2 := dY
+    }
     // 1x1 conv: ONE kernel for its data gradient (into the concat gradient) and its weight gradient - both contract
     // the same dY and X tiles (RXB_DBG_NO_WGFUSE=1: the separate weight-gradient launch, for comparison)
     static const bool no_wgfuse = getenv("RXB_DBG_NO_WGFUSE") && atoi(getenv("RXB_DBG_NO_WGFUSE")) != 0;
     if (no_wgfuse)
       RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, 1, 0, &L.bn1.fold, n.dy2, kBott, kBott,
                              n.grads + L.c1.w_off, 0, st));
-    RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
-                          OUT_G_ACCUM, blk.G, blk.Ctot, st, no_wgfuse ? nullptr : n.grads + L.c1.w_off));
-    RXB_TRY(bn_bwd_finalize(0, n.params + L.c1.w_off, n.grads + L.c1.w_off, kBott, 1, L.bn1.dsum, L.bn1.dsq,
-                            L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
-                            n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, n.params + L.bn1.gamma_off,
-                            n.params + L.bn1.beta_off, st));
+    if (!no_wgfuse && !no_tail) {
+      // ... and bn1's backward reductions (dgamma, dbeta, the lazy correction terms of the concat gradient): every
+      // CTA adds its share in its tail
+      BnTailArgs t1 = {};
+      t1.mode = 1;
+      t1.W = n.params + L.c1.w_off;
+      t1.mean = L.bn1.fold.mean; t1.rstd = L.bn1.fold.rstd;
+      t1.inv_count = 1.f / (float)blk.M;
+      t1.dgamma = n.grads + L.bn1.gamma_off; t1.dbeta = n.grads + L.bn1.beta_off;
+      t1.corrA = blk.corrA; t1.corrB = blk.corrB;
+      RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
+                            OUT_G_ACCUM, blk.G, blk.Ctot, st, n.grads + L.c1.w_off, &t1));
+    } else {
+      RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
+                            OUT_G_ACCUM, blk.G, blk.Ctot, st, no_wgfuse ? nullptr : n.grads + L.c1.w_off));
+      RXB_TRY(bn_bwd_finalize(0, n.params + L.c1.w_off, n.grads + L.c1.w_off, kBott, 1, L.bn1.dsum, L.bn1.dsq,
+                              L.bn1.fold, (float)blk.M, L.Cin, n.grads + L.bn1.gamma_off,
+                              n.grads + L.bn1.beta_off, blk.corrA, blk.corrB, n.params + L.bn1.gamma_off,
+                              n.params + L.bn1.beta_off, st));
+    }
   }
   // exact gradient of the block's input channels
   RXB_TRY(grad_fixup(blk.G, blk.X, blk.Ctot, blk.M, 0, blk.C0, closing.fold.mean, closing.fold.rstd, blk.corrA,

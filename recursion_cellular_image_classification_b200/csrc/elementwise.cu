@@ -393,7 +393,8 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 // A thread keeps ONE channel group (its folded constants live in registers) and walks pixels, four rows in flight.
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(__nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
-                    BnFold f, const float* __restrict__ m1, const float* __restrict__ m2, __nv_bfloat16* dst) {
+                    BnFold f, const float* __restrict__ m1, const float* __restrict__ m2, __nv_bfloat16* dst,
+                    const int raw_on, const BnRawSums raw) {
   pdl_sync();
   const int groups = C >> 3;                         // divides the block size (C = 64 or 128)
   const int cg = threadIdx.x % groups;
@@ -406,6 +407,27 @@ bn_bwd_apply_kernel(__nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long
     load8f(f.rstd + cg * 8, rs);
     load8f(m1 + cg * 8, a1);
     load8f(m2 + cg * 8, a2);
+    if (raw_on) {
+      // a1 = sum dy, a2 = W.dW (or the direct sum dy*x): the means, as bn_bwd_finalize mode 1 derives them
+      float sh[8], ga[8], be[8];
+      load8f(f.shift + cg * 8, sh);
+      load8f(raw.gamma + cg * 8, ga);
+      load8f(raw.beta + cg * 8, be);
+      const bool writer = blockIdx.x == 0 && (int)threadIdx.x < groups;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float s = a1[e];
+        const float es = bf16_round(sc[e]), eh = bf16_round(sh[e]);
+        const float rawv = bn_degenerate(ga[e], be[e]) ? a2[e] : (es != 0.f ? (a2[e] - eh * s) / es : 0.f);
+        const float q = rs[e] * (rawv - mu[e] * s);
+        if (writer) {
+          raw.dgamma[cg * 8 + e] = q;
+          raw.dbeta[cg * 8 + e] = s;
+        }
+        a1[e] = s * raw.inv_count;
+        a2[e] = q * raw.inv_count;
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       cb[e] = -sc[e] * rs[e] * a2[e];
@@ -466,8 +488,10 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restric
 }
 
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st, __nv_bfloat16* dst) {
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst, const BnRawSums* raw) {
   if (C % 8) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+  if (raw != nullptr && (C / 8 > kEwThreads || kEwThreads % (C / 8)))
+    return set_error(RXB_ERR_INVALID, "bn_bwd_apply: raw sums need a channel count that divides the block (C=%d)", C);
   if (dst == nullptr) dst = dy;
   RXB_PROF(st, PROF_EW_BN_APPLY);
   if (C / 8 > kEwThreads || kEwThreads % (C / 8)) {
@@ -475,7 +499,9 @@ int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, 
                       (const __nv_bfloat16*)dy, X, M, C, f, m1, m2, dst));
   } else {
     const int rows_per_block = kEwThreads / (C / 8);
-    RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2, dst));
+    const BnRawSums none = {nullptr, nullptr, nullptr, nullptr, 0.f};
+    RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2, dst,
+                      raw != nullptr ? 1 : 0, raw != nullptr ? *raw : none));
   }
   RXB_LAUNCH_OK();
   return RXB_OK;

@@ -58,8 +58,19 @@ int sum_dyx_from_wdw_launch(const float* W, const float* dW, int K, int C, int t
                             const float* shift, const float* sum_dy, float* out, cudaStream_t st);
 
 // dx[p,c] = scale[c] * (dy[p,c] - m1[c] - xhat[p,c]*m2[c])  (bf16 [M,C] dense), in place on dy, or into dst when given.
+// raw != nullptr (C = 64 or 128 ...: the row-walking kernel): m1 / m2 hold the RAW reductions sum(dy) and W.dW (direct
+// sum(dy*x) for the channels bn_degenerate flags) as the fused 3x3 data+weight-gradient kernel leaves them; the
+// kernel derives the means itself (bn_bwd_finalize's mode-1 arithmetic, no separate launch) and block 0 writes
+// dgamma / dbeta.
+struct BnRawSums {
+  const float* gamma;
+  const float* beta;
+  float* dgamma;
+  float* dbeta;
+  float inv_count;
+};
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st, __nv_bfloat16* dst = nullptr);
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst = nullptr, const BnRawSums* raw = nullptr);
 
 // dst[p, c] = G[p, c0+c] - corrA[c0+c] - xhat[p, c0+c]*corrB[c0+c]   for c in [0, nch)   (bf16 dense out)
 int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long M, int c0, int nch,

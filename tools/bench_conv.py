@@ -79,6 +79,8 @@ if __name__ == "__main__":
         run_dgrad(B, 128, 128, 128, 224, 256, 1, 2)
         run_wgrad(B, 128, 128, 128, 128, 32, 3, 1)
         run_wgrad(B, 128, 128, 224, 256, 128, 1, 1)
+        run_dgrad(B, 128, 128, 32, 128, 128, 3, 0, 1)      # the fused data+weight-gradient launches the step runs
+        run_dgrad(B, 128, 128, 128, 224, 256, 1, 2, 1)
         sys.exit(0)
     B = 64
     for pro, st in itertools.product((0, 1), (0, 1)):

@@ -43,7 +43,8 @@ def rows_of(rep):
 
 
 # order of the launches of `tools/bench_conv.py prof B`
-CONV_ORDER = ["fwd_3x3", "fwd_1x1", "dgrad_3x3_bn", "dgrad_1x1_bn_accum", "wgrad_3x3", "wgrad_1x1"]
+CONV_ORDER = ["fwd_3x3", "fwd_1x1", "dgrad_3x3_bn", "dgrad_1x1_bn_accum", "wgrad_3x3", "wgrad_1x1",
+              "dgrad_3x3_bn_wgrad", "dgrad_1x1_bn_accum_wgrad"]
 
 
 def main():
