@@ -770,6 +770,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // EPI 4 runs the transform one tile AHEAD (software pipelining): tile it+1 is transformed between the TMEM reads
     // of tile it and the wait for tile it's weight-gradient MMAs, so those MMAs never wait for this group to come
     // round again.  (CTAs with degenerate BatchNorm channels need the raw x after tmem_full and keep the simple order.)
+    // EPI 0 statistics without the tensor pipe: each of the group's 128 threads owns one channel PAIR and one half of
+    // the tile's rows, and walks the staged bf16 tile once it is complete (a warp reads one 128-byte row per
+    // instruction: conflict-free under the swizzle); the sums live in registers for the life of the CTA.  Replaces the
+    // Gram + column-sum MMAs, whose operand reads (100 KB per tile) competed with the main loop for shared-memory
+    // bandwidth - the resource these kernels run out of.
+    const bool col_stats = EPI == 0 && p.do_stats && !p.mma_stats;
+    float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
     const bool wg_ahead = wg3 && !any_flag;
     if (wg_ahead && my_tiles > 0) {
       ptx::mbar_wait(&aux->epi_in_full[0][0], 0, 23);
@@ -971,6 +978,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (leader) {
         RXB_TL(2, it, 6);
         ptx::mbar_arrive(&aux->stg_full[sb]);
+      }
+      if constexpr (EPI == 0) {
+        if (col_stats) {
+          const int pr = et & 63, half = et >> 6;          // channel pair, row half
+          const uint8_t* colp = so + (pr >> 5) * (128 * 128) + (pr & 3) * 4;
+          const int j = (pr & 31) >> 2;                      // 16-byte chunk of the 128-byte row
+#pragma unroll 8
+          for (int r = half * 64; r < half * 64 + 64; ++r) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(colp + r * 128 + ((j ^ (r & 7)) << 4));
+            const float lo = bf16_lo(v), hi = bf16_hi(v);
+            cs0 += lo; cs1 += hi;
+            cq0 = fmaf(lo, lo, cq0); cq1 = fmaf(hi, hi, cq1);
+          }
+        }
+      }
+    }
+    if constexpr (EPI == 0) {
+      if (col_stats) {   // s_stat was zeroed at kernel start; the common tail below adds it to the global sums
+        const int c0 = 2 * (et & 63);
+        atomicAdd(&aux->s_stat[0][c0], cs0);
+        atomicAdd(&aux->s_stat[0][c0 + 1], cs1);
+        atomicAdd(&aux->s_stat[1][c0], cq0);
+        atomicAdd(&aux->s_stat[1][c0 + 1], cq1);
       }
     }
     float tail_s = 0.f, tail_dyx = 0.f;   // this CTA's sum(dy) / direct sum(dy*x) of channel n0 + row (fused BatchNorm tail)
@@ -1620,7 +1650,10 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   if (p.e_gamma != nullptr && (p.e_beta == nullptr || p.ch_sumsq == nullptr))
     return set_error(RXB_ERR_INVALID, "conv_gemm: e_gamma needs e_beta and ch_sumsq");
   p.bn = (dgrad || p.n_total >= kMaxBN) ? kMaxBN : p.n_total;
-  p.mma_stats = (dgrad || (p.do_stats && p.bn == kMaxBN)) ? 1 : 0;
+  // statistics of 128-wide store tiles: by default a pass of the epilogue group over the staged tile (col_stats in the
+  // kernel); RXB_DBG_GRAM_STATS=1 restores the Gram / column-sum MMAs on the tensor pipe (kept for comparison)
+  static const int dbg_gram = getenv("RXB_DBG_GRAM_STATS") ? atoi(getenv("RXB_DBG_GRAM_STATS")) : 0;
+  p.mma_stats = (dgrad || (dbg_gram && p.do_stats && p.bn == kMaxBN)) ? 1 : 0;
   static const int dbg_dgrad = getenv("RXB_DBG_DGRAD") ? atoi(getenv("RXB_DBG_DGRAD")) : 0;   // timing experiments only
   if (dgrad && (dbg_dgrad & 1)) { p.mma_stats = 0; p.do_stats = 0; }
   if (dgrad && (dbg_dgrad & 2) && p.out_mode == OUT_G_ACCUM) p.out_mode = OUT_G_WRITE;

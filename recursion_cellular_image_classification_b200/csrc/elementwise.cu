@@ -105,11 +105,21 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
   load8f(shift + cg * 8, sf);
 #pragma unroll
   for (int e = 0; e < 8; ++e) as[e] = aq[e] = 0.f;
+  // packed sign flips: bit 15 / 31 of word e/2 set where the channel's scale is negative
+  uint4 sgn;
+  sgn.x = (sc[0] < 0.f ? 0x8000u : 0u) | (sc[1] < 0.f ? 0x80000000u : 0u);
+  sgn.y = (sc[2] < 0.f ? 0x8000u : 0u) | (sc[3] < 0.f ? 0x80000000u : 0u);
+  sgn.z = (sc[4] < 0.f ? 0x8000u : 0u) | (sc[5] < 0.f ? 0x80000000u : 0u);
+  sgn.w = (sc[6] < 0.f ? 0x8000u : 0u) | (sc[7] < 0.f ? 0x80000000u : 0u);
   for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < total; pix += (long long)gridDim.x * 32) {
     const int ox = (int)(pix % Wo);
     const long long r = pix / Wo;
     const int oy = (int)(r % Ho);
     const int b = (int)(r / Ho);
+    // relu(sc*x+sf) is monotone in x (increasing for sc >= 0, decreasing for sc < 0), so the window maximum of the
+    // activation is the activation of the window's largest sgn*x: the nine taps compare raw values (compare + two
+    // selects per element instead of fma, max, compare and two selects) and the fold runs once.  Equal activations come
+    // only from equal x (first tap wins, as before) or from the ReLU's zero region, where the gradient is zero anyway.
     float best[8];
     int bi[8];
 #pragma unroll
@@ -126,13 +136,13 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
       const int iy = 2 * oy - 1 + k / 3, ix = 2 * ox - 1 + k % 3;
       if (iy < 0 || iy >= Hs || ix < 0 || ix >= Ws) continue;
       float x[8];
-      unpack8(win[k], x);
+      unpack8(make_uint4(win[k].x ^ sgn.x, win[k].y ^ sgn.y, win[k].z ^ sgn.z, win[k].w ^ sgn.w), x);   // sgn*x
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float a = fmaxf(fmaf(x[e], sc[e], sf[e]), 0.f);
-        if (a > best[e]) { best[e] = a; bi[e] = k; }
-      }
+      for (int e = 0; e < 8; ++e)
+        if (x[e] > best[e]) { best[e] = x[e]; bi[e] = k; }
     }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = fmaxf(fmaf(sc[e] < 0.f ? -best[e] : best[e], sc[e], sf[e]), 0.f);
     const uint4 o = pack8(best);
     *reinterpret_cast<uint4*>(out + pix * ld_out + cg * 8) = o;
     float rb[8];
@@ -259,8 +269,41 @@ bn_relu_bwd_to_G_kernel(const void* __restrict__ upstream, const __nv_bfloat16* 
   load8f(f.shift + cg * 8, sf);
 #pragma unroll
   for (int e = 0; e < 8; ++e) { as[e] = aq[e] = 0.f; gk[e] = sc[e] * k; }
-  for (long long pix = (long long)blockIdx.x * ppi + threadIdx.x / groups; pix < total;
-       pix += (long long)gridDim.x * ppi) {
+  const long long pstride = (long long)gridDim.x * ppi;
+  long long pix = (long long)blockIdx.x * ppi + threadIdx.x / groups;
+  // avgpool backward: four pixels in flight per thread (all loads issued before any is used)
+  if (MODE == 0) {
+    const __nv_bfloat16* dP = static_cast<const __nv_bfloat16*>(upstream);
+    for (; pix + 3 * pstride < total; pix += 4 * pstride) {
+      uint4 dv[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pu = pix + u * pstride;
+        const int x_ = (int)(pu % W);
+        const long long r = pu / W;
+        const int y_ = (int)(r % H);
+        const int b = (int)(r / H);
+        const long long pp = ((long long)b * (H >> 1) + (y_ >> 1)) * (W >> 1) + (x_ >> 1);
+        dv[u] = __ldg(reinterpret_cast<const uint4*>(dP + pp * C + cg * 8));
+        xv[u] = ld_stream_v4(X + pu * ldx + cg * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float da[8], x[8], g[8];
+        unpack8(dv[u], da);
+        unpack8(xv[u], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dy = fmaf(x[e], sc[e], sf[e]) > 0.f ? da[e] : 0.f;
+          as[e] += dy;
+          aq[e] = fmaf(dy, x[e], aq[e]);
+          g[e] = gk[e] * dy;
+        }
+        st_stream_v4(G + (pix + u * pstride) * ldx + cg * 8, pack8(g));
+      }
+    }
+  }
+  for (; pix < total; pix += pstride) {
     const int x_ = (int)(pix % W);
     const long long r = pix / W;
     const int y_ = (int)(r % H);
