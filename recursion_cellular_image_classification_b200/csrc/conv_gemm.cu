@@ -317,6 +317,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool dgrad = EPI >= 2;
   constexpr bool wg = EPI >= 3;
   constexpr bool wg3 = EPI == 4;                      // 3x3: one accumulator stage, one epilogue group
+  // EPI 3 splits the sixteen workers like the forward kernel: workers 0-7 turn each activation tile into A' the moment
+  // it lands (the weight-gradient MMAs never wait for an epilogue group to come round), workers 8-15 are two epilogue
+  // groups of four warps.  EPI 2 and EPI 4 use all sixteen workers as epilogue.
+  constexpr bool epi16 = dgrad && EPI != 3;
   constexpr int kWgCol = wg3 ? kAccStride : kGramCol;   // TMEM columns of the weight-gradient accumulators
   constexpr int kSumC = wg3 ? 448 : kSumCol;            // ... and of the running column sums
   constexpr bool narrow = EPI == 1;
@@ -338,7 +342,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int box_w = p.halo == 2 ? tw + p.taps_x - 1 : tw;   // halo 3: the 16-wide M tile already contains its x halo
   const bool xmerge = narrow && p.halo == 3;
   const int out_w = xmerge ? tw - (p.taps_x - 1) : tw;       // valid output columns of a tile
-  const int n_epi_threads = dgrad ? 512 : 256;                 // dgrad: sixteen worker warps ; store: workers 8-15
+  const int n_epi_threads = epi16 ? 512 : 256;                 // EPI 2/4: sixteen worker warps ; stores, EPI 3: workers 8-15
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
@@ -366,7 +370,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::mbar_init(&aux->stats_done, 1);
     if (wg) {
       for (int a = 0; a < 4; ++a) {
-        ptx::mbar_init(&aux->xa_ready[a], 1);
+        ptx::mbar_init(&aux->xa_ready[a], wg3 ? 1 : kXformThreads / 32);   // EPI 3: one arrival per transform warp
         ptx::mbar_init(&aux->wg_done[a][0], 1);
         ptx::mbar_init(&aux->wg_done[a][1], 1);
       }
@@ -724,19 +728,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       ptx::tma_store_wait_all();
     }
-  } else if (dgrad || warp >= kWorker0 + 8) {
+  } else if (epi16 || warp >= kWorker0 + 8) {
     // =============================== epilogue: two groups of warps take alternate tiles (group g owns TMEM accumulator
     // stage g), so one group's TMEM reads overlap the other's arithmetic and shared-memory traffic.  Within a
     // group a warp reads TMEM lanes (warp & 3) * 32 .. ; dgrad has two warps per lane quarter that split the
     // 32-column chunks round-robin.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int first_epi_warp = dgrad ? kWorker0 : kWorker0 + 8;
-    const int warps_per_group = wg3 ? 16 : dgrad ? 8 : 4;   // EPI 4: ONE group of sixteen warps takes every tile
+    const int first_epi_warp = epi16 ? kWorker0 : kWorker0 + 8;
+    const int warps_per_group = wg3 ? 16 : epi16 ? 8 : 4;   // EPI 4: ONE group of sixteen warps takes every tile
     const int e = warp - first_epi_warp;
     const int g2 = e / warps_per_group;                       // epilogue group = accumulator stage
     const int grp = (e - g2 * warps_per_group) >> 2;          // column group inside the epilogue group
-    const int n_grp = wg3 ? 4 : dgrad ? 2 : 1;
+    const int n_grp = wg3 ? 4 : epi16 ? 2 : 1;
     const int group_threads = warps_per_group * 32;
     const int et = threadIdx.x - (first_epi_warp + g2 * warps_per_group) * 32;   // 0..group_threads-1
     const bool leader = et == 0;
@@ -753,14 +757,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int bx = et >> 8;
         transform_box_sw128(tso + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et & 255, p.t, tw,
                             th, tx0, ty0, tb0);
-      } else {
+      } else {   // EPI 3 (only CTAs with degenerate channels come here): 128 threads do the 256-thread pattern twice
         for (int bx = 0; bx < n_boxes; ++bx)
-          transform_box_sw128(tso + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et, p.t, tw, th,
-                              tx0, ty0, tb0);
+          for (int hh = 0; hh < 2; ++hh)
+            transform_box_sw128(tso + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, et + 128 * hh,
+                                p.t, tw, th, tx0, ty0, tb0);
       }
       ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-      if (leader) ptx::mbar_arrive(&aux->xa_ready[tsb]);
+      if (wg3 ? leader : et < kXformThreads / 32) ptx::mbar_arrive(&aux->xa_ready[tsb]);   // the barrier's arrival count
     };
     bool any_flag = false;
     if constexpr (dgrad) {
@@ -803,9 +808,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // fused weight gradient: the activation tile is transformed as soon as it lands (EPI 4: already done, one tile
       // ahead).  CTAs with degenerate BatchNorm channels (rare) need the raw x for their direct reductions and
       // transform after that pass, below.
-      if constexpr (wg) {
-        if (!any_flag && !wg_ahead) wg_transform_tile(it);
-      }
+      // (EPI 3: workers 0-7 transform the tile; EPI 4: done one tile ahead, below)
       if (leader) RXB_TL(2, it, 3);
       // rows whose pixel lies outside the image are clipped by the TMA store; keep them out of the channel sums
       // (a multi-tap filter gives them non-zero accumulators from their in-image neighbours)
@@ -1153,6 +1156,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // =============================== workers 0-7: A-operand transform (pre-activation BatchNorm + ReLU)
+    if constexpr (EPI == 3) {
+      // fused 1x1 weight gradient: every activation tile becomes A' = relu(bn(x)) in place as soon as it lands and is
+      // handed to the MMA warp.  (CTAs with degenerate BatchNorm channels leave it to the owning epilogue group, which
+      // needs the raw x first.)
+      const uint4 any4 = *reinterpret_cast<const uint4*>(aux->e_flag_any4);
+      if ((any4.x | any4.y | any4.z | any4.w) == 0) {
+        const int t = threadIdx.x - kWorker0 * 32;  // 0..kXformThreads-1
+        const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
+        for (int it = 0; it < my_tiles; ++it) {
+          int x0, y0, b0;
+          tile_origin(p.t, blockIdx.x + it * gridDim.x, x0, y0, b0);
+          const int sb = it % p.n_stg;
+          uint8_t* so = st_out + (size_t)sb * stage_tile;
+          ptx::mbar_wait(&aux->epi_in_full[sb][it & 1], (uint32_t)(it / period) & 1u, 25);
+          for (int bx = 0; bx < n_boxes; ++bx)
+            transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, t, p.t, tw, th,
+                                x0, y0, b0);
+          ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&aux->xa_ready[sb]);
+        }
+      }
+    }
     if (PROLOGUE) {
       const int t = threadIdx.x - kWorker0 * 32;  // 0..kXformThreads-1
       int stage = 0;

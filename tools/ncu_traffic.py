@@ -34,7 +34,10 @@ def rows_of(rep):
         for m, key in METRICS:
             if m in hdr:
                 i = hdr.index(m)
-                v = float(r[i].replace(",", "")) if r[i] not in ("", "n/a") else None
+                try:
+                    v = float(r[i].replace(",", "")) if r[i] not in ("", "n/a") else None
+                except ValueError:      # 'no data'
+                    v = None
                 if v is not None and units[i] in UNIT:
                     v *= UNIT[units[i]]
                 d[key] = v
