@@ -105,21 +105,13 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
   load8f(shift + cg * 8, sf);
 #pragma unroll
   for (int e = 0; e < 8; ++e) as[e] = aq[e] = 0.f;
-  // packed sign flips: bit 15 / 31 of word e/2 set where the channel's scale is negative
-  uint4 sgn;
-  sgn.x = (sc[0] < 0.f ? 0x8000u : 0u) | (sc[1] < 0.f ? 0x80000000u : 0u);
-  sgn.y = (sc[2] < 0.f ? 0x8000u : 0u) | (sc[3] < 0.f ? 0x80000000u : 0u);
-  sgn.z = (sc[4] < 0.f ? 0x8000u : 0u) | (sc[5] < 0.f ? 0x80000000u : 0u);
-  sgn.w = (sc[6] < 0.f ? 0x8000u : 0u) | (sc[7] < 0.f ? 0x80000000u : 0u);
   for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < total; pix += (long long)gridDim.x * 32) {
     const int ox = (int)(pix % Wo);
     const long long r = pix / Wo;
     const int oy = (int)(r % Ho);
     const int b = (int)(r / Ho);
-    // relu(sc*x+sf) is monotone in x (increasing for sc >= 0, decreasing for sc < 0), so the window maximum of the
-    // activation is the activation of the window's largest sgn*x: the nine taps compare raw values (compare + two
-    // selects per element instead of fma, max, compare and two selects) and the fold runs once.  Equal activations come
-    // only from equal x (first tap wins, as before) or from the ReLU's zero region, where the gradient is zero anyway.
+    // (measured and rejected, round 2: comparing the raw activations - BN+ReLU is monotone - and folding once after the
+    // window: fewer instructions per tap, but 718 -> 798 us)
     float best[8];
     int bi[8];
 #pragma unroll
@@ -136,13 +128,13 @@ stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs,
       const int iy = 2 * oy - 1 + k / 3, ix = 2 * ox - 1 + k % 3;
       if (iy < 0 || iy >= Hs || ix < 0 || ix >= Ws) continue;
       float x[8];
-      unpack8(make_uint4(win[k].x ^ sgn.x, win[k].y ^ sgn.y, win[k].z ^ sgn.z, win[k].w ^ sgn.w), x);   // sgn*x
+      unpack8(win[k], x);
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (x[e] > best[e]) { best[e] = x[e]; bi[e] = k; }
+      for (int e = 0; e < 8; ++e) {
+        const float a = fmaxf(fmaf(x[e], sc[e], sf[e]), 0.f);
+        if (a > best[e]) { best[e] = a; bi[e] = k; }
+      }
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) best[e] = fmaxf(fmaf(sc[e] < 0.f ? -best[e] : best[e], sc[e], sf[e]), 0.f);
     const uint4 o = pack8(best);
     *reinterpret_cast<uint4*>(out + pix * ld_out + cg * 8) = o;
     float rb[8];
