@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librxb.so")
+# RXB_LIB (development): an alternative build of the same ABI, for same-box A/B timing
+LIB_PATH = os.environ.get("RXB_LIB") or os.path.join(_HERE, "librxb.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

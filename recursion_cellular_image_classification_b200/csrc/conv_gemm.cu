@@ -155,6 +155,29 @@ __device__ __forceinline__ void transform_chunk(uint4* p, const uint32_t (&s)[4]
   v.w = fma_relu_bf16x2(v.w, s[3], h[3]);
   *p = v;
 }
+__device__ __forceinline__ void transform_box_sw128_regs(uint8_t* tile, int rows, const uint32_t (&s)[4],
+                                                         const uint32_t (&h)[4], int t, const PixelTiling& til, int box_w,
+                                                         int box_h, int bx, int by, int bb) {
+  const int j = t & 7;
+  const int tb = 1 << til.tb_log2;
+  const bool interior = bx >= 0 && bx + box_w <= til.W && by >= 0 && by + box_h <= til.H && bb + tb <= til.B;
+  constexpr int kRowsPerIter = kXformThreads / 8;
+  if (interior) {
+#pragma unroll 4
+    for (int row = t >> 3; row < rows; row += kRowsPerIter)
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
+  } else {
+    for (int row = t >> 3; row < rows; row += kRowsPerIter) {
+      const int r2 = row / box_w;
+      const int xi = row - r2 * box_w;
+      const int bi = tb == 1 ? 0 : r2 / box_h;     // halo boxes hold one image: no second division
+      const int yi = r2 - bi * box_h;
+      const int x = bx + xi, y = by + yi, b = bb + bi;
+      if (x < 0 || x >= til.W || y < 0 || y >= til.H || b >= til.B) continue;
+      transform_chunk(reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)), s, h);
+    }
+  }
+}
 __device__ __forceinline__ void transform_box_sw128(uint8_t* tile, int rows, const __nv_bfloat16* sc,
                                                     const __nv_bfloat16* sh, int t, const PixelTiling& til, int box_w,
                                                     int box_h, int bx, int by, int bb) {
@@ -865,20 +888,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint4* xc1 = staging_chunk(so, cw, row, cc + 8);
             const uint4 xa = *xc0, xb = *xc1;
             const uint32_t xin[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            // per-column constants are warp-uniform 16-byte loads - each costs shared-memory wavefronts like a data row,
+            // and they were as much traffic as the tile itself (ncu source view).  The fused variants need none for the
+            // mask (A' > 0: thr = +0, no sign flip) and take the scale as the bf16 pairs the forward prologue used
+            // (one load per eight columns instead of two)
             const uint4* thr4 = reinterpret_cast<const uint4*>(aux->e_thr2 + (cc >> 1));
             const uint4* sgn4 = reinterpret_cast<const uint4*>(aux->e_sgn2 + (cc >> 1));
             const float4* es4 = reinterpret_cast<const float4*>(aux->e_scale + cc);
+            const uint4* esb4 = reinterpret_cast<const uint4*>(aux->s_scale + cc);
             ptx::tmem_ld_wait();
             uint32_t pk[8];
 #pragma unroll
             for (int i4 = 0; i4 < 2; ++i4) {
-              const uint4 th4 = thr4[i4], sg4 = sgn4[i4];
-              const uint32_t thv[4] = {th4.x, th4.y, th4.z, th4.w}, sgv[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
+              uint32_t thv[4] = {0u, 0u, 0u, 0u}, sgv[4] = {0u, 0u, 0u, 0u};
+              if constexpr (!wg) {
+                const uint4 th4 = thr4[i4], sg4 = sgn4[i4];
+                thv[0] = th4.x; thv[1] = th4.y; thv[2] = th4.z; thv[3] = th4.w;
+                sgv[0] = sg4.x; sgv[1] = sg4.y; sgv[2] = sg4.z; sgv[3] = sg4.w;
+              }
               float esv[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
               if (scaled) {
-                const float4 e0 = es4[2 * i4], e1 = es4[2 * i4 + 1];
-                esv[0] = e0.x; esv[1] = e0.y; esv[2] = e0.z; esv[3] = e0.w;
-                esv[4] = e1.x; esv[5] = e1.y; esv[6] = e1.z; esv[7] = e1.w;
+                if constexpr (wg) {
+                  const uint4 eb = esb4[i4];
+                  esv[0] = bf16_lo(eb.x); esv[1] = bf16_hi(eb.x); esv[2] = bf16_lo(eb.y); esv[3] = bf16_hi(eb.y);
+                  esv[4] = bf16_lo(eb.z); esv[5] = bf16_hi(eb.z); esv[6] = bf16_lo(eb.w); esv[7] = bf16_hi(eb.w);
+                } else {
+                  const float4 e0 = es4[2 * i4], e1 = es4[2 * i4 + 1];
+                  esv[0] = e0.x; esv[1] = e0.y; esv[2] = e0.z; esv[3] = e0.w;
+                  esv[4] = e1.x; esv[5] = e1.y; esv[6] = e1.z; esv[7] = e1.w;
+                }
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -1027,8 +1065,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tail_deg = true;
             tail_dyx = dyx;
             if (ch < p.n_total && dyx != 0.f && !(wg && p.tail.mode == 1)) atomicAdd(p.ch_sumsq + ch, dyx);
-          } else if (p.out_mode != OUT_DY) {  // the staged value was es*dy
-            const float es = aux->e_scale[row];
+          } else if (p.out_mode != OUT_DY) {  // the staged value was es*dy (fused variants: es as the bf16 the epilogue applied)
+            const float es = wg ? bf16_round(aux->e_scale[row]) : aux->e_scale[row];
             total = es != 0.f ? total / es : 0.f;
           }
         } else {
@@ -1139,7 +1177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float es = bf16_round(aux->e_scale[row]), eh = bf16_round(aux->e_shift[row]);
           const float raw = tail_deg ? tail_dyx : (es != 0.f ? (t - eh * tail_s) / es : 0.f);
           const float qv = p.tail.rstd[ch] * (raw - p.tail.mean[ch] * tail_s);
-          const float sc = aux->e_scale[row] * p.tail.inv_count;
+          const float sc = es * p.tail.inv_count;   // the scale the staged gradient carried (bf16, like the forward's fold)
           if (qv != 0.f) atomicAdd(p.tail.dgamma + ch, qv);
           if (tail_s != 0.f) atomicAdd(p.tail.dbeta + ch, tail_s);
           if (tail_s != 0.f) atomicAdd(p.tail.corrA + ch, sc * tail_s);
@@ -1164,15 +1202,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if ((any4.x | any4.y | any4.z | any4.w) == 0) {
         const int t = threadIdx.x - kWorker0 * 32;  // 0..kXformThreads-1
         const int period = (p.n_stg & 1) ? 2 * p.n_stg : p.n_stg;
+        // this thread's fold constants (its 16-byte chunk of both 64-channel boxes) stay in registers for the life of
+        // the CTA: re-loading them per tile cost a fifth of the transform's shared-memory wavefronts
+        uint32_t fs[2][4], fh[2][4];
+        for (int bx = 0; bx < 2; ++bx) {
+          const uint4 s4 = *reinterpret_cast<const uint4*>(aux->s_scale + bx * 64 + (t & 7) * 8);
+          const uint4 h4 = *reinterpret_cast<const uint4*>(aux->s_shift + bx * 64 + (t & 7) * 8);
+          fs[bx][0] = s4.x; fs[bx][1] = s4.y; fs[bx][2] = s4.z; fs[bx][3] = s4.w;
+          fh[bx][0] = h4.x; fh[bx][1] = h4.y; fh[bx][2] = h4.z; fh[bx][3] = h4.w;
+        }
         for (int it = 0; it < my_tiles; ++it) {
           int x0, y0, b0;
           tile_origin(p.t, blockIdx.x + it * gridDim.x, x0, y0, b0);
           const int sb = it % p.n_stg;
           uint8_t* so = st_out + (size_t)sb * stage_tile;
           ptx::mbar_wait(&aux->epi_in_full[sb][it & 1], (uint32_t)(it / period) & 1u, 25);
-          for (int bx = 0; bx < n_boxes; ++bx)
-            transform_box_sw128(so + bx * (128 * 128), 128, aux->s_scale + bx * 64, aux->s_shift + bx * 64, t, p.t, tw, th,
-                                x0, y0, b0);
+#pragma unroll
+          for (int bx = 0; bx < 2; ++bx)
+            if (bx < n_boxes)
+              transform_box_sw128_regs(so + bx * (128 * 128), 128, fs[bx], fh[bx], t, p.t, tw, th, x0, y0, b0);
           ptx::fence_proxy_async_smem();     // every writing thread orders its stores before the MMA's async reads
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&aux->xa_ready[sb]);
@@ -1183,6 +1231,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t = threadIdx.x - kWorker0 * 32;  // 0..kXformThreads-1
       int stage = 0;
       uint32_t phase = 0;
+      // (measured and rejected: keeping the fold constants of up to two k-blocks in registers instead of re-loading them
+      // per stage - 3x3 forward 0.293 -> 0.353 ms, the role's registers spill under the kernel's 96-register cap)
       for (int m_tile = blockIdx.x; m_tile < m_tiles; m_tile += gridDim.x) {
         int x0, y0, b0;
         tile_origin(p.t, m_tile, x0, y0, b0);
