@@ -252,11 +252,17 @@ def step_traffic_model(B):
             cin = C + 32 * i
             t["conv_fwd_1x1"] += 2.0 * M * (cin + 128)
             t["conv_fwd_3x3"] += 2.0 * M * (128 + 32)
-            t["grad_fixup"] += 2.0 * M * 32 * 3
-            # (the 3x3 weight gradient rides in the 3x3 data-gradient kernel wherever its 8x16 tiling applies: H > 8)
-            if H <= 8 or os.environ.get("RXB_DBG_NO_WGFUSE3", "0") not in ("", "0"):
+            # (the 3x3 weight gradient rides in the 3x3 data-gradient kernel wherever its 8x16 tiling applies: H > 8; that
+            # kernel then also derives its dOut from the G and X slices of the concat buffers on load - no grad_fixup
+            # pass writing and re-reading a dense dZ)
+            env_on = lambda k: os.environ.get(k, "0") not in ("", "0")
+            fused3 = H > 8 and not env_on("RXB_DBG_NO_WGFUSE3")
+            folded = fused3 and not env_on("RXB_DBG_NO_FIXFOLD") and not env_on("RXB_DBG_NO_BNTAIL")
+            if not fused3:
                 t["conv_wgrad_3x3"] += 2.0 * M * (128 + 32)
-            t["conv_dgrad_3x3"] += 2.0 * M * (32 + 128 + 128)
+            if not folded:
+                t["grad_fixup"] += 2.0 * M * 32 * 3
+            t["conv_dgrad_3x3"] += 2.0 * M * ((64 if folded else 32) + 128 + 128)
             t["bn_bwd_apply"] += 2.0 * M * 128 * 3
             # the 1x1 weight gradient is accumulated by the 1x1 data-gradient kernel from the tiles it already holds
             # (conv_gemm.cu EPI 3) and moves no bytes of its own; RXB_DBG_NO_WGFUSE=1 restores the separate launch

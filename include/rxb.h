@@ -215,6 +215,17 @@ int rxb_conv_dgrad_bn_wgrad(const rxb_conv_desc* d, const void* dOut_bf16, const
                             int ldX, const float* bn_scale, const float* bn_shift, const float* bn_gamma,
                             const float* bn_beta, int out_mode, void* out_bf16, float* sum_dy, float* sum_dyx,
                             float* dW, rxb_stream_t stream);
+/* The 3x3 form of rxb_conv_dgrad_bn_wgrad with dOut NOT given as a dense tensor but derived on load from a DenseNet
+ * block's concat buffers (what a separate element-wise pass would write first):
+ *   dOut[p][c] = G[p][c0+c] + kb[c]*Xc[p][c0+c] + kc[c],  kb = -rstd[c0+c]*corrB[c0+c],  kc = mean*rstd*corrB - corrA
+ * (the exact gradient G - corrA - xhat*corrB of the convolution's 32 output channels under the lazy BatchNorm
+ * backward), evaluated in packed bf16 in shared memory: t = bf16(fma(x, bf16(kb), bf16(kc))), dOut = bf16(g + t).
+ * G, Xc: bf16 [B,H,W,ld]; mean, rstd, corrA, corrB: f32 per concat channel.  d->Cin = 32, d->Cout = 128, 3x3, pad 1. */
+int rxb_conv_dgrad3x3_bn_wgrad_fixup(const rxb_conv_desc* d, const void* G_bf16, const void* Xc_bf16, int ld, int c0,
+                                     const float* mean, const float* rstd, const float* corrA, const float* corrB,
+                                     const void* Wt_bf16, const void* X_bf16, int ldX, const float* bn_scale,
+                                     const float* bn_shift, int out_mode, void* out_bf16, float* sum_dy, float* dW,
+                                     rxb_stream_t stream);
 /* sum_dyx[c] = sum_p dy[p,c]*X[p,c] for the BatchNorm in front of a convolution, from that convolution's weights and
  * finished weight gradient (fp32 OIHW [Cout][Cin][taps]):  with z = bn_scale*x + bn_shift,
  *   sum_p dy*z = sum_{k,tap} W[k][c][tap]*dW[k][c][tap]   (both equal sum_p dL/dA' * A', A' = relu(z)),

@@ -74,6 +74,9 @@ SIGNATURES = {
     "rxb_conv_dgrad_bn_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
+    "rxb_conv_dgrad3x3_bn_wgrad_fixup": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rxb_bn_sum_dyx_from_wdw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "rxb_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -89,6 +89,38 @@ int rxb_conv_dgrad_bn_wgrad(const rxb_conv_desc* d, const void* dOut_bf16, const
                           as_stream(stream));
 }
 
+int rxb_conv_dgrad3x3_bn_wgrad_fixup(const rxb_conv_desc* d, const void* G_bf16, const void* Xc_bf16, int ld, int c0,
+                                     const float* mean, const float* rstd, const float* corrA, const float* corrB,
+                                     const void* Wt_bf16, const void* X_bf16, int ldX, const float* bn_scale,
+                                     const float* bn_shift, int out_mode, void* out_bf16, float* sum_dy, float* dW,
+                                     rxb_stream_t stream) {
+  using namespace rxb;
+  RXB_CHECK_ARG(d && G_bf16 && Xc_bf16 && mean && rstd && corrA && corrB && Wt_bf16 && X_bf16 && bn_scale && bn_shift &&
+                out_bf16 && sum_dy && dW, "rxb_conv_dgrad3x3_bn_wgrad_fixup: null pointer");
+  RXB_CHECK_ARG(d->Cin == 32 && d->Cout == 128 && d->taps_x == 3 && d->taps_y == 3 && d->pad_x == 1 && d->pad_y == 1,
+                "rxb_conv_dgrad3x3_bn_wgrad_fixup: 3x3, pad 1, 32 -> 128 channels");
+  RXB_CHECK_ARG(ld % 8 == 0 && c0 % 8 == 0 && c0 + 32 <= ld && d->ldC >= d->Cout && ldX >= d->Cout,
+                "rxb_conv_dgrad3x3_bn_wgrad_fixup: bad ld / c0");
+  RXB_CHECK_ARG(out_mode >= OUT_DY && out_mode <= OUT_G_ACCUM, "rxb_conv_dgrad3x3_bn_wgrad_fixup: bad out_mode");
+  int rc = rxb_check_device();
+  if (rc) return rc;
+  GemmParams p = {};
+  p.B = d->B; p.H = d->H; p.W = d->W;
+  p.n_total = d->Cout;
+  p.taps_x = p.taps_y = 3; p.pad_x = p.pad_y = 1;
+  p.cin = 32;
+  p.epi_mode = EPI_DGRAD_BN;
+  p.out_mode = out_mode;
+  p.do_stats = 1;
+  p.ch_sum = sum_dy;
+  p.e_scale = bn_scale;
+  p.e_shift = bn_shift;
+  p.wg_dW = dW;
+  p.fix.G = G_bf16; p.fix.X = Xc_bf16; p.fix.ld = ld; p.fix.c0 = c0;
+  p.fix.mean = mean; p.fix.rstd = rstd; p.fix.corrA = corrA; p.fix.corrB = corrB;
+  return launch_conv_gemm(p, nullptr, 32, Wt_bf16, out_bf16, d->ldC, 0, X_bf16, ldX, 32, false, as_stream(stream));
+}
+
 int rxb_bn_sum_dyx_from_wdw(const float* W, const float* dW, int Cout, int Cin, int taps, const float* bn_scale,
                             const float* bn_shift, const float* sum_dy, float* sum_dyx, rxb_stream_t stream) {
   using namespace rxb;

@@ -76,6 +76,9 @@ struct __align__(16) GemmAux {
   uint64_t xa_ready[4];      // [buffer] activation tile transformed to A' = relu(bn(x)) in place (epilogue group -> MMA warp)
   uint64_t wg_done[4][2];    // [buffer][epilogue group] the weight-gradient MMAs have finished reading the A' tile
   uint64_t wg_final;         // every weight-gradient MMA of this CTA has completed
+  uint64_t dz_ready[kMaxStages];   // EPI 4 with FixupArgs: the stage's G box has become dZ (epilogue group -> MMA warp)
+  __align__(16) __nv_bfloat16 f_kb[32];    // ... its per-channel constants as bf16 (dZ = g + fma(x, kb, kc))
+  __align__(16) __nv_bfloat16 f_kc[32];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -144,6 +147,17 @@ __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, in
 __device__ __forceinline__ uint32_t fma_relu_bf16x2(uint32_t x, uint32_t s, uint32_t h) {
   uint32_t d;
   asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t fma_bf16x2(uint32_t x, uint32_t s, uint32_t h) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(s), "r"(h));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
 
@@ -317,7 +331,7 @@ template <int BK, bool PROLOGUE, int EPI>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmX,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
   static_assert(BK == 64 || BK == 32, "BK");
   static_assert(!PROLOGUE || BK == 64, "the in-smem BatchNorm+ReLU transform is written for 128B rows");
   constexpr int ROW_BYTES = BK * 2;
@@ -329,8 +343,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int stages = p.stages;
   const int taps = p.taps_x * p.taps_y;
   const int tps = p.halo == 1 ? p.taps_y : 1;                  // row taps served by one stage of streamed weights
-  const int a_tx = p.rows_a * ROW_BYTES;                       // bytes TMA delivers per A stage
-  const int a_stage = (a_tx + 1023) & ~1023;
+  const int a_tx = p.rows_a * ROW_BYTES;                       // bytes TMA delivers per A box
+  const bool fix = EPI == 4 && p.fix.G != nullptr;             // stage = G box + X box (FixupArgs)
+  const int a_box = (a_tx + 1023) & ~1023;                     // (both boxes of a stage start 1024-byte aligned: the
+  const int a_stage = (fix ? 2 : 1) * a_box;                   //  swizzle pattern follows the absolute address)
   const int b_tap = p.bn * ROW_BYTES;                          // one (tap, k-block) weight tile
   const int b_stage = tps * b_tap;
   const int b_total = p.b_resident ? taps * p.kb_per_tap * b_tap : stages * b_stage;
@@ -398,6 +414,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_init(&aux->wg_done[a][1], 1);
       }
       ptx::mbar_init(&aux->wg_final, 1);
+      for (int s = 0; s < stages; ++s) ptx::mbar_init(&aux->dz_ready[s], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -447,6 +464,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         aux->s_scale[c] = __float2bfloat16_rn(c < p.cin ? p.scale[c] : 0.f);
         aux->s_shift[c] = __float2bfloat16_rn(c < p.cin ? p.shift[c] : 0.f);
       }
+    }
+  }
+  if (fix) {
+    for (int c = threadIdx.x; c < 32; c += kConvThreads) {
+      const int ch = p.fix.c0 + c;
+      const float rb = p.fix.rstd[ch] * p.fix.corrB[ch];
+      aux->f_kb[c] = __float2bfloat16_rn(-rb);
+      aux->f_kc[c] = __float2bfloat16_rn(p.fix.mean[ch] * rb - p.fix.corrA[ch]);
     }
   }
   for (int c = threadIdx.x; c < kMaxBN; c += kConvThreads) {
@@ -528,9 +553,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int gy = p.halo ? 0 : g / p.taps_x, gx = p.halo >= 2 ? 0 : p.halo == 1 ? g : g - gy * p.taps_x;
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             ptx::mbar_wait(&aux->empty[stage], phase ^ 1, 1);
-            ptx::mbar_arrive_expect_tx(&aux->full[stage], a_tx + (p.b_resident ? 0 : b_stage));
+            ptx::mbar_arrive_expect_tx(&aux->full[stage], (fix ? 2 : 1) * a_tx + (p.b_resident ? 0 : b_stage));
             ptx::tma_load_4d(smA + (size_t)stage * a_stage, &tmA, &aux->full[stage], kb * BK, x0 + gx - p.pad_x,
                              y0 + gy - p.pad_y, b0);
+            if (fix)   // the X slice's box behind the G slice's
+              ptx::tma_load_4d(smA + (size_t)stage * a_stage + a_box, &tmA2, &aux->full[stage], kb * BK, x0 + gx - p.pad_x,
+                               y0 + gy - p.pad_y, b0);
             if (!p.b_resident) {
               for (int ty = 0; ty < tps; ++ty) {
                 const int tap = p.halo == 1 ? ty * p.taps_x + gx : g;
@@ -607,7 +635,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t accumulate = 0;
         for (int g = 0; g < groups; ++g) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
-            ptx::mbar_wait(PROLOGUE ? &aux->xform[stage] : &aux->full[stage], phase, 3);
+            ptx::mbar_wait(fix ? &aux->dz_ready[stage] : PROLOGUE ? &aux->xform[stage] : &aux->full[stage], phase, 3);
             ptx::tcgen05_fence_after();
             if (ptx::elect_one()) {
               const uint32_t a_lo = d_lo0 + smA16 + (uint32_t)stage * a_stage16;
@@ -805,6 +833,37 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // bandwidth - the resource these kernels run out of.
     const bool col_stats = EPI == 0 && p.do_stats && !p.mma_stats;
     float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
+    // EPI 4 with FixupArgs: tile t's stage holds the G and X slices' full-halo boxes [box_h][box_w] pixels x 32 channels
+    // (64-byte rows, 64B swizzle); the G box becomes dZ = g + fma(x, kb, kc) in place.  Pixels outside the image keep
+    // the zeros TMA wrote.  One tile ahead, like the A' transform.
+    auto dz_transform_tile = [&](int t) {
+      const int st = t % stages;
+      ptx::mbar_wait(&aux->full[st], (uint32_t)(t / stages) & 1u, 26);
+      uint8_t* gbox = smA + (size_t)st * a_stage;
+      const uint8_t* xbox = gbox + a_box;
+      int tx0, ty0, tb0;
+      tile_origin(p.t, blockIdx.x + t * gridDim.x, tx0, ty0, tb0);
+      const int n_chunks = p.rows_a * 4;                     // 16-byte chunks of a box
+      for (int idx = et; idx < n_chunks; idx += (int)bar_threads) {
+        const int rowb = idx >> 2, j = idx & 3;
+        const int yi = rowb / box_w, xi = rowb - yi * box_w;
+        const int x = tx0 - p.pad_x + xi, y = ty0 - p.pad_y + yi;
+        if (x < 0 || x >= p.t.W || y < 0 || y >= p.t.H) continue;
+        const int off = rowb * 64 + ((j ^ ((rowb >> 1) & 3)) << 4);
+        const uint4 kb4 = *reinterpret_cast<const uint4*>(aux->f_kb + j * 8), kc4 = *reinterpret_cast<const uint4*>(aux->f_kc + j * 8);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xbox + off);
+        uint4 gv = *reinterpret_cast<uint4*>(gbox + off);
+        gv.x = add_bf16x2(gv.x, fma_bf16x2(xv.x, kb4.x, kc4.x));
+        gv.y = add_bf16x2(gv.y, fma_bf16x2(xv.y, kb4.y, kc4.y));
+        gv.z = add_bf16x2(gv.z, fma_bf16x2(xv.z, kb4.z, kc4.z));
+        gv.w = add_bf16x2(gv.w, fma_bf16x2(xv.w, kb4.w, kc4.w));
+        *reinterpret_cast<uint4*>(gbox + off) = gv;
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (leader) ptx::mbar_arrive(&aux->dz_ready[st]);
+    };
+    if (fix && my_tiles > 0) dz_transform_tile(0);
     const bool wg_ahead = wg3 && !any_flag;
     if (wg_ahead && my_tiles > 0) {
       ptx::mbar_wait(&aux->epi_in_full[0][0], 0, 23);
@@ -941,6 +1000,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&aux->tmem_empty[acc]);
+            if (fix && it + 1 < my_tiles) dz_transform_tile(it + 1);   // the next tile's dZ, ahead of its MMAs
             if (wg_ahead && it + 1 < my_tiles) {   // the next tile's transform, ahead of its weight-gradient MMAs
               ptx::mbar_wait(&aux->epi_in_full[(it + 1) % p.n_stg][0], (uint32_t)((it + 1) / p.n_stg) & 1u, 24);
               wg_transform_tile(it + 1);
@@ -1781,9 +1841,22 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   p.rows_a = p.halo ? box_h * box_w : 128;
   if (box_h > 256) return set_error(RXB_ERR_INVALID, "conv_gemm: halo box too tall");
 
-  CUtensorMap tmA, tmB, tmOut, tmX;
-  int rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h, box_w);
-  if (rc) return rc;
+  CUtensorMap tmA, tmB, tmOut, tmX, tmA2;
+  const bool fix = p.fix.G != nullptr;
+  if (fix && !(wg3 && p.halo == 2 && p.fix.X && p.fix.mean && p.fix.rstd && p.fix.corrA && p.fix.corrB &&
+               (p.fix.ld * 2) % 16 == 0 && p.fix.c0 % 8 == 0 && p.fix.c0 + p.cin <= p.fix.ld))
+    return set_error(RXB_ERR_INVALID, "conv_gemm: FixupArgs need the fused 3x3 kernel (EPI 4) and aligned concat slices");
+  int rc;
+  if (fix) {   // the A operand is derived from the two concat slices
+    rc = make_act_tmap(&tmA, static_cast<const __nv_bfloat16*>(p.fix.G) + p.fix.c0, p.t, p.cin, p.fix.ld, bk, box_h, box_w);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmA2, static_cast<const __nv_bfloat16*>(p.fix.X) + p.fix.c0, p.t, p.cin, p.fix.ld, bk, box_h, box_w);
+    if (rc) return rc;
+  } else {
+    rc = make_act_tmap(&tmA, A, p.t, p.cin, ldA, bk, box_h, box_w);
+    if (rc) return rc;
+    tmA2 = tmA;
+  }
   {
     uint64_t dims[3] = {(uint64_t)p.cin, (uint64_t)p.n_total, (uint64_t)taps};
     uint64_t strides[2] = {(uint64_t)p.cin * 2, (uint64_t)p.cin * 2 * p.n_total};
@@ -1805,7 +1878,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
 
   // ---- shared-memory plan: [A stages][B: resident panel or per-stage][staging x n_stg][x tile x 2 (dgrad)][ones][aux]
   const int row_bytes = bk * 2;
-  const long long a_stage = (p.rows_a * row_bytes + 1023) & ~1023;
+  const long long a_stage = (fix ? 2 : 1) * (long long)((p.rows_a * row_bytes + 1023) & ~1023);
   const long long b_tap = (long long)p.bn * row_bytes;
   const long long b_stage = (p.halo == 1 ? p.taps_y : 1) * b_tap;
   const long long b_panel = (long long)taps * p.kb_per_tap * b_tap;
@@ -1839,7 +1912,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     static const int dbg_nx = getenv("RXB_DBG_NX") ? atoi(getenv("RXB_DBG_NX")) : 3;   // 3: odd count, per-group barriers
     p.n_stg = 2;
     if (dbg_nx == 3) {
-      if ((avail - stage_tile) / per_stage >= 3) { p.n_stg = 3; avail -= stage_tile; }
+      // (FixupArgs: a stage is two boxes; two stages = two tiles of prefetch are enough for the small dZ loads)
+      if ((avail - stage_tile) / per_stage >= (fix ? 2 : 3)) { p.n_stg = 3; avail -= stage_tile; }
     } else if (dbg_nx >= 4 && (avail - 2 * stage_tile) / per_stage >= 3) {
       p.n_stg = 4;
       avail -= 2 * stage_tile;
@@ -1879,7 +1953,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     RXB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BK_, PRO_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                  \
     RXB_CUDA(launch_k((conv_gemm_kernel<BK_, PRO_, EPI_>), grid, dim3(kConvThreads), smem, stream, tmA, tmB, tmOut, \
-                      tmX, p));                                                                                 \
+                      tmX, tmA2, p));                                                                           \
   } while (0)
   const int epi = dgrad ? (wg3 ? 4 : p.wg_dW != nullptr ? 3 : 2) : (p.bn < kMaxBN ? 1 : 0);
   if (bk == 64 && prologue) { if (epi == 1) RXB_LAUNCH_GEMM(64, true, 1); else RXB_LAUNCH_GEMM(64, true, 0); }

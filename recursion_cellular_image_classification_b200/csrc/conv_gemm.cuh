@@ -59,6 +59,23 @@ struct BnTailArgs {
   float* corrB;
 };
 
+// EPI 4 only (optional): the exact gradient of the convolution's 32 output channels is not read from a dense tensor
+// but derived from the block's concat buffers on the way in (what grad_fixup_kernel wrote before):
+//   dZ[p][c] = G[p][c0+c] - corrA[c0+c] - xhat[p][c0+c]*corrB[c0+c] = G + kb*X + kc,  kb = -rstd*corrB, kc = mean*rstd*corrB - corrA
+// Every A stage then holds TWO full-halo boxes (the G slice and the X slice, strided 64-byte runs of the concat tensors)
+// and the epilogue group turns the G box into dZ in place one tile ahead (packed bf16: t = fma(x, kb, kc), dZ = g + t;
+// pixels outside the image keep TMA's zeros = the convolution's padding).
+struct FixupArgs {
+  const void* G;        // bf16 concat gradient [B,H,W,ld]
+  const void* X;        // bf16 concat activations [B,H,W,ld]
+  long long ld;
+  int c0;               // first channel of the slice
+  const float* mean;    // per concat channel (index c0 + c)
+  const float* rstd;
+  const float* corrA;
+  const float* corrB;
+};
+
 struct GemmParams {
   int B, H, W;      // pixel space shared by A and the output (stride-1 convolutions)
   int n_total;      // valid N (multiple of 32)
@@ -85,6 +102,7 @@ struct GemmParams {
   // the forward prologue), accumulated by the same kernel from the tiles it already holds (conv_gemm.cu, EPI 3)
   float* wg_dW;
   BnTailArgs tail;      // with wg_dW: the BatchNorm-backward reductions that follow, folded into the tail (mode != 0)
+  FixupArgs fix;        // with wg_dW of a 3x3 (EPI 4): dOut derived from the concat buffers on load (fix.G != nullptr)
   // ---- filled by launch_conv_gemm
   PixelTiling t;
   int n_tiles, bn, kb_per_tap;

@@ -287,7 +287,7 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
 static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* dOut, int ldD, int cout,
                          const ConvLayer& cv, int Nprime, int taps, int pad, const __nv_bfloat16* X, int ldx,
                          const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st,
-                         float* fused_dW = nullptr, const BnTailArgs* tail = nullptr) {
+                         float* fused_dW = nullptr, const BnTailArgs* tail = nullptr, const FixupArgs* fix = nullptr) {
   GemmParams p = {};
   p.B = B; p.H = H; p.W = W;
   p.n_total = Nprime;
@@ -302,6 +302,7 @@ static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfl
   p.e_gamma = n.params + bn.gamma_off; p.e_beta = n.params + bn.beta_off;   // degenerate channels: direct reductions
   p.wg_dW = fused_dW;   // the conv's weight gradient accumulated by the same kernel
   if (tail) p.tail = *tail;   // ... and the BatchNorm-backward reductions that follow it (no bn_bwd_finalize launch)
+  if (fix) p.fix = *fix;      // 3x3: dOut derived from the concat buffers on load (no grad_fixup launch)
   return launch_conv_gemm(p, dOut, ldD, n.arena + cv.dgrad_off, out, ldc, 0, X, ldx, cout <= 32 ? 32 : 64, false, st);
 }
 
@@ -426,22 +427,29 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
   const BnLayer& closing = b < 3 ? n.trans[b].bn : n.bn5;  // its fold covers every channel of the block
   for (int i = (int)blk.layers.size() - 1; i >= 0; --i) {
     DenseLayer& L = blk.layers[i];
-    // exact gradient of this layer's 32 output channels
-    RXB_TRY(grad_fixup(blk.G, blk.X, blk.Ctot, blk.M, L.Cin, kGrowth, closing.fold.mean, closing.fold.rstd, blk.corrA,
-                       blk.corrB, n.dZ, st));
     // 3x3 conv: data gradient fused with ReLU/BN2 backward reductions AND the conv's weight gradient (one kernel: the
     // full-halo dZ box and the Y tile serve both); maps too small for the 8x16 tiling keep the separate launch
     const bool fuse3 = conv_dgrad3x3_wgrad_fusable(c.B, blk.H, blk.W);
+    static const bool no_tail = getenv("RXB_DBG_NO_BNTAIL") && atoi(getenv("RXB_DBG_NO_BNTAIL")) != 0;
+    static const bool no_fixfold = getenv("RXB_DBG_NO_FIXFOLD") && atoi(getenv("RXB_DBG_NO_FIXFOLD")) != 0;
+    // exact gradient of this layer's 32 output channels, dZ = G - corrA - xhat*corrB: derived by the fused 3x3 kernel
+    // itself from the concat buffers on load (FixupArgs), or written densely by grad_fixup for the separate kernels
+    const bool fixfold = fuse3 && !no_tail && !no_fixfold;
+    FixupArgs fx = {};
+    fx.G = blk.G; fx.X = blk.X; fx.ld = blk.Ctot; fx.c0 = L.Cin;
+    fx.mean = closing.fold.mean; fx.rstd = closing.fold.rstd; fx.corrA = blk.corrA; fx.corrB = blk.corrB;
+    if (!fixfold)
+      RXB_TRY(grad_fixup(blk.G, blk.X, blk.Ctot, blk.M, L.Cin, kGrowth, closing.fold.mean, closing.fold.rstd, blk.corrA,
+                         blk.corrB, n.dZ, st));
     if (!fuse3)
       RXB_TRY(conv_wgrad_any(c.B, blk.H, blk.W, L.Y, kBott, kBott, 3, 1, &L.bn2.fold, n.dZ, kGrowth, kGrowth,
                              n.grads + L.c2.w_off, 0, st));
-    static const bool no_tail = getenv("RXB_DBG_NO_BNTAIL") && atoi(getenv("RXB_DBG_NO_BNTAIL")) != 0;
     if (fuse3 && !no_tail) {
       // the kernel leaves sum(dy) and W.dW (every CTA's share) in bn2.dsum / bn2.dsq; bn_bwd_apply derives the means
       BnTailArgs t2 = {};
       t2.mode = 2;
       RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
-                            n.dy2, kBott, st, n.grads + L.c2.w_off, &t2));
+                            n.dy2, kBott, st, n.grads + L.c2.w_off, &t2, fixfold ? &fx : nullptr));
       const BnRawSums raw = {n.params + L.bn2.gamma_off, n.params + L.bn2.beta_off, n.grads + L.bn2.gamma_off,
                              n.grads + L.bn2.beta_off, 1.f / (float)blk.M};
       RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st, nullptr, &raw));  // dy2 := dY

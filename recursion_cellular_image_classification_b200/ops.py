@@ -346,6 +346,25 @@ def conv_dgrad_bn(dOut, Wt, X, bn_scale, bn_shift, Cout, out_mode=OUT_DY, out=No
     return out, s1
 
 
+def conv_dgrad3x3_bn_wgrad_fixup(G, Xc, c0, mean, rstd, corrA, corrB, Wt, X, bn_scale, bn_shift, out=None):
+    """The dense layers' 3x3 data + weight gradient with dOut derived on load from the block's concat buffers:
+    dOut = G[..., c0:c0+32] - corrA - xhat*corrB (packed bf16, see rxb.h).  G, Xc bf16 [B,H,W,ld]; Wt bf16 [3,3,128,32];
+    X bf16 [B,H,W,ldX] (the bottleneck activation).  Returns (out bf16 [B,H,W,128] = dy, sum_dy, dW f32 [32,128,3,3])."""
+    require_gpu()
+    G, Xc, Wt, X = (_cuda(t, torch.bfloat16) for t in (G, Xc, Wt, X))
+    B, H, W, ld = G.shape
+    if out is None:
+        out = torch.zeros(B, H, W, 128, dtype=torch.bfloat16, device=G.device)
+    s1 = torch.zeros(128, dtype=torch.float32, device=G.device)
+    dW = torch.zeros(32, 128, 3, 3, dtype=torch.float32, device=G.device)
+    d = _desc(B, H, W, 32, 32, 128, out.shape[-1], 0, (3, 3), (1, 1), False, True)
+    check(load().rxb_conv_dgrad3x3_bn_wgrad_fixup(ctypes.byref(d), ptr(G), ptr(Xc), ld, c0, ptr(_cuda(mean)), ptr(_cuda(rstd)),
+                                                  ptr(_cuda(corrA)), ptr(_cuda(corrB)), ptr(Wt), ptr(X), X.shape[-1],
+                                                  ptr(_cuda(bn_scale)), ptr(_cuda(bn_shift)), OUT_DY, ptr(out), ptr(s1),
+                                                  ptr(dW), stream_ptr()))
+    return out, s1, dW
+
+
 def bn_sum_dyx_from_wdw(W, dW, bn_scale, bn_shift, sum_dy):
     """sum_p dy*x per input channel of a conv from its fp32 OIHW weights and finished weight gradient."""
     require_gpu()

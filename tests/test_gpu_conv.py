@@ -352,6 +352,46 @@ def test_conv_dgrad3x3_bn_fused_wgrad_repeatable_output(cuda):
             assert (dW - first[1]).abs().max().item() <= 1e-4 * first[1].abs().max().item()
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (2, 12, 20), (3, 32, 32), (16, 128, 128)])
+def test_conv_dgrad3x3_fixup_fold(cuda, B, H, W):
+    """rxb_conv_dgrad3x3_bn_wgrad_fixup: dOut = G - corrA - xhat*corrB derived on load from the concat buffers (two
+    strided full-halo boxes per stage, packed-bf16 transform in shared memory, zero padding kept), then the fused 3x3
+    data + weight gradient.  The reference restates the packed arithmetic: t = bf16(fma(x, bf16(kb), bf16(kc))),
+    dOut = bf16(g + t)."""
+    ld, c0, Cx = 256, 96, 128
+    gen = torch.Generator().manual_seed(B * 19 + H + W)
+    G = _rand_bf16((B, H, W, ld), gen)
+    Xc = _rand_bf16((B, H, W, ld), gen)
+    mean = torch.randn(ld, generator=gen) * 0.2
+    rstd = torch.rand(ld, generator=gen) + 0.5
+    corrA = torch.randn(ld, generator=gen) * 0.05
+    corrB = torch.randn(ld, generator=gen) * 0.05
+    kb = (-rstd * corrB)[c0:c0 + 32].bfloat16().double()
+    kc = (mean * rstd * corrB - corrA)[c0:c0 + 32].bfloat16().double()
+    t = (Xc[..., c0:c0 + 32].double() * kb + kc).to(torch.bfloat16)
+    dz = (G[..., c0:c0 + 32].double() + t.double()).to(torch.bfloat16)
+    exact = G[..., c0:c0 + 32].float() - corrA[c0:c0 + 32] - (Xc[..., c0:c0 + 32].float() - mean[c0:c0 + 32]) * rstd[c0:c0 + 32] * corrB[c0:c0 + 32]
+    assert (dz.float() - exact).abs().max().item() <= 2e-2 * exact.abs().max().item()      # the packed form is the fix-up
+    Wt = _rand_bf16((Cx, 32, 3, 3), gen, scale=(32 * 9) ** -0.5)
+    X = _rand_bf16((B, H, W, Cx), gen)
+    s = torch.rand(Cx, generator=gen) + 0.5
+    h = torch.randn(Cx, generator=gen) * 0.3
+    acc = _ref_conv(dz, Wt, 1)
+    a_prime = torch.relu(X.float() * s.bfloat16().float() + h.bfloat16().float()).to(torch.bfloat16).float()
+    dy = acc * (a_prime > 0)
+    w = torch.zeros(32, Cx, 3, 3, dtype=torch.double, requires_grad=True)
+    F.conv2d(a_prime.double().permute(0, 3, 1, 2), w, padding=1).backward(dz.double().permute(0, 3, 1, 2))
+    out, s1, dW = ops.conv_dgrad3x3_bn_wgrad_fixup(G.to(cuda), Xc.to(cuda), c0, mean.to(cuda), rstd.to(cuda), corrA.to(cuda),
+                                                   corrB.to(cuda), _tap_major(Wt).to(cuda), X.to(cuda), s.to(cuda), h.to(cuda))
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - dy).abs().max().item()
+    assert err <= 2e-2 * dy.abs().max().item(), "max err %g vs %g" % (err, dy.abs().max().item())
+    d64 = dy.double().reshape(-1, Cx)
+    np.testing.assert_allclose(s1.cpu().numpy(), d64.sum(0).numpy(), rtol=4e-3, atol=4e-3 * d64.abs().sum(0).max().item())
+    werr = (dW.cpu().double() - w.grad).abs().max().item()
+    assert werr <= 2e-3 * w.grad.abs().max().item() + 1e-3, "dW max err %g vs %g" % (werr, w.grad.abs().max().item())
+
+
 @pytest.mark.parametrize("k,Cin,Cout", [(1, 96, 128), (3, 128, 32)])
 def test_bn_backward_sums_from_wdw(cuda, k, Cin, Cout):
     """The BatchNorm-backward reduction sum(dy*x) recovered from W.dW equals the direct reduction: forward
