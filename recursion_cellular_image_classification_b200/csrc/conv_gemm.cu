@@ -100,6 +100,7 @@ PixelTiling make_tiling(int B, int H, int W) {
   t.tiles_y = ceil_div(H, 1 << thl);
   t.tiles_b = ceil_div(B, 1 << tbl);
   t.x_step = 1 << twl;
+  t.rev = 0;
   return t;
 }
 
@@ -122,10 +123,12 @@ PixelTiling make_tiling_tall(int B, int H, int W) {
   t.tiles_y = ceil_div(H, 1 << thl);
   t.tiles_b = ceil_div(B, 1 << tbl);
   t.x_step = 1 << twl;
+  t.rev = 0;
   return t;
 }
 
 __device__ __forceinline__ void tile_origin(const PixelTiling& t, int m_tile, int& x0, int& y0, int& b0) {
+  if (t.rev) m_tile = t.rev - 1 - m_tile;
   const int tx = m_tile % t.tiles_x;
   const int rest = m_tile / t.tiles_x;
   const int ty = rest % t.tiles_y;
@@ -1887,6 +1890,7 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   const long long fixed = (long long)sizeof(GemmAux) + 1024 /*alignment*/ + 1024 /*ones*/ + (dgrad ? stage_tile : 0);
   const long long budget = 227 * 1024;
   const int m_tiles = p.t.tiles_x * p.t.tiles_y * p.t.tiles_b;
+  p.t.rev = p.reverse ? m_tiles : 0;
   int gx = num_sms() / p.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > m_tiles) gx = m_tiles;

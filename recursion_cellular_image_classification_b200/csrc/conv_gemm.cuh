@@ -13,6 +13,7 @@ struct PixelTiling {
   int tw_log2, th_log2, tb_log2;
   int tiles_x, tiles_y, tiles_b;
   int x_step;   // distance between tile origins in x: 1 << tw_log2, or tw - (taps_x - 1) when the M tile carries its x halo
+  int rev;      // 0, or the tile count: tiles are then visited from the last to the first (GemmParams::reverse)
 };
 PixelTiling make_tiling(int B, int H, int W);       // wide tiles (tw as large as possible)
 PixelTiling make_tiling_tall(int B, int H, int W);  // tw <= 8: tall tiles for the row-halo tap reuse
@@ -101,6 +102,8 @@ struct GemmParams {
   // gradient, dW[k][c] += sum_p A[p][k] * relu(X[p][c]*e_scale[c] + e_shift[c]) (fold operands rounded to bf16 like
   // the forward prologue), accumulated by the same kernel from the tiles it already holds (conv_gemm.cu, EPI 3)
   float* wg_dW;
+  int reverse;          // 1: walk the pixel tiles from the last to the first.  Consecutive kernels of the executor alternate
+                        // direction, so each starts on the part of its input the previous one touched last (still in L2)
   BnTailArgs tail;      // with wg_dW: the BatchNorm-backward reductions that follow, folded into the tail (mode != 0)
   FixupArgs fix;        // with wg_dW of a 3x3 (EPI 4): dOut derived from the concat buffers on load (fix.G != nullptr)
   // ---- filled by launch_conv_gemm

@@ -266,8 +266,10 @@ static int check_cfg(const rxb_dn121_config* c) {
 // ---------------------------------------------------------------------------------------------- helpers
 static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* A, int ldA, int cin,
                       const ConvLayer& cv, int Cout, int taps, int pad, const BnFold* pro, __nv_bfloat16* out,
-                      int ldc, int c_off, float* ssum, float* ssq, cudaStream_t st, const BnPrepArgs* fused = nullptr) {
+                      int ldc, int c_off, float* ssum, float* ssq, cudaStream_t st, const BnPrepArgs* fused = nullptr,
+                      int reverse = 0) {
   GemmParams p = {};
+  p.reverse = reverse;
   p.B = B; p.H = H; p.W = W;
   p.n_total = Cout;
   p.taps_x = p.taps_y = taps;
@@ -287,8 +289,10 @@ static int conv_store(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat
 static int conv_dgrad_bn(const rxb_dn121& n, int B, int H, int W, const __nv_bfloat16* dOut, int ldD, int cout,
                          const ConvLayer& cv, int Nprime, int taps, int pad, const __nv_bfloat16* X, int ldx,
                          const BnLayer& bn, int out_mode, __nv_bfloat16* out, int ldc, cudaStream_t st,
-                         float* fused_dW = nullptr, const BnTailArgs* tail = nullptr, const FixupArgs* fix = nullptr) {
+                         float* fused_dW = nullptr, const BnTailArgs* tail = nullptr, const FixupArgs* fix = nullptr,
+                         int reverse = 0) {
   GemmParams p = {};
+  p.reverse = reverse;
   p.B = B; p.H = H; p.W = W;
   p.n_total = Nprime;
   p.taps_x = p.taps_y = taps;
@@ -348,6 +352,11 @@ static int prep(const rxb_dn121& n, const BnLayer& bn, const float* sum, const f
                  n.buffers + bn.rv_off, n.cfg.bn_eps, n.cfg.bn_momentum, training, bn.C, bn.fold, st);
 }
 
+static bool snake_on() {
+  static const bool off = getenv("RXB_DBG_NO_SNAKE") && atoi(getenv("RXB_DBG_NO_SNAKE")) != 0;
+  return !off;
+}
+
 #define RXB_TRY(expr)          \
   do {                         \
     int rc__ = (expr);         \
@@ -383,8 +392,10 @@ static int forward(rxb_dn121& n, const void* input, int training, cudaStream_t s
       RXB_TRY(conv_store(n, c.B, blk.H, blk.W, blk.X, blk.Ctot, L.Cin, L.c1, kBott, 1, 0, &L.bn1.fold, L.Y, kBott, 0,
                          stats ? L.ysum : nullptr, stats ? L.ysq : nullptr, st, &p1));
       const BnPrepArgs p2 = fused_prep(n, L.bn2, L.ysum, L.ysq, (float)blk.M, training);
+      // (the 3x3 walks its tiles backwards: it starts on the end of Y, which the 1x1 wrote last and L2 still holds, and
+      // ends on the start of the concat buffer, where the next 1x1 begins - RXB_DBG_NO_SNAKE=1 disables)
       RXB_TRY(conv_store(n, c.B, blk.H, blk.W, L.Y, kBott, kBott, L.c2, kGrowth, 3, 1, &L.bn2.fold, blk.X, blk.Ctot,
-                         L.Cin, stats ? blk.xsum : nullptr, stats ? blk.xsq : nullptr, st, &p2));
+                         L.Cin, stats ? blk.xsum : nullptr, stats ? blk.xsq : nullptr, st, &p2, snake_on() ? 1 : 0));
     }
     if (b < 3) {
       Transition& t = n.trans[b];
@@ -425,6 +436,9 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
   const rxb_dn121_config& c = n.cfg;
   Block& blk = n.blocks[b];
   const BnLayer& closing = b < 3 ? n.trans[b].bn : n.bn5;  // its fold covers every channel of the block
+  // consecutive kernels walk their rows in alternating directions: each starts on what the previous one touched last
+  int dir = 0;
+  auto next_dir = [&]() { const int d = dir; if (snake_on()) dir ^= 1; return d; };
   for (int i = (int)blk.layers.size() - 1; i >= 0; --i) {
     DenseLayer& L = blk.layers[i];
     // 3x3 conv: data gradient fused with ReLU/BN2 backward reductions AND the conv's weight gradient (one kernel: the
@@ -449,10 +463,10 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
       BnTailArgs t2 = {};
       t2.mode = 2;
       RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
-                            n.dy2, kBott, st, n.grads + L.c2.w_off, &t2, fixfold ? &fx : nullptr));
+                            n.dy2, kBott, st, n.grads + L.c2.w_off, &t2, fixfold ? &fx : nullptr, next_dir()));
       const BnRawSums raw = {n.params + L.bn2.gamma_off, n.params + L.bn2.beta_off, n.grads + L.bn2.gamma_off,
                              n.grads + L.bn2.beta_off, 1.f / (float)blk.M};
-      RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st, nullptr, &raw));  // dy2 := dY
+      RXB_TRY(bn_bwd_apply(n.dy2, L.Y, blk.M, kBott, L.bn2.fold, L.bn2.dsum, L.bn2.dsq, st, nullptr, &raw, next_dir()));  // dy2 := dY
     } else {
       RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dZ, kGrowth, kGrowth, L.c2, kBott, 3, 1, L.Y, kBott, L.bn2, OUT_DY,
                             n.dy2, kBott, st, fuse3 ? n.grads + L.c2.w_off : nullptr));
@@ -479,7 +493,7 @@ static int backward_block(rxb_dn121& n, int b, const void* input, cudaStream_t s
       t1.dgamma = n.grads + L.bn1.gamma_off; t1.dbeta = n.grads + L.bn1.beta_off;
       t1.corrA = blk.corrA; t1.corrB = blk.corrB;
       RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
-                            OUT_G_ACCUM, blk.G, blk.Ctot, st, n.grads + L.c1.w_off, &t1));
+                            OUT_G_ACCUM, blk.G, blk.Ctot, st, n.grads + L.c1.w_off, &t1, nullptr, next_dir()));
     } else {
       RXB_TRY(conv_dgrad_bn(n, c.B, blk.H, blk.W, n.dy2, kBott, kBott, L.c1, L.Cin, 1, 0, blk.X, blk.Ctot, L.bn1,
                             OUT_G_ACCUM, blk.G, blk.Ctot, st, no_wgfuse ? nullptr : n.grads + L.c1.w_off));

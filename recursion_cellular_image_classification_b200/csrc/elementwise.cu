@@ -429,7 +429,7 @@ int bn_bwd_finalize(int mode, const float* W, const float* dW, int K, int taps, 
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(__nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long long M, int C,
                     BnFold f, const float* __restrict__ m1, const float* __restrict__ m2, __nv_bfloat16* dst,
-                    const int raw_on, const BnRawSums raw) {
+                    const int raw_on, const BnRawSums raw, const int reverse) {
   pdl_sync();
   const int groups = C >> 3;                         // divides the block size (C = 64 or 128)
   const int cg = threadIdx.x % groups;
@@ -471,30 +471,35 @@ bn_bwd_apply_kernel(__nv_bfloat16* dy, const __nv_bfloat16* __restrict__ X, long
   }
   const long long stride = (long long)gridDim.x * rows_per_block;
   long long row = (long long)blockIdx.x * rows_per_block + threadIdx.x / groups;
+  // (reverse: the same rows, visited from the last to the first)
+  const long long rbase = reverse ? M - 1 : 0, rsign = reverse ? -1 : 1;
   for (; row + 3 * stride < M; row += 4 * stride) {
     uint4 dv[4], xv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      dv[u] = *reinterpret_cast<const uint4*>(dy + (row + u * stride) * C + cg * 8);   // in place: coherent load
-      xv[u] = ld_stream_v4(X + (row + u * stride) * C + cg * 8);
+      const long long r = rbase + rsign * (row + u * stride);
+      dv[u] = *reinterpret_cast<const uint4*>(dy + r * C + cg * 8);   // in place: coherent load
+      xv[u] = ld_stream_v4(X + r * C + cg * 8);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      const long long r = rbase + rsign * (row + u * stride);
       float d[8], x[8];
       unpack8(dv[u], d);
       unpack8(xv[u], x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
-      st_stream_v4(dst + (row + u * stride) * C + cg * 8, pack8(d));
+      st_stream_v4(dst + r * C + cg * 8, pack8(d));
     }
   }
   for (; row < M; row += stride) {
+    const long long r = rbase + rsign * row;
     float d[8], x[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + row * C + cg * 8), d);
-    unpack8(ld_stream_v4(X + row * C + cg * 8), x);
+    unpack8(*reinterpret_cast<const uint4*>(dy + r * C + cg * 8), d);
+    unpack8(ld_stream_v4(X + r * C + cg * 8), x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) d[e] = fmaf(sc[e], d[e], fmaf(cb[e], x[e], cc[e]));
-    st_stream_v4(dst + row * C + cg * 8, pack8(d));
+    st_stream_v4(dst + r * C + cg * 8, pack8(d));
   }
 }
 
@@ -523,7 +528,7 @@ bn_bwd_apply_wide_kernel(const __nv_bfloat16* dy, const __nv_bfloat16* __restric
 }
 
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st, __nv_bfloat16* dst, const BnRawSums* raw) {
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst, const BnRawSums* raw, int reverse) {
   if (C % 8) return set_error(RXB_ERR_INVALID, "bn_bwd_apply: C=%d must be a multiple of 8", C);
   if (raw != nullptr && (C / 8 > kEwThreads || kEwThreads % (C / 8)))
     return set_error(RXB_ERR_INVALID, "bn_bwd_apply: raw sums need a channel count that divides the block (C=%d)", C);
@@ -536,7 +541,7 @@ int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, 
     const int rows_per_block = kEwThreads / (C / 8);
     const BnRawSums none = {nullptr, nullptr, nullptr, nullptr, 0.f};
     RXB_CUDA(launch_k(bn_bwd_apply_kernel, dim3(ew_grid(M, rows_per_block * 4)), dim3(kEwThreads), (size_t)(0), st, dy, X, M, C, f, m1, m2, dst,
-                      raw != nullptr ? 1 : 0, raw != nullptr ? *raw : none));
+                      raw != nullptr ? 1 : 0, raw != nullptr ? *raw : none, reverse));
   }
   RXB_LAUNCH_OK();
   return RXB_OK;

@@ -70,7 +70,8 @@ struct BnRawSums {
   float inv_count;
 };
 int bn_bwd_apply(__nv_bfloat16* dy, const __nv_bfloat16* X, long long M, int C, BnFold f, const float* m1,
-                 const float* m2, cudaStream_t st, __nv_bfloat16* dst = nullptr, const BnRawSums* raw = nullptr);
+                 const float* m2, cudaStream_t st, __nv_bfloat16* dst = nullptr, const BnRawSums* raw = nullptr,
+                 int reverse = 0);   // reverse: rows from the last to the first (the executor alternates directions)
 
 // dst[p, c] = G[p, c0+c] - corrA[c0+c] - xhat[p, c0+c]*corrB[c0+c]   for c in [0, nch)   (bf16 dense out)
 int grad_fixup(const __nv_bfloat16* G, const __nv_bfloat16* X, int ld, long long M, int c0, int nch,
