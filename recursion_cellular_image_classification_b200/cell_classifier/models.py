@@ -270,7 +270,7 @@ class DenseNet121(torch.nn.Module):
     def train_step(self, xs, target, global_batch=None, phase=-1, loss_out=None, graph=False):
         """forward + CrossEntropy(mean over global_batch) + backward into self.flat.grad.  Returns the
         device scalar holding this rank's share of the loss.
-        graph=True replays the phase from a CUDA graph: the executor enqueues ~620 kernels per step with no host
+        graph=True replays the phase from a CUDA graph: the executor enqueues ~340 kernels per step with no host
         synchronisation, so a phase is captured once per (buffers, phase, global batch) — on its second use, the first
         one runs eagerly and loads every kernel — and replayed afterwards (about 4 % of the step at batch 128).  The
         inputs must then sit at fixed addresses: use `static_buffers()`; other tensors are copied into them."""
