@@ -90,7 +90,9 @@ int bn_prep(const float* sum, const float* sumsq, float count, const float* gamm
 }
 
 // ------------------------------------------------------------------------------------------------ stem pool fwd
-__global__ void __launch_bounds__(kEwThreads)
+// (three blocks per SM: 102 -> 80 registers with a few spills, 721 -> 580 us; four blocks spill too much, and the same
+// cap slowed stem_pool_bwd 578 -> 692 us and changed nothing for bn_relu_bwd_to_G)
+__global__ void __launch_bounds__(kEwThreads, 3)
 stem_bn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ S0, int B, int Hs, int Ws,
                             const float* __restrict__ scale, const float* __restrict__ shift,
                             __nv_bfloat16* __restrict__ out, int ld_out, uint8_t* __restrict__ idx,
