@@ -406,7 +406,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&aux->epi_in_full[a][1], 1);
       ptx::mbar_init(&aux->epi_in_empty[a], p.mma_stats ? 2 : 1);   // dgrad: store warp has read it + stats MMAs done
       ptx::mbar_init(&aux->stg_full[a], 1);
-      ptx::mbar_init(&aux->stg_free[a], p.mma_stats ? 2 : 1);   // store warp has read it (+ statistics MMAs done)
+      // store warp has read it (+ statistics MMAs done; + shared-buffer mode: the owning group's column pass is done)
+      ptx::mbar_init(&aux->stg_free[a], (p.mma_stats || (!dgrad && p.n_stg == 1 && EPI == 0 && p.do_stats)) ? 2 : 1);
     }
     ptx::mbar_init(&aux->b_full, 1);
     ptx::mbar_init(&aux->stats_done, 1);
@@ -778,7 +779,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ptx::tma_store_commit();
         ptx::tma_store_wait_read();
-        ptx::mbar_arrive(dgrad ? &aux->epi_in_empty[sb] : &aux->stg_free[sb]);
+        // (shared staging buffer, n_stg == 1: the release goes to the barrier of the group that stages the NEXT tile)
+        ptx::mbar_arrive(dgrad ? &aux->epi_in_empty[sb] : &aux->stg_free[p.n_stg == 1 ? ((it + 1) & 1) : sb]);
       }
       ptx::tma_store_wait_all();
     }
@@ -885,7 +887,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // the staging buffer is free once the TMA store issued n_stg tiles ago has read it and (statistics on the
       // tensor pipe) the MMAs over it have completed; dgrad stages in place over the activation tile it owns
       // (stores always have TWO staging buffers, one per epilogue group, so a group waits on every phase of its buffer)
-      if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
+      if (!dgrad && p.n_stg == 1) {
+        // ONE staging buffer shared by the two groups (32 KB more for the operand pipeline): tile it waits for the
+        // release of tile it-1, which arrives on this group's own barrier - its ((it-1)/2)-th phase
+        if (it > 0) ptx::mbar_wait(&aux->stg_free[g2], (uint32_t)((it - 1) >> 1) & 1u, 10);
+      } else if (!dgrad && use > 0) ptx::mbar_wait(&aux->stg_free[sb], (use - 1) & 1, 10);
       if (leader) RXB_TL(2, it, 2);
       // this group's own barrier of the buffer, used (it / period) times before; period = lcm(n_stg, 2) tiles
       const int period = (wg3 || !(p.n_stg & 1)) ? p.n_stg : 2 * p.n_stg;
@@ -1094,6 +1100,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float lo = bf16_lo(v), hi = bf16_hi(v);
             cs0 += lo; cs1 += hi;
             cq0 = fmaf(lo, lo, cq0); cq1 = fmaf(hi, hi, cq1);
+          }
+          if (p.n_stg == 1) {   // shared buffer: the other group may overwrite it only after this pass
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+            if (leader) ptx::mbar_arrive(&aux->stg_free[(it + 1) & 1]);
           }
         }
       }
@@ -1926,6 +1936,17 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
     // one staging buffer per epilogue group (the groups alternate tiles; a shared buffer would make their parity
     // waits ambiguous)
     p.n_stg = 2;
+    // Forward 1x1 with more than 128 input channels: ONE 32 KB staging buffer shared by the two groups - two more
+    // operand stages in flight for a kernel bound by bytes in flight (per-group release barriers keep the waits
+    // unambiguous).  Measured per shape: Cin 224 0.339 -> 0.327 ms, 256 (64x64) -3 %, 992 -5 %; with 64 input
+    // channels the tile is too short and the groups wait for each other (0.193 -> 0.266 ms), hence the threshold.
+    // RXB_DBG_STG1=0 disables, =2 forces it for every Cin.
+    static const int dbg_stg1 = getenv("RXB_DBG_STG1") ? atoi(getenv("RXB_DBG_STG1")) : 1;
+    if (dbg_stg1 && (p.kb_per_tap >= 3 || dbg_stg1 == 2) && prologue && p.bn == kMaxBN && bk == 64 && p.taps_x == 1 &&
+        p.taps_y == 1 && !p.mma_stats) {
+      p.n_stg = 1;
+      avail += stage_tile;
+    }
   }
   long long stages = avail / per_stage;
   if (stages > kMaxStages) stages = kMaxStages;
