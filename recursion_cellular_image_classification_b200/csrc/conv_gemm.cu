@@ -837,6 +837,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Gram + column-sum MMAs, whose operand reads (100 KB per tile) competed with the main loop for shared-memory
     // bandwidth - the resource these kernels run out of.
     const bool col_stats = EPI == 0 && p.do_stats && !p.mma_stats;
+    // EPI 1 (bn = 32 or 64): the same pass instead of warp-shuffle column sums - a shuffle costs a shared-memory
+    // wavefront like a load, and the butterfly needed 124 of them per warp and tile against 14-32 row loads
+    const bool col_narrow = EPI == 1 && p.do_stats && !p.mma_stats && p.col_narrow;
     float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
     // EPI 4 with FixupArgs: tile t's stage holds the G and X slices' full-halo boxes [box_h][box_w] pixels x 32 channels
     // (64-byte rows, 64B swizzle); the G box becomes dZ = g + fma(x, kb, kc) in place.  Pixels outside the image keep
@@ -1055,7 +1058,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *staging_chunk(so, cw, srow, c + 8 * i) =
                   make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
           }
-          if (narrow && p.do_stats && !p.mma_stats) {
+          if (narrow && p.do_stats && !p.mma_stats && !col_narrow) {
             // sums, then squares re-derived from the packed values: the two 32-value arrays are never live together
             float v[32];
 #pragma unroll
@@ -1106,6 +1109,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (leader) ptx::mbar_arrive(&aux->stg_free[(it + 1) & 1]);
           }
         }
+      }
+      if constexpr (EPI == 1) {
+        if (col_narrow) {
+          const int n_rows = xmerge ? th * out_w : 128;        // staged rows of a tile (every one rewritten per tile)
+          const int wq = et >> 5;                                 // warp of the group
+          if (cw == 64) {
+            // 64 channels = 32 pairs: lane = pair, a warp reads one 128-byte row per instruction, warps split the rows
+            const uint8_t* colp = so + (lane & 3) * 4;
+            const int j = lane >> 2;
+            for (int r = wq; r < n_rows; r += 4) {
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(colp + r * 128 + ((j ^ (r & 7)) << 4));
+              const float lo = bf16_lo(v), hi = bf16_hi(v);
+              cs0 += lo; cs1 += hi;
+              cq0 = fmaf(lo, lo, cq0); cq1 = fmaf(hi, hi, cq1);
+            }
+          } else {
+            // 32 channels = 16 pairs: lanes 0-15 read an even row, lanes 16-31 the odd row after it (64-byte rows: the
+            // two halves of one 128-byte bank line), warps split the row pairs
+            const int pr = lane & 15, odd = lane >> 4;
+            const uint8_t* colp = so + (pr & 3) * 4;
+            const int j = pr >> 2;
+            for (int q2 = wq; 2 * q2 + odd < n_rows; q2 += 4) {
+              const int r = 2 * q2 + odd;
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(colp + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+              const float lo = bf16_lo(v), hi = bf16_hi(v);
+              cs0 += lo; cs1 += hi;
+              cq0 = fmaf(lo, lo, cq0); cq1 = fmaf(hi, hi, cq1);
+            }
+          }
+        }
+      }
+    }
+    if constexpr (EPI == 1) {
+      if (col_narrow) {   // (s_stat was zeroed at kernel start; the common tail adds it to the global sums)
+        const int c0 = 2 * (cw == 64 ? lane : (lane & 15));
+        atomicAdd(&aux->s_stat[0][c0], cs0);
+        atomicAdd(&aux->s_stat[0][c0 + 1], cs1);
+        atomicAdd(&aux->s_stat[1][c0], cq0);
+        atomicAdd(&aux->s_stat[1][c0 + 1], cq1);
       }
     }
     if constexpr (EPI == 0) {
@@ -1811,6 +1853,8 @@ int launch_conv_gemm(GemmParams p, const void* A, long long ldA, const void* Wt,
   // ~4k cycles per tile (profiles/r02_timelines.log)
   static const int dbg_nacc = getenv("RXB_DBG_NACC") ? atoi(getenv("RXB_DBG_NACC")) : 4;
   p.n_acc = (!dgrad && p.bn < kMaxBN && !p.mma_stats && dbg_nacc == 4) ? 4 : 2;
+  static const int dbg_shfl = getenv("RXB_DBG_SHFL_STATS") ? atoi(getenv("RXB_DBG_SHFL_STATS")) : 0;
+  p.col_narrow = (!dgrad && !dbg_shfl && (p.bn == 32 || p.bn == 64)) ? 1 : 0;
   if (wg3) p.n_acc = 1;   // TMEM: 128 accumulator + 288 weight-gradient + 16 sum columns
   p.n_tiles = ceil_div(p.n_total, p.bn);
   p.kb_per_tap = ceil_div(p.cin, bk);

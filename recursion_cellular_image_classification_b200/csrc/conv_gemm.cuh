@@ -119,6 +119,8 @@ struct GemmParams {
   int b_resident;   // 1: the whole [taps][k-blocks] weight panel of the N tile is loaded once per CTA
   int n_acc;        // TMEM accumulator stages of kAccStride columns: 2, or 4 for the narrow store epilogue
   int mma_stats;    // 1: per-channel sums of the stored tile are accumulated by tcgen05.mma over the staging buffer
+  int col_narrow;   // narrow store epilogue (bn 32 or 64): 1 = statistics by a pass of the group over the staged tile
+                    // (like the 128-wide epilogue), 0 = warp-shuffle column sums in the epilogue
   unsigned long long* dbg;  // development: per-role clock64 timeline of CTA (0,0) (RXB_DBG_TIMELINE=1), else nullptr
 };
 
