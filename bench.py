@@ -329,6 +329,25 @@ def conv_kernel_rooflines(B, dev, peaks):
                      "algorithmic_bytes": bytes_, "tflops": tf, "tensor_frac": tf / peaks["bf16_tflops_sustained"],
                      "traffic": tr}
 
+    def smem_port(name, wavefronts_per_tile, tiles, breakdown):
+        """The 3x3 kernels are bound by the shared-memory port (128 B per clock and SM), not by HBM or the tensor
+        pipe: modelled 128-byte wavefronts per tile (tensor-core operand reads at
+        (A + B bytes)/128 per MMA, the in-place transforms, the epilogue's reads and writes, TMA writes and store reads;
+        the measured counterpart is l1tex__data_pipe_*_wavefronts_mem_shared in profiles/r02_ncu_summary_fused.txt)
+        against the cycles a tile takes at the nominal SM clock."""
+        try:
+            ms = out[name]["ms"]
+            cycles_per_tile = ms * 1e-3 * 1.965e9 / (tiles / 148.0)
+            out[name]["smem_port"] = {"bound": "shared-memory port (128 B/clk/SM)",
+                                      "model_wavefronts_per_tile": wavefronts_per_tile, "cycles_per_tile": cycles_per_tile,
+                                      "frac": wavefronts_per_tile / cycles_per_tile, "model": breakdown,
+                                      "sm_clock_mhz_assumed": 1965,
+                                      "note": "cycles at the NOMINAL clock: under sw_power_cap the SMs run slower (ncu: "
+                                              "525k cycles for a 307 us launch = 1.71 GHz), so the real fraction of the "
+                                              "port is ~15 % higher; ncu counts 2520 / 5035 wavefronts per tile"}
+        except Exception as e:          # informational: never takes the bench line down
+            out[name]["smem_port"] = {"error": repr(e)}
+
     g = torch.Generator(device=dev)
     g.manual_seed(5)
     rnd = lambda *sh: torch.randn(*sh, device=dev, generator=g).to(torch.bfloat16)
@@ -343,6 +362,10 @@ def conv_kernel_rooflines(B, dev, peaks):
     entry("fwd_1x1", ms, M * (224 + 128) * 2, 2.0 * M * 128 * 224, "dense layer 1x1, Cin 224")
     ms = timeit(lambda: ops.conv_fwd(Y, W3, Cin=128, scale=sc128, shift=sh128, out=X, c_off=224, pad=(1, 1), stats=True))
     entry("fwd_3x3", ms, M * (128 + 32) * 2, 2.0 * M * 32 * 128 * 9, "dense layer 3x3, 128 -> 32")
+    # x-merged 16x8 tiles with 14 valid columns: ceil(W/14) x H/8 tiles per image
+    smem_port("fwd_3x3", 1344 + 736 + 424 + 100, B * ((W + 13) // 14) * (H // 8),
+              {"mma_operands": "24 MMAs x (4 KB A + 3 KB B)/128 = 1344", "transform": "2 k-blocks x 160 rows x 128 B, read + write = 640 (+96 constants)",
+               "tma": "46 KB in + 7 KB out = 424", "epilogue": 100})
     # backward: 3x3 dgrad (dZ 32 -> dy2 128), 1x1 dgrad accumulating into the concat gradient, both wgrads
     dZ = rnd(B, H, W, 32)
     W3d = (torch.randn(3, 3, 128, 32, device=dev) * 0.03).to(torch.bfloat16)
@@ -353,6 +376,10 @@ def conv_kernel_rooflines(B, dev, peaks):
     entry("dgrad_3x3_bn_wgrad", ms, M * (32 + 128 + 128) * 2, 2.0 * M * 128 * 32 * 9 * 2,
           "the same launch also accumulating the 3x3 weight gradient (what the step runs; bound by shared-memory "
           "bandwidth of the tensor-core operand reads, DESIGN.md 5.3)")
+    smem_port("dgrad_3x3_bn_wgrad", 1152 + 1344 + 288 + 512 + 512 + 608, B * (W // 8) * (H // 16),
+              {"dgrad_mma_operands": "18 MMAs x 8 KB/128 = 1152", "wgrad_mma_operands": "24 MMAs x 7 KB/128 = 1344",
+               "statistics_mma": "8 x 4.5 KB/128 = 288", "transform": "32 KB read + 32 KB write = 512",
+               "epilogue": "32 KB read + 32 KB write = 512", "tma": "44 KB in + 32 KB store read = 608"})
     W1d = (torch.randn(1, 1, 224, 128, device=dev) * 0.05).to(torch.bfloat16)
     G = torch.zeros(B, H, W, 256, dtype=torch.bfloat16, device=dev)
     ms = timeit(lambda: ops.conv_dgrad_bn(dy2, W1d, X, sc224, sh224, 224, out_mode=ops.OUT_G_ACCUM, out=G))
