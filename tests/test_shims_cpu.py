@@ -406,6 +406,32 @@ def test_bench_host_helpers():
     assert json.loads(r.stdout) == {"ok": 1} and "NCCL version x" in r.stderr and "python print" in r.stderr
 
 
+def test_bench_traffic_model_follows_the_fused_backward(monkeypatch):
+    """bench.py's algorithmic-HBM-traffic model of one training step (the denominator of `hbm_frac_step`): the data flow
+    before the dense layers' weight gradients and gradient fix-ups moved into the data-gradient kernels moved 148.7 GB
+    per 128-image step, the shipped one 120.6 GB; the debug switches that restore the separate kernels
+    restore their bytes."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for k in ("RXB_DBG_NO_WGFUSE", "RXB_DBG_NO_WGFUSE3", "RXB_DBG_NO_FIXFOLD", "RXB_DBG_NO_BNTAIL"):
+        monkeypatch.delenv(k, raising=False)
+    t = bench.step_traffic_model(128)
+    assert t["conv_wgrad_1x1"] == 0 and t["conv_wgrad_3x3"] == 0
+    assert abs(sum(t.values()) / 1e9 - 120.6) < 0.1
+    assert abs(t["conv_dgrad_1x1"] / 1e9 - 42.26) < 0.01            # M*(128 + 3*Cin)*2 B over the 58 dense layers
+    for k in ("RXB_DBG_NO_WGFUSE", "RXB_DBG_NO_WGFUSE3"):
+        monkeypatch.setenv(k, "1")
+    t0 = bench.step_traffic_model(128)
+    assert abs(sum(t0.values()) / 1e9 - 148.66) < 0.1
+    assert abs(t0["conv_wgrad_1x1"] / 1e9 - 17.93) < 0.01 and abs(t0["grad_fixup"] / 1e9 - 5.84) < 0.01
+    # weak scaling: the model is linear in the batch
+    assert abs(sum(bench.step_traffic_model(64).values()) * 2 - sum(t0.values())) < 1e-3 * sum(t0.values())
+
+
 def test_test_shim_unwraps_dataparallel_and_default_device(monkeypatch, golden_dir):
     """main.py:94 hands test() a torch.nn.DataParallel wrapper: the shim calls the wrapped module itself (one process
     drives one GPU; the wrapper's scatter/replicate must not run).  Models built without a device follow the rank."""
